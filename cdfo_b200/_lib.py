@@ -1,0 +1,65 @@
+"""ctypes binding of libcdfo_b200.so (the C ABI declared in include/cdfo_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing, or a call returns a non-zero status, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcdfo_b200.so")
+
+OK = 0
+F32, F16, BF16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+class CdfoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(SO_PATH):
+            raise CdfoError(
+                "cdfo_b200: %s not found -- build it with `python cdfo_b200/csrc/build.py` "
+                "(there is no CPU or PyTorch fallback for this path)" % SO_PATH)
+        _lib = ctypes.CDLL(SO_PATH)
+        _lib.cdfo_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != OK:
+        msg = lib().cdfo_last_error().decode("utf-8", "replace")
+        # same exception classes as the reference raises at this boundary
+        # (TORCH_CHECK / AT_ERROR -> RuntimeError, deform_conv_cuda.cpp:493-511)
+        raise CdfoError("%s failed (status %d): %s" % (what or "cdfo call", rc, msg))
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise CdfoError("cdfo_b200: unsupported dtype %s" % t.dtype)
+
+
+def ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            # the reference raises NotImplementedError for CPU tensors (deform_conv.py:46-47,136-137)
+            raise NotImplementedError("cdfo_b200 ops are CUDA-only (got a %s tensor)" % t.device)

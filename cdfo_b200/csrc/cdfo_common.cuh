@@ -1,0 +1,48 @@
+// Shared helpers of the cdfo_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cdfo_b200.h"
+
+namespace cdfo {
+
+// thread-local message of the last failing call (cdfo_last_error)
+char *last_error_buf();
+int fail(int code, const char *fmt, ...);
+
+inline int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return CDFO_OK;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+inline int conv_out_size(int in, int pad, int dil, int k, int stride) {
+  return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+}  // namespace cdfo
+
+#define CDFO_REQUIRE(cond, code, ...)                 \
+  do {                                                \
+    if (!(cond)) return cdfo::fail(code, __VA_ARGS__); \
+  } while (0)

@@ -1,0 +1,88 @@
+/*
+ * cdfo_b200 -- C ABI of the B200 (sm_100a) hot path of CDFO's CVSR_V8 forward.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream
+ * (cudaStream_t passed as void*), allocates nothing, never throws, returns
+ * CDFO_OK (0) or a negative cdfo_status and leaves a message retrievable with
+ * cdfo_last_error().  Tensors are contiguous; "NCHW" = the reference's layout.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   cdfo_dcn_fwd            ops/dcn/src/deform_conv_cuda.cpp:486-564  modulated_deform_conv_cuda_forward
+ *                           ops/dcn/src/deform_conv_cuda.cpp:151-258  deform_conv_forward_cuda  (mask == NULL)
+ *                           bound by ops/dcn/deform_conv.py:52-57,144-148; also the semantics of
+ *                           torchvision.ops.deform_conv2d at arch/SIDECVSR_our.py:3352
+ *   cdfo_dcn_sample_index   floor() indices of deform_conv_cuda_kernel.cu:614-615 + :470-471 (parity probe)
+ *   cdfo_flow_warp_fwd      arch/SIDECVSR_our.py:3068-3099  flow_warp (bilinear, zeros, align_corners=True)
+ *   cdfo_mv2mvs             test_LD_37.py:83-105  mv2mvs  (+ permute at :160-161)
+ *   cdfo_mv_end_fix         test_LD_37.py:209-234 modify_mv_for_end_frames
+ *   cdfo_pack_c8 / unpack   layout adapters NCHW fp32 <-> channel-chunked bf16 used by the sm_100a kernels
+ *   cdfo_dcn_sm100_fwd      same contraction as cdfo_dcn_fwd at the model's hot shape (C=Co=64, 3x3, s=p=d=1,
+ *                           groups=1), tcgen05 implicit GEMM, bf16 operands, fp32 accumulate
+ *   cdfo_mv_offset_assemble arch/SIDECVSR_our.py:3341-3350 (chunk/cat/tanh/x10/+flow.flip/sigmoid)
+ *   cdfo_conv3x3_sm100_fwd  3x3 s1 p1 convolutions on the path (arch/SIDECVSR_our.py:3271-3275 conv_offset,
+ *                           :254-271 ResidualBlock_noBN, :4382 conv_expand_fea_r), tcgen05 implicit GEMM
+ *   cdfo_mdta_*             arch/SIDECVSR_our.py:3303-3337 / :3455-3492 (warp + fusion + dual MDTA)
+ *   cdfo_lra_*              arch/SIDECVSR_our.py:2179-2249 LLongRangAttention.forward
+ *   cdfo_tail_fwd           arch/SIDECVSR_our.py:4473-4480 (upconv/PixelShuffle/lrelu x2, conv_last, bilinear x4 skip)
+ */
+#ifndef CDFO_B200_H_
+#define CDFO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cdfo_status {
+  CDFO_OK = 0,
+  CDFO_ERR_SHAPE = -1,       /* inconsistent sizes (the reference raises AT_ERROR / TORCH_CHECK) */
+  CDFO_ERR_NULL = -2,        /* required pointer is NULL */
+  CDFO_ERR_CUDA = -3,        /* CUDA runtime / launch error (reference only printf()s these) */
+  CDFO_ERR_UNSUPPORTED = -4, /* valid request outside what this build implements */
+  CDFO_ERR_NO_DEVICE = -5    /* no sm_100 device visible */
+} cdfo_status;
+
+typedef enum cdfo_dtype { CDFO_F32 = 0, CDFO_F16 = 1, CDFO_BF16 = 2 } cdfo_dtype;
+
+/* Message of the last failing call on this thread ("" if none). */
+const char *cdfo_last_error(void);
+/* ABI version: major*1000 + minor. */
+int cdfo_version(void);
+/* 1 if device `dev` is compute capability 10.x, 0 otherwise, <0 on CUDA error. */
+int cdfo_device_ok(int dev);
+
+/* ---- A6/A7: deformable convolution forward, reference semantics, any shape ----
+ * x [B,C,H,W], offset [B,dg*2*kh*kw,Ho,Wo], mask [B,dg*kh*kw,Ho,Wo] or NULL (DCNv1),
+ * weight [Co,C/groups,kh,kw], bias [Co] or NULL, y [B,Co,Ho,Wo] (overwritten).
+ * dtype applies to x/offset/mask/weight/bias/y alike (fp32 accumulate). */
+int cdfo_dcn_fwd(const void *x, const void *offset, const void *mask, const void *weight,
+                 const void *bias, void *y, int B, int C, int H, int W, int Co, int kh, int kw,
+                 int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                 int groups, int dg, int dtype, void *stream);
+
+/* Integer sample indices (floor(h_im), floor(w_im)) per (b, g*kh*kw+tap, ho, wo): idx int32 [B,dg*kh*kw,Ho,Wo,2].
+ * offset fp32. */
+int cdfo_dcn_sample_index(const float *offset, int32_t *idx, int B, int H, int W, int kh, int kw,
+                          int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                          int dg, void *stream);
+
+/* ---- A3: flow_warp. x [B,C,H,W] fp32, flow [B,2,H,W] fp32 (channel 0 = x, 1 = y: the layout the model holds
+ * before its permute, arch/SIDECVSR_our.py:3304,3456), y [B,C,H,W]; idx int32 [B,H,W,2]=(iy_nw,ix_nw) or NULL. */
+int cdfo_flow_warp_fwd(const float *x, const float *flow, float *y, int B, int C, int H, int W,
+                       int32_t *idx, void *stream);
+
+/* ---- A1: mv [H,W,3] (mv_a, mv_b, refdist) int8 or int32 -> flows fp32 [7,2,H,W] (already permuted). ---- */
+int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H, int W, void *stream);
+/* ---- A2: in-place end-of-sequence fix-up on flows [B,7,2,H,W]; frame index i, max_idx as the caller passes. */
+int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void *stream);
+
+/* ---- layout adapters: NCHW fp32 <-> "c8" = [B, C/8, H, W, 8] bf16 (C % 8 == 0). ---- */
+int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H, int W, void *stream);
+int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDFO_B200_H_ */
