@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from torch.nn.modules.utils import _pair
 
-from . import deform_conv_cuda
+from . import config, dcn_sm100, deform_conv_cuda
 
 __all__ = ["deform_conv", "modulated_deform_conv", "deform_conv2d", "DeformConv", "DeformConvPack",
            "ModulatedDeformConv", "ModulatedDeformConvPack"]
@@ -53,12 +53,8 @@ def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1
 
 
 @torch.no_grad()
-def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                          deformable_groups=1):
-    """DCNv2 forward. Mirrors ModulatedDeformConvFunction.forward (ops/dcn/deform_conv.py:116-149):
-    scalar stride/padding/dilation, caller-side output allocation, CUDA only."""
-    if not input.is_cuda:
-        raise NotImplementedError
+def _generic_modulated(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups):
+    """fp32-exact catch-all kernel through the drop-in module (caller-side output allocation like the reference)."""
     with_bias = bias is not None
     kh, kw = weight.shape[2:4]
     oh = (input.size(2) + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
@@ -69,6 +65,27 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
         input, weight, bias if with_bias else input.new_empty(1), scratch, offset, mask, output, scratch,
         kh, kw, stride, stride, padding, padding, dilation, dilation, groups, deformable_groups, with_bias)
     return output
+
+
+@torch.no_grad()
+def _tensor_core_modulated(input, offset, mask, weight, bias, deformable_groups, mv=None):
+    """Hot shape: pack x (bf16, zero border), cached bf16 weights, one tcgen05 implicit-GEMM kernel."""
+    y = dcn_sm100.dcn_sm100(dcn_sm100.pack_q4p(input), offset.float(), mask.float(), dcn_sm100.pack_weight(weight),
+                            bias, mv=mv)
+    return y if input.dtype == torch.float32 else y.to(input.dtype)
+
+
+@torch.no_grad()
+def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                          deformable_groups=1):
+    """DCNv2 forward. Mirrors ModulatedDeformConvFunction.forward (ops/dcn/deform_conv.py:116-149):
+    scalar stride/padding/dilation, CUDA only.  The model's hot shape runs on the tensor cores."""
+    if not input.is_cuda:
+        raise NotImplementedError
+    if config.tensor_core and input.is_contiguous() and dcn_sm100.supported(
+            input, weight, _pair(stride), _pair(padding), _pair(dilation), groups, deformable_groups, mask):
+        return _tensor_core_modulated(input, offset, mask, weight, bias, deformable_groups)
+    return _generic_modulated(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
 
 
 @torch.no_grad()
@@ -88,6 +105,8 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
                            "2 * weight.size[2] * weight.size[3].")
     oh, ow = _out_hw((H, W), (kh, kw), (sh, sw), (ph, pw), (dh, dw))
     x = input.contiguous()
+    if config.tensor_core and dcn_sm100.supported(x, weight, (sh, sw), (ph, pw), (dh, dw), groups, dg, mask):
+        return _tensor_core_modulated(x, offset, mask, weight, bias, dg)
     y = x.new_empty((B, Co, oh, ow))
     rc = _lib.lib().cdfo_dcn_fwd(
         _lib.ptr(x), _lib.ptr(offset.contiguous()), _lib.ptr(None if mask is None else mask.contiguous()),

@@ -1,0 +1,68 @@
+"""Host side of the tcgen05 DCN kernel (cdfo_dcn_sm100_fwd): operand packing, weight cache, launch."""
+import weakref
+
+import torch
+
+from . import _lib
+
+_wcache = {}  # id(weight) -> (weakref, version, packed)
+
+
+def supported(x, weight, stride, padding, dilation, groups, deformable_groups, mask):
+    """The model's hot shape: 64 -> 64 channels, 3x3, stride = padding = dilation = 1, one weight group."""
+    return (mask is not None and x.is_cuda and x.dim() == 4 and x.size(1) == 64 and tuple(weight.shape) == (64, 64, 3, 3)
+            and tuple(stride) == (1, 1) and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1
+            and deformable_groups in (1, 2, 4, 8, 16) and x.dtype in (torch.float32, torch.bfloat16))
+
+
+@torch.no_grad()
+def pack_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[64,64,3,3] -> bf16 B operand [9, 8, 64, 8]; cached per parameter tensor / version counter."""
+    key = id(weight)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    w = weight.detach().contiguous().float()
+    out = torch.empty((9, 8, 64, 8), dtype=torch.bfloat16, device=w.device)
+    rc = _lib.lib().cdfo_dcn_sm100_pack_weight(_lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
+    _lib.check(rc, "cdfo_dcn_sm100_pack_weight")
+    _wcache[key] = (weakref.ref(weight), weight._version, out)
+    return out
+
+
+@torch.no_grad()
+def pack_q4p(x: torch.Tensor) -> torch.Tensor:
+    """NCHW fp32 -> [B, C/4, H+3, W+3, 4] bf16: quad-planar, zero border of 1 pixel before and 2 after."""
+    B, C, H, W = x.shape
+    x = x.contiguous().float()
+    out = torch.empty((B, C // 4, H + 3, W + 3, 4), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.lib().cdfo_pack_q4p(_lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
+    _lib.check(rc, "cdfo_pack_q4p")
+    return out
+
+
+@torch.no_grad()
+def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ctas=0):
+    """x_q4p [B,16,H+3,W+3,4] bf16; offset [B,dg*18,H,W], mask [B,dg*9,H,W] fp32 or fp16; mv [B,2,H,W] fp32 or None.
+    Returns [B,64,H,W] fp32 (out_c8=False) or [B,8,H,W,8] bf16."""
+    B, _, Hp, Wp, _ = x_q4p.shape
+    H, W = Hp - 3, Wp - 3
+    dg = offset.size(1) // 18
+    if offset.dtype != mask.dtype or offset.dtype not in (torch.float32, torch.float16):
+        raise _lib.CdfoError("dcn_sm100: offset/mask must both be fp32 or fp16")
+    if tuple(offset.shape) != (B, dg * 18, H, W) or tuple(mask.shape) != (B, dg * 9, H, W):
+        raise _lib.CdfoError("dcn_sm100: offset/mask shape mismatch")
+    offset, mask = offset.contiguous(), mask.contiguous()
+    if mv is not None:
+        mv = mv.contiguous().float()
+    if bias is not None:
+        bias = bias.detach().contiguous().float()
+    if out_c8:
+        y = torch.empty((B, 8, H, W, 8), dtype=torch.bfloat16, device=x_q4p.device)
+    else:
+        y = torch.empty((B, 64, H, W), dtype=torch.float32, device=x_q4p.device)
+    rc = _lib.lib().cdfo_dcn_sm100_fwd(
+        _lib.ptr(x_q4p), _lib.ptr(offset), _lib.ptr(mask), _lib.ptr(mv), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(y),
+        B, H, W, dg, _lib.dtype_code(offset), 1 if out_c8 else 0, int(num_ctas), _lib.stream_ptr(x_q4p.device))
+    _lib.check(rc, "cdfo_dcn_sm100_fwd")
+    return y

@@ -82,6 +82,26 @@ int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void 
 int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H, int W, void *stream);
 int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, void *stream);
 
+/* ---- A6 at the model's hot shape on the 5th-generation tensor cores (tcgen05, TMEM) ----
+ * C = Co = 64, 3x3, stride = pad = dil = 1, groups = 1, dg in {1,2,4,8,16}; bf16 operands, fp32 accumulate.
+ *   x_q4p  [B, 16, H+3, W+3, 4] bf16 : quad-planar input (4 channels = 8 bytes per pixel per plane) with a zero
+ *           border of 1 pixel before and 2 after in H and W (cdfo_pack_q4p)
+ *   offset [B, dg*18, H, W], mask [B, dg*9, H, W] : fp32 (off_dtype = CDFO_F32) or fp16 (CDFO_F16), reference layout
+ *   mv     [B, 2, H, W] fp32 (x, y) or NULL : decoded MV prior added to every offset pair inside the kernel
+ *           (dy += mv_y, dx += mv_x), i.e. offset + flow.flip(1).repeat(...) of arch/SIDECVSR_our.py:3347
+ *   wpk    73728 bytes from cdfo_dcn_sm100_pack_weight; bias [64] fp32 or NULL
+ *   y      out_mode 0: [B, 64, H, W] fp32 (reference layout); out_mode 1: [B, 8, H, W, 8] bf16
+ *   num_ctas <= 0: one persistent CTA per SM. */
+int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const void *mask, const float *mv,
+                       const void *wpk, const float *bias, void *y, int B, int H, int W, int dg,
+                       int off_dtype, int out_mode, int num_ctas, void *stream);
+/* weight [64, 64, 3, 3] fp32 (reference layout) -> bf16 B operand [tap, ci/8, co, 8]. */
+int cdfo_dcn_sm100_pack_weight(const float *w, void *wpk, void *stream);
+/* NCHW fp32 -> [B, C/4, H+3, W+3, 4] bf16 with the zero border described above (C % 4 == 0). */
+int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, void *stream);
+/* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
+int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,16 @@ from oracle import c_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def exact_fp32_path():
+    """These tests pin the fp32 catch-all kernel; the tcgen05 route has its own file (test_sm100_gpu.py)."""
+    import cdfo_b200
+    saved = cdfo_b200.config.tensor_core
+    cdfo_b200.config.tensor_core = False
+    yield
+    cdfo_b200.config.tensor_core = saved
+
+
 def _rand_case(case, seed=0):
     B, C, H, W, Co, k, s, p, d, groups, dg, use_mask, use_bias = case
     g = torch.Generator().manual_seed(seed)

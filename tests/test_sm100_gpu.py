@@ -1,0 +1,105 @@
+"""tcgen05 path: plumbing self-test, then the DCN implicit-GEMM kernel against the pinned C oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_umma_selftest(cuda_dev):
+    import cdfo_b200
+    L = cdfo_b200._lib
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 64, generator=g).to(torch.bfloat16)
+    Bm = torch.randn(64, 64, generator=g).to(torch.bfloat16)
+    ref = A.float() @ Bm.float().t()
+    Ad, Bd = A.to(cuda_dev), Bm.to(cuda_dev)
+    D = torch.zeros(128, 64, device=cuda_dev)
+    L.check(L.lib().cdfo_umma_selftest(L.ptr(Ad), L.ptr(Bd), L.ptr(D), 0, L.stream_ptr(cuda_dev)))
+    torch.cuda.synchronize()
+    err = (D.cpu() - ref).abs().max().item()
+    assert err < 1e-3, "tcgen05 descriptor convention is wrong: max err %g" % err
+
+
+def _case(B, H, W, dg, seed, off_scale=3.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float()
+    offset = torch.randn(B, dg * 18, H, W, generator=g) * off_scale
+    mask = torch.rand(B, dg * 9, H, W, generator=g)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+    b = torch.randn(64, generator=g)
+    return x, offset, mask, wt, b
+
+
+@pytest.mark.parametrize("B,H,W,dg", [(1, 16, 24, 16), (2, 33, 47, 16), (1, 64, 64, 16), (1, 20, 20, 4), (3, 8, 8, 1)])
+def test_dcn_sm100_vs_oracle(cuda_dev, B, H, W, dg):
+    """x and W are pre-rounded to bf16 on both sides, so the only differences are the bf16 rounding of the
+    blended A operand (rel 2^-9 per term) and the accumulation order."""
+    from cdfo_b200 import dcn_sm100 as S
+    x, offset, mask, wt, b = _case(B, H, W, dg, seed=H * W + dg)
+    ref = O.dcn_forward(x.numpy(), offset.numpy(), mask.numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
+    d = lambda t: t.to(cuda_dev)
+    y = S.dcn_sm100(S.pack_q4p(d(x)), d(offset), d(mask), S.pack_weight(d(wt)), d(b))
+    err = np.abs(y.cpu().numpy() - ref).max()
+    scale = np.abs(ref).max()
+    print("dcn_sm100 B%d %dx%d dg%d: max err %.3g (max|ref| %.3g)" % (B, H, W, dg, err, scale))
+    assert err <= 4e-3 * scale
+
+
+def test_dcn_sm100_mv_prior_and_c8_output(cuda_dev):
+    """MV prior added in-kernel == offset + flow.flip(1).repeat(...) (arch/SIDECVSR_our.py:3347); c8 bf16 output."""
+    from cdfo_b200 import dcn_sm100 as S
+    B, H, W, dg = 1, 24, 40, 16
+    x, offset, mask, wt, b = _case(B, H, W, dg, seed=1)
+    g = torch.Generator().manual_seed(9)
+    flow = torch.randint(-64 * 3, 64 * 3, (B, 2, H, W), generator=g).float() / 128.0
+    full = offset + flow.flip(1).repeat(1, dg * 9, 1, 1)
+    ref = O.dcn_forward(x.numpy(), full.numpy(), mask.numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
+    d = lambda t: t.to(cuda_dev)
+    xc = S.pack_q4p(d(x))
+    y = S.dcn_sm100(xc, d(offset), d(mask), S.pack_weight(d(wt)), d(b), mv=d(flow))
+    y_full = S.dcn_sm100(xc, d(full), d(mask), S.pack_weight(d(wt)), d(b))
+    assert torch.equal(y, y_full)          # same fp32 op order as the reference's offset assembly -> identical
+    assert np.abs(y.cpu().numpy() - ref).max() <= 4e-3 * np.abs(ref).max()
+    y8 = S.dcn_sm100(xc, d(offset), d(mask), S.pack_weight(d(wt)), d(b), mv=d(flow), out_c8=True)
+    y8_nchw = y8.permute(0, 1, 4, 2, 3).reshape(B, 64, H, W).float()
+    assert (y8_nchw - y.to(torch.bfloat16).float()).abs().max().item() == 0.0
+
+
+def test_dcn_sm100_fp16_offsets_and_borders(cuda_dev):
+    from cdfo_b200 import dcn_sm100 as S
+    B, H, W, dg = 1, 17, 29, 16
+    x, offset, mask, wt, b = _case(B, H, W, dg, seed=2, off_scale=12.0)   # many samples leave the frame
+    offset[:, ::3] = torch.round(offset[:, ::3])
+    offset[0, 5] = 1e4
+    offset[0, 6] = float("nan")
+    off16, m16 = offset.half(), mask.half()
+    ref = O.dcn_forward(x.numpy(), off16.float().numpy(), m16.float().numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
+    d = lambda t: t.to(cuda_dev)
+    y = S.dcn_sm100(S.pack_q4p(d(x)), d(off16), d(m16), S.pack_weight(d(wt)), d(b))
+    assert np.isfinite(y.cpu().numpy()).all()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 4e-3 * np.abs(ref).max()
+
+
+def test_dcn_sm100_full_size_linearity(cuda_dev):
+    """BASELINE config c3 size (272x480): size-independent properties instead of the (slow) oracle --
+    linearity in x, zero offsets + mask 1 == plain convolution, and agreement with the generic fp32 kernel."""
+    import cdfo_b200
+    from cdfo_b200 import dcn_sm100 as S
+    B, H, W, dg = 1, 272, 480, 16
+    g = torch.Generator().manual_seed(4)
+    x1 = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float().to(cuda_dev)
+    offset = (torch.randn(B, dg * 18, H, W, generator=g) * 2.0).to(cuda_dev)
+    mask = torch.rand(B, dg * 9, H, W, generator=g).to(cuda_dev)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float().to(cuda_dev)
+    wpk = S.pack_weight(wt)
+    y1 = S.dcn_sm100(S.pack_q4p(x1), offset, mask, wpk)
+    y2 = S.dcn_sm100(S.pack_q4p(2.0 * x1), offset, mask, wpk)
+    assert (y2 - 2.0 * y1).abs().max().item() == 0.0                 # scaling by 2 is exact in bf16/fp32
+    gen = cdfo_b200.dcn._generic_modulated(x1, offset, mask, wt, None, 1, 1, 1, 1, dg)
+    assert (y1 - gen).abs().max().item() <= 4e-3 * gen.abs().max().item()
+    y0 = S.dcn_sm100(S.pack_q4p(x1), torch.zeros_like(offset), torch.ones_like(mask), wpk)
+    conv = torch.nn.functional.conv2d(x1, wt, None, 1, 1)
+    assert (y0 - conv).abs().max().item() <= 2e-3 * conv.abs().max().item()

@@ -1,0 +1,78 @@
+"""Micro-benchmark of the DCN kernels at BASELINE config c3 (272x480 LR), B = 6 neighbour calls of one frame.
+Times with CUDA events on the launching stream; inputs (>= 450 MB of offsets/masks) exceed the 126 MB L2."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cdfo_b200  # noqa: E402
+from cdfo_b200 import dcn_sm100 as S  # noqa: E402
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=6)
+    ap.add_argument("--H", type=int, default=272)
+    ap.add_argument("--W", type=int, default=480)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--smooth", type=int, default=1, help="block-constant MV-like offsets (1) or i.i.d. random (0)")
+    ap.add_argument("--skip-baselines", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    B, H, W, dg = a.B, a.H, a.W, 16
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(B, 64, H, W, device=dev, generator=g)
+    if a.smooth:
+        mvb = torch.randint(-192, 192, (B, 2, H // 8, W // 8), device=dev, generator=g).float() / 128.0
+        mv = torch.nn.functional.interpolate(mvb, scale_factor=8, mode="nearest")
+        offset = torch.randn(B, dg * 18, H, W, device=dev, generator=g) * 0.3 + mv.flip(1).repeat(1, dg * 9, 1, 1)
+    else:
+        offset = torch.randn(B, dg * 18, H, W, device=dev, generator=g) * 4.0
+    mask = torch.rand(B, dg * 9, H, W, device=dev, generator=g)
+    wt = torch.randn(64, 64, 3, 3, device=dev, generator=g) * 0.05
+    bias = torch.randn(64, device=dev, generator=g)
+    xc = S.pack_q4p(x)
+    wpk = S.pack_weight(wt)
+    off16, m16 = offset.half(), mask.half()
+    P = H * W
+    res = {"B": B, "H": H, "W": W, "smooth": a.smooth}
+    t = timeit(lambda: S.dcn_sm100(xc, offset, mask, wpk, bias, num_ctas=a.ctas), a.iters)
+    res["sm100_f32off_us"] = t
+    res["sm100_f32off_GBs_fp32io_2240"] = 2240.0 * P * B / t / 1e3
+    t = timeit(lambda: S.dcn_sm100(xc, off16, m16, wpk, bias, out_c8=True, num_ctas=a.ctas), a.iters)
+    res["sm100_f16off_c8out_us"] = t
+    res["sm100_f16off_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
+    res["pack_q4p_us"] = timeit(lambda: S.pack_q4p(x), a.iters)
+    if not a.skip_baselines:
+        cdfo_b200.config.tensor_core = False
+        res["generic_fp32_us"] = timeit(
+            lambda: cdfo_b200.modulated_deform_conv(x, offset, mask, wt, bias, 1, 1, 1, 1, dg), 5, 1)
+        cdfo_b200.config.tensor_core = True
+        try:
+            import torchvision
+            res["torchvision_cuda_fp32_us"] = timeit(
+                lambda: torchvision.ops.deform_conv2d(x, offset, wt, bias, 1, 1, 1, mask), 5, 1)
+        except Exception as e:  # noqa: BLE001
+            res["torchvision_cuda_fp32_us"] = "unavailable: %s" % e
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
