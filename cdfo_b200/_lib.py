@@ -35,6 +35,21 @@ def lib():
     return _lib
 
 
+# number of CUDA kernels each C-ABI entry launches (for bench.py's gpu_launches claim)
+_LAUNCHES = {"cdfo_mv_end_fix": 3}
+launch_count = 0
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point, count its kernel launches, raise on a non-zero status."""
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != OK:
+        check(rc, name)
+    launch_count += _LAUNCHES.get(name, 1)
+    return rc
+
+
 def check(rc, what=""):
     if rc != OK:
         msg = lib().cdfo_last_error().decode("utf-8", "replace")

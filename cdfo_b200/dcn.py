@@ -108,11 +108,10 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
     if config.tensor_core and dcn_sm100.supported(x, weight, (sh, sw), (ph, pw), (dh, dw), groups, dg, mask):
         return _tensor_core_modulated(x, offset, mask, weight, bias, dg)
     y = x.new_empty((B, Co, oh, ow))
-    rc = _lib.lib().cdfo_dcn_fwd(
+    _lib.call("cdfo_dcn_fwd", 
         _lib.ptr(x), _lib.ptr(offset.contiguous()), _lib.ptr(None if mask is None else mask.contiguous()),
         _lib.ptr(weight.contiguous()), _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(y),
         B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, groups, dg, _lib.dtype_code(x), _lib.stream_ptr(x.device))
-    _lib.check(rc, "deform_conv2d")
     return y
 
 

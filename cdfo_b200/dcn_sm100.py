@@ -7,6 +7,10 @@ from . import _lib
 
 _wcache = {}  # id(weight) -> (weakref, version, packed)
 
+# When a list, every dcn_sm100() launch appends (start_event, end_event, pixels) recorded on the launching
+# stream: bench.py reads the kernel's live duration from these for its roofline line.
+event_log = None
+
 
 def supported(x, weight, stride, padding, dilation, groups, deformable_groups, mask):
     """The model's hot shape: 64 -> 64 channels, 3x3, stride = padding = dilation = 1, one weight group."""
@@ -24,8 +28,7 @@ def pack_weight(weight: torch.Tensor) -> torch.Tensor:
         return hit[2]
     w = weight.detach().contiguous().float()
     out = torch.empty((9, 8, 64, 8), dtype=torch.bfloat16, device=w.device)
-    rc = _lib.lib().cdfo_dcn_sm100_pack_weight(_lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
-    _lib.check(rc, "cdfo_dcn_sm100_pack_weight")
+    _lib.call("cdfo_dcn_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
     _wcache[key] = (weakref.ref(weight), weight._version, out)
     return out
 
@@ -36,8 +39,7 @@ def pack_q4p(x: torch.Tensor) -> torch.Tensor:
     B, C, H, W = x.shape
     x = x.contiguous().float()
     out = torch.empty((B, C // 4, H + 3, W + 3, 4), dtype=torch.bfloat16, device=x.device)
-    rc = _lib.lib().cdfo_pack_q4p(_lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
-    _lib.check(rc, "cdfo_pack_q4p")
+    _lib.call("cdfo_pack_q4p", _lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
     return out
 
 
@@ -61,8 +63,14 @@ def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ct
         y = torch.empty((B, 8, H, W, 8), dtype=torch.bfloat16, device=x_q4p.device)
     else:
         y = torch.empty((B, 64, H, W), dtype=torch.float32, device=x_q4p.device)
-    rc = _lib.lib().cdfo_dcn_sm100_fwd(
+    ev = None
+    if event_log is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.call("cdfo_dcn_sm100_fwd", 
         _lib.ptr(x_q4p), _lib.ptr(offset), _lib.ptr(mask), _lib.ptr(mv), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(y),
         B, H, W, dg, _lib.dtype_code(offset), 1 if out_c8 else 0, int(num_ctas), _lib.stream_ptr(x_q4p.device))
-    _lib.check(rc, "cdfo_dcn_sm100_fwd")
+    if ev is not None:
+        ev[1].record()
+        event_log.append((ev[0], ev[1], B * H * W, offset.element_size()))
     return y

@@ -57,11 +57,10 @@ def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, k
         raise RuntimeError("invalid spatial size of offset, expected height: %d width: %d, but got height: %d "
                            "width: %d" % (Ho, Wo, off.size(2), off.size(3)))
     out = output if output.is_contiguous() else torch.empty_like(output, memory_format=torch.contiguous_format)
-    rc = _lib.lib().cdfo_dcn_fwd(_lib.ptr(x), _lib.ptr(off), _lib.ptr(None), _lib.ptr(w), _lib.ptr(None),
+    _lib.call("cdfo_dcn_fwd", _lib.ptr(x), _lib.ptr(off), _lib.ptr(None), _lib.ptr(w), _lib.ptr(None),
                                  _lib.ptr(out), B, C, H, W, w.size(0), kH, kW, dH, dW, padH, padW,
                                  dilationH, dilationW, group, deformable_group, _lib.dtype_code(x),
                                  _lib.stream_ptr(x.device))
-    _lib.check(rc, "deform_conv_forward_cuda")
     if out is not output:
         output.copy_(out)
     return 1
@@ -88,11 +87,10 @@ def modulated_deform_conv_cuda_forward(input, weight, bias, ones, offset, mask, 
     b = bias.contiguous() if with_bias else None
     _same_dtype(input, off, msk, weight, b, output)
     out = output if output.is_contiguous() else torch.empty_like(output, memory_format=torch.contiguous_format)
-    rc = _lib.lib().cdfo_dcn_fwd(_lib.ptr(input), _lib.ptr(off), _lib.ptr(msk), _lib.ptr(weight), _lib.ptr(b),
+    _lib.call("cdfo_dcn_fwd", _lib.ptr(input), _lib.ptr(off), _lib.ptr(msk), _lib.ptr(weight), _lib.ptr(b),
                                  _lib.ptr(out), B, C, H, W, Co, kernel_h, kernel_w, stride_h, stride_w, pad_h,
                                  pad_w, dilation_h, dilation_w, group, deformable_group,
                                  _lib.dtype_code(input), _lib.stream_ptr(input.device))
-    _lib.check(rc, "modulated_deform_conv_cuda_forward")
     if out is not output:
         output.copy_(out)
 

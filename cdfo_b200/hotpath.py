@@ -1,0 +1,161 @@
+"""Execution of the hot-path modules of CVSR_V8 on the device.
+
+Each function takes the parameter-holder module (cdfo_b200/model.py) plus activations and runs the path the
+reference runs at the cited lines.  `backend` switches per stage between the hand-written kernels of
+libcdfo_b200 ("cuda") and an interim cuDNN/ATen composition ("aten") that exists only for stages whose
+fused kernel has not landed yet; DESIGN.md lists which stage is where.  Everything is CUDA-only.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib, dcn_sm100
+from .priors import flow_warp_chw
+
+# stage -> "cuda" | "aten"
+backend = {
+    "flow_warp": "cuda",
+    "dcn": "cuda",
+}
+
+
+def _lrelu(x):
+    return F.leaky_relu(x, 0.1)
+
+
+def _c(mod, x, **kw):
+    return F.conv2d(x, mod.weight, mod.bias, **kw)
+
+
+# ------------------------------------------------------------------------------------------ MDTA (A4 / A5 shared)
+def _mdta(q, k, v, temperature, heads):
+    b, c, h, w = q.shape
+    sh = (b, heads, c // heads, h * w)
+    q = F.normalize(q.reshape(sh), dim=-1)
+    k = F.normalize(k.reshape(sh), dim=-1)
+    attn = ((q @ k.transpose(-2, -1)) * temperature).softmax(dim=-1)
+    return (attn @ v.reshape(sh)).reshape(b, c, h, w)
+
+
+def _gate(seq, x):
+    y = x.mean(dim=(2, 3), keepdim=True)
+    y = F.relu(_c(seq._modules["0"], y))
+    return torch.sigmoid(_c(seq._modules["2"], y))
+
+
+def _warp(extra_feat, flow):
+    if backend["flow_warp"] == "cuda":
+        return flow_warp_chw(extra_feat.contiguous().float(), flow.contiguous().float())
+    raise _lib.CdfoError("flow_warp has no other backend")
+
+
+def _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused):
+    """warp + fusion_out + the two MDTA passes + project_out (arch:3304-3337 / :3456-3490). Returns (o1, o2)."""
+    warped = _warp(extra_feat, flow)
+    fo = mod.fusion_out._modules["0"] if relu_fused else mod.fusion_out
+    fused = F.conv2d(torch.cat([warped, pred_feat], 1), fo.weight)
+    if relu_fused:
+        fused = F.relu(fused)
+    t, hd = mod.temperature, mod.num_heads
+    o1 = F.conv2d(_mdta(x, fused, warped * _gate(mod.conv_du, warped), t, hd), mod.project_out.weight)
+    o2 = F.conv2d(_mdta(x, fused, pred_feat * _gate(mod.conv_du, pred_feat), t, hd), mod.project_out.weight)
+    return o1, o2
+
+
+def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
+    """DualAttAlignment.forward, arch:3455-3496 (flow [B,2,H,W])."""
+    o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=True)
+    out = F.relu(F.conv2d(torch.cat([o1 + o2, x], 1), mod.fusion_out._modules["0"].weight))
+    out = out * _gate(mod.CALayer.conv_du, out)
+    for rb in (mod.ResidualBlock, mod.ResidualBlock1):
+        out = out + _c(rb.conv2, F.relu(_c(rb.conv1, out, padding=1)), padding=1)
+    return out + x
+
+
+def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
+    """Learned offset residual and mask of MVDualAttAlignment WITHOUT the MV prior (arch:3339-3350 minus the
+    `+ flow.flip(1).repeat(...)` term, which the DCN kernel adds itself)."""
+    o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=False)
+    c0, c2 = mod.conv_offset._modules["0"], mod.conv_offset._modules["2"]
+    h1 = _c(c2, _lrelu(_c(c0, o1, padding=1)), padding=1)
+    h2 = _c(c2, _lrelu(_c(c0, o2, padding=1)), padding=1)
+    n = h1.size(1) // 3
+    mag = float(mod.max_residue_magnitude)
+    residual = mag * torch.tanh(h1[:, :2 * n]) + mag * torch.tanh(h2[:, :2 * n])
+    mask = torch.sigmoid(h1[:, 2 * n:] + h2[:, 2 * n:])
+    return residual, mask
+
+
+def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
+    """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior."""
+    residual, mask = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
+    xq = dcn_sm100.pack_q4p(x)
+    return dcn_sm100.dcn_sm100(xq, residual, mask, dcn_sm100.pack_weight(mod.weight), mod.bias, mv=flow)
+
+
+# ------------------------------------------------------------------------------------------ A8
+def _lra_mask(mod, res, u):
+    v = F.relu(_c(mod.conv_du_re._modules["0"], res))
+    v = F.relu(_c(mod.conv_du_re._modules["2"], v, stride=2, padding=2))
+    v = v.mean(dim=(2, 3), keepdim=True)
+    v = F.relu(_c(mod.conv_du_re2._modules["0"], v))     # [B,C,1,1]; bilinear upsampling of a 1x1 map is a broadcast
+    g = -torch.log(-torch.log(u))
+    r = torch.softmax(v + g, dim=1)
+    return (r >= 0.5).to(res.dtype)
+
+
+def long_range_attention(mod, res, x, u):
+    """LLongRangAttention.forward, arch:2179-2249, u = uniform noise of gumbel_softmax (arch:2169)."""
+    b, c, h, w = x.shape
+    mask = _lra_mask(mod, res, u)
+    qv = _c(mod.input_conv, x)
+    q, v = qv[:, :c], qv[:, c:]
+    wk, wb = mod.directW1_conv.weight, mod.directW1_conv.bias
+    hk, hb = mod.directH1_conv.weight, mod.directH1_conv.bias
+    q_r = (mask * q).permute(0, 2, 3, 1).reshape(b * h, 1, w, c)
+    v_r = v.permute(0, 2, 3, 1).reshape(b * h, 1, w, c)
+    sq = F.conv2d(q_r, wk, wb, padding=(0, 4)).squeeze(1)
+    v_r = F.conv2d(v_r, wk, wb, padding=(0, 4)).squeeze(1)
+    v_r = torch.softmax(sq @ sq.transpose(-2, -1), dim=-1) @ v_r
+    q_c = sq.reshape(b, h, w, c).permute(0, 2, 1, 3).reshape(b * w, 1, h, c)
+    q_c = F.conv2d(q_c, hk, hb, padding=(4, 0)).squeeze(1)
+    v_c = v_r.reshape(b, h, w, c).permute(0, 2, 1, 3).reshape(b * w, h, c)
+    long_out = torch.softmax(q_c @ q_c.transpose(-2, -1), dim=-1) @ v_c
+    long_out = long_out.reshape(b, w, h, c).permute(0, 3, 2, 1)
+    ws = mod.window_size
+
+    def windows(t):
+        return t.reshape(b, c, h // ws, ws, w // ws, ws).permute(0, 2, 4, 3, 5, 1).reshape(-1, ws * ws, c)
+
+    sq_w = windows((1.0 - mask) * q)
+    loc = torch.softmax(sq_w @ sq_w.transpose(-2, -1), dim=-1) @ windows(v)
+    loc = loc.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, h, w)
+    return _c(mod.fuse, torch.cat([long_out, loc], 1)) + x
+
+
+# ------------------------------------------------------------------------------------------ model-level stages
+def align_neighbours(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb):
+    """The body of the reference's neighbour loop (arch:4445-4456) for all six neighbours at once.
+    Batch index = n * B + b (neighbour-major); `center` [B,64,H,W] is shared by the six."""
+    ufs_prior = _c(model.conv_expand_ufs, ufs_nb, padding=1)
+    rms_prior = _c(model.conv_expand_rms, rms_nb, padding=1)
+    x_n = long_range_attention(model.RDAB, rms_prior, fea_nb + rms_prior, u_nb)
+    fea_i = _c(model.conv_expand_fea_r, torch.cat([fea_nb, x_n], 1), padding=1)
+    reps = fea_nb.size(0) // center.size(0)
+    center_rep = center.repeat(reps, 1, 1, 1)
+    return model.MV_deform_align(center_rep, fea_i, ufs_prior, mv_nb)
+
+
+def temporal_fusion(model, aligned, center, B):
+    """stack + tsa_fusion 1x1 + lrelu, arch:4463-4466. aligned [6B,64,H,W] neighbour-major."""
+    _, c, h, w = aligned.shape
+    a = aligned.view(6, B, c, h, w)
+    stacked = torch.cat([a[0], a[1], a[2], center, a[3], a[4], a[5]], dim=1)   # [B, 448, H, W], frame order 0..6
+    return _lrelu(_c(model.tsa_fusion, stacked))
+
+
+def tail(model, t, x_center):
+    """arch:4473-4480."""
+    out = _lrelu(F.pixel_shuffle(_c(model.upconv1, t), 2))
+    out = _lrelu(F.pixel_shuffle(_c(model.upconv2, out), 2))
+    out = _c(model.conv_last, out, padding=1)
+    return out + F.interpolate(x_center, scale_factor=4.0, mode="bilinear", align_corners=False)

@@ -23,9 +23,8 @@ def mv2mvs(mv: torch.Tensor) -> torch.Tensor:
     mv = mv.contiguous()
     H, W = mv.shape[:2]
     out = torch.empty((1, 7, 2, H, W), dtype=torch.float32, device=mv.device)
-    rc = _lib.lib().cdfo_mv2mvs(_lib.ptr(mv), int(mv.dtype == torch.int32), _lib.ptr(out), H, W,
+    _lib.call("cdfo_mv2mvs", _lib.ptr(mv), int(mv.dtype == torch.int32), _lib.ptr(out), H, W,
                                 _lib.stream_ptr(mv.device))
-    _lib.check(rc, "mv2mvs")
     return out
 
 
@@ -38,8 +37,7 @@ def modify_mv_for_end_frames(i: int, mvs: torch.Tensor, max_idx: int) -> torch.T
     if not mvs.is_contiguous():
         raise RuntimeError("mvs has to be contiguous")
     B, _, _, H, W = mvs.shape
-    rc = _lib.lib().cdfo_mv_end_fix(_lib.ptr(mvs), B, H, W, int(i), int(max_idx), _lib.stream_ptr(mvs.device))
-    _lib.check(rc, "modify_mv_for_end_frames")
+    _lib.call("cdfo_mv_end_fix", _lib.ptr(mvs), B, H, W, int(i), int(max_idx), _lib.stream_ptr(mvs.device))
     return mvs
 
 
@@ -62,7 +60,6 @@ def flow_warp_chw(x, flow_chw, return_index=False):
     B, C, H, W = x.shape
     y = torch.empty_like(x)
     idx = torch.empty((B, H, W, 2), dtype=torch.int32, device=x.device) if return_index else None
-    rc = _lib.lib().cdfo_flow_warp_fwd(_lib.ptr(x), _lib.ptr(flow_chw), _lib.ptr(y), B, C, H, W, _lib.ptr(idx),
+    _lib.call("cdfo_flow_warp_fwd", _lib.ptr(x), _lib.ptr(flow_chw), _lib.ptr(y), B, C, H, W, _lib.ptr(idx),
                                        _lib.stream_ptr(x.device))
-    _lib.check(rc, "flow_warp")
     return (y, idx) if return_index else y

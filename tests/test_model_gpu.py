@@ -1,0 +1,114 @@
+"""GPU parity of the hot-path modules and of the whole CVSR_V8 forward against fixtures produced by the REAL
+reference (tests/golden), plus oracle comparisons at sizes the fixtures do not cover."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+from oracle import torch_ref
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (BASELINE.json north_star): max abs error <= 1e-2 on outputs in [0,1]; |dPSNR| <= 0.02 dB.
+TOL_ABS = 1e-2
+TOL_PSNR = 0.02
+
+
+def _model(variant, dev, lowp=None):
+    from cdfo_b200.model import CVSR_V8
+    m = CVSR_V8(alignment="dual_att" if variant == "O1" else "mv_dcn")
+    m.load_state_dict(G.seeded_weights(variant), strict=True)
+    m = m.to(dev).eval()
+    m.lowp = lowp
+    return m
+
+
+def _dev(d, dev):
+    return {k: v.to(dev) for k, v in d.items()}
+
+
+def test_module_long_range_attention(cuda_dev):
+    g = G.load("modules_golden.npz")
+    d = _dev(G.module_inputs(), cuda_dev)
+    m = _model("O1", cuda_dev)
+    out = m.RDAB(d["res"], d["x"], d["u"])
+    err = np.abs(out.cpu().numpy() - g["lra_out"]).max()
+    print("RDAB max err %.3g (max|ref| %.3g)" % (err, np.abs(g["lra_out"]).max()))
+    assert err <= 5e-3
+
+
+def test_module_dual_att_alignment(cuda_dev):
+    g = G.load("modules_golden.npz")
+    d = _dev(G.module_inputs(), cuda_dev)
+    m = _model("O1", cuda_dev)
+    out = m.MV_deform_align(d["x"], d["extra"], d["pred"], d["flow"])
+    err = np.abs(out.cpu().numpy() - g["dual_att_out"]).max()
+    print("DualAttAlignment max err %.3g (max|ref| %.3g)" % (err, np.abs(g["dual_att_out"]).max()))
+    assert err <= 5e-3
+
+
+def test_module_mv_dcn_alignment(cuda_dev):
+    from cdfo_b200 import hotpath
+    g = G.load("modules_golden.npz")
+    d = _dev(G.module_inputs(), cuda_dev)
+    m = _model("O2", cuda_dev)
+    res, msk = hotpath.mv_offset_fields(m.MV_deform_align, d["x"], d["extra"], d["pred"], d["flow"])
+    off = res + d["flow"].flip(1).repeat(1, 144, 1, 1)
+    e_off = np.abs(torch.cat([off[:, :18], off[:, -18:]], 1).cpu().numpy() - g["mv_offset_g0g15"]).max()
+    e_msk = np.abs(torch.cat([msk[:, :9], msk[:, -9:]], 1).cpu().numpy() - g["mv_mask_g0g15"]).max()
+    out = m.MV_deform_align(d["x"], d["extra"], d["pred"], d["flow"])
+    err = np.abs(out.cpu().numpy() - g["mv_dcn_out"]).max()
+    print("MVDualAttAlignment offset err %.3g mask err %.3g out err %.3g (max|ref| %.3g)"
+          % (e_off, e_msk, err, np.abs(g["mv_dcn_out"]).max()))
+    assert e_off <= 2e-2 and e_msk <= 2e-3 and err <= 5e-3
+
+
+def test_module_tail(cuda_dev):
+    from cdfo_b200 import hotpath
+    g = G.load("modules_golden.npz")
+    d = _dev(G.module_inputs(), cuda_dev)
+    m = _model("O1", cuda_dev)
+    out = hotpath.tail(m, d["trunk_out"], d["x_center"])
+    err = np.abs(out.cpu().numpy() - g["tail_out"]).max()
+    print("tail max err %.3g" % err)
+    assert err <= 2e-3
+
+
+@pytest.mark.parametrize("variant", ["O1", "O2"])
+@pytest.mark.parametrize("lowp", [None, torch.bfloat16])
+def test_full_model_vs_reference_golden(cuda_dev, variant, lowp):
+    """Config c1 of BASELINE.json (7 x 64x64 LR -> 256x256): first frame and a second frame through the cache."""
+    g = G.load("model_golden.npz")
+    (c0, m0, n0), (c1, m1, n1) = G.two_frames()
+    m = _model(variant, cuda_dev, lowp)
+    c0, c1 = _dev(c0, cuda_dev), _dev(c1, cuda_dev)
+    sr0, l1 = m(c0["x"], None, m0.to(cuda_dev), c0["pms"], c0["rms"], c0["ufs"], None, noise=n0)
+    sr1, _ = m(c1["x"], None, m1.to(cuda_dev), c1["pms"], c1["rms"], c1["ufs"], l1, noise=n1)
+    tgt_rng = np.random.default_rng(0)
+    for name, sr in (("sr0", sr0), ("sr1", sr1)):
+        ref = g["%s_%s" % (variant, name)]
+        out = sr.float().cpu().numpy()
+        err = np.abs(out - ref).max()
+        target = np.clip(ref + tgt_rng.normal(0, 0.02, ref.shape), 0, 1)   # synthetic HR ground truth, ~34 dB
+        dpsnr = abs(G.psnr(np.clip(out, 0, 1), target) - G.psnr(np.clip(ref, 0, 1), target))
+        print("CVSR_V8 %s lowp=%s %s: max abs err %.3g, dPSNR %.4f dB" % (variant, lowp, name, err, dpsnr))
+        assert err <= TOL_ABS and dpsnr <= TOL_PSNR
+
+
+def test_full_model_ragged_size_vs_oracle(cuda_dev):
+    """A size with a ragged last DCN tile (W = 40, not a multiple of 32), B = 2, against the torch oracle."""
+    from cdfo_b200 import synthetic
+    H, W, B = 24, 40, 2
+    clip = synthetic.make_clip(7, H, W, B)
+    from oracle import priors_ref
+    mvs = torch.stack([torch.from_numpy(priors_ref.mv2mvs_model_layout(clip["mv_l0"][b].numpy())[0]) for b in range(B)])
+    noise = synthetic.gumbel_uniforms(4, 3, 0, B, H, W)
+    sd = G.seeded_weights("O2")
+    with torch.no_grad():
+        ref, _ = torch_ref.cvsr_v8_forward(sd, clip["x"], mvs, clip["pms"], clip["rms"], clip["ufs"], None, noise, "O2")
+    m = _model("O2", cuda_dev)
+    c = _dev(clip, cuda_dev)
+    sr, _ = m(c["x"], None, mvs.to(cuda_dev), c["pms"], c["rms"], c["ufs"], None, noise=noise)
+    err = (sr.cpu() - ref).abs().max().item()
+    print("ragged O2 B=2 24x40: max abs err %.3g" % err)
+    assert err <= TOL_ABS
