@@ -32,6 +32,7 @@ def lib():
                 "(there is no CPU or PyTorch fallback for this path)" % SO_PATH)
         _lib = ctypes.CDLL(SO_PATH)
         _lib.cdfo_last_error.restype = ctypes.c_char_p
+        _lib.cdfo_conv3x3_sm100_weight_bytes.restype = ctypes.c_size_t
     return _lib
 
 

@@ -1,0 +1,346 @@
+// 3x3 / stride 1 / padding 1 convolution as a tcgen05 implicit GEMM (sm_100a), channel-chunked bf16 activations.
+//
+// Replaces the cuDNN calls behind the reference's nn.Conv2d(…, 3, 1, 1) layers on the hot path:
+//   conv_offset.0 (64->64) and conv_offset.2 (64->432) of MVDualAttAlignment   arch/SIDECVSR_our.py:3271-3275
+//   ResidualBlock_noBN.conv1/conv2 (64->64) of DualAttAlignment                arch/SIDECVSR_our.py:254-271, :3452-3453
+//   conv_expand_fea_r (128->64)                                                arch/SIDECVSR_our.py:4382, :4454
+// (and, as the "next" row, the trunk's 64->256 / 256->64 pairs, arch:378-406).
+//
+// D[128 px, NT co] = sum over (64-channel block kb, tap) of A_{kb,tap}[128 px, 64 ci] * W_{kb,tap}[NT co, 64 ci]^T
+//   * activations live in HBM as "c8" = [B][C/8][H][W][8] bf16.  One TMA 5-D box per (tile, kb) lands the
+//     (16+2) x (8+2) pixel halo of 64 channels in shared memory as [ci/8][18][10][8]: exactly the tcgen05
+//     canonical K-major layout (8 pixels x 16 bytes = one 128-byte core matrix), with the convolution's zero
+//     padding supplied by TMA out-of-bounds fill.  The A operand of tap (i, j) is the SAME shared memory at a
+//     byte offset of (i*10 + j)*16: no im2col, no data movement between taps (SBO = 160 B, LBO = 2880 B).
+//   * a CTA is persistent, owns one N tile (NT output channels) whose weights stay resident in shared memory,
+//     and walks 16x8-pixel M tiles; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+//     (tcgen05.ld -> +bias -> activation -> +residual -> bf16 c8 or fp32 NCHW); TMEM accumulator double buffered.
+#include <cuda.h>
+
+#include "cdfo_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cdfo {
+
+constexpr int kCvTileH = 16, kCvTileW = 8;                 // 128 output pixels
+constexpr int kCvHaloH = kCvTileH + 2, kCvHaloW = kCvTileW + 2;
+constexpr int kCvPlane = kCvHaloH * kCvHaloW * 16;         // 2880 B: one 8-channel chunk of the halo
+constexpr int kCvStageBytes = 8 * kCvPlane;                // 23040 B: 64 channels
+constexpr int kCvSbo = kCvHaloW * 16;                      // 160 B between 8-pixel rows of the tile
+constexpr int kCvThreads = 192;
+
+struct Conv3x3Params {
+  const uint8_t *wpk;   // [n_tiles][9 taps][Cin/8][NT][8] bf16
+  const float *bias;    // [Cout] or nullptr
+  const uint4 *resid;   // c8 bf16 [B][Cout/8][H][W][8] or nullptr: added after the activation
+  void *y;
+  int B, Cin, Cout, H, W;
+  int act;       // 0 none, 1 relu, 2 leaky relu 0.1
+  int out_mode;  // 0: NCHW fp32, 1: c8 bf16
+  int n_tiles, tiles_x, tiles_y, m_tiles;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t cv_pack_bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int NT, int kStages>
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Params p) {
+  constexpr int kAccCols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));  // per accumulator buffer
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int KB = p.Cin / 64;                    // 64-channel blocks
+  const int w_bytes = 9 * p.Cin * NT * 2;
+  uint8_t *wsm = smem;
+  uint8_t *asmem = smem + ((w_bytes + 1023) & ~1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(asmem + kStages * kCvStageBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  float *bias_s = reinterpret_cast<float *>(bars + 18);
+  // barrier map: [0,kStages) A full, [4,4+kStages) A empty, 8/9 accumulator full, 10/11 accumulator empty, 12 weights
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
+  const int n0 = n_tile * NT;
+
+  for (int i = tid; i < NT; i += kCvThreads) bias_s[i] = (p.bias && n0 + i < p.Cout) ? p.bias[n0 + i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(BAR(s), 1);
+      ptx::mbar_init(BAR(4 + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(BAR(8 + a), 1);
+      ptx::mbar_init(BAR(10 + a), 128);
+    }
+    ptx::mbar_init(BAR(12), 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmap);
+    // resident weights of this N tile: 9 * KB pieces of NT x 64 bf16
+    ptx::mbar_arrive_expect_tx(BAR(12), w_bytes);
+    const int piece = NT * 64 * 2;
+    const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes;
+    for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * piece, src + (size_t)i * piece, piece, BAR(12));
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    int stage = 0, phase = 0;
+    for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+      const int b = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - b * p.tiles_x * p.tiles_y;
+      const int h0 = (r / p.tiles_x) * kCvTileH, w0 = (r % p.tiles_x) * kCvTileW;
+      for (int kb = 0; kb < KB; ++kb) {
+        if (lane == 0) {
+          ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
+          ptx::mbar_arrive_expect_tx(BAR(stage), kCvStageBytes);
+          ptx::tma_load_5d(ptx::smem_u32(asmem) + stage * kCvStageBytes, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * 8, b);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = ptx::make_idesc_bf16(128, NT);
+    ptx::mbar_wait(BAR(12), 0);
+    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+      ptx::mbar_wait(BAR(10 + acc), acc_phase ^ 1);
+      ptx::tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(BAR(stage), phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = ptx::smem_u32(asmem) + stage * kCvStageBytes;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_tap = a0 + ((tap / 3) * kCvHaloW + (tap % 3)) * 16;
+            const uint32_t b_tap = ptx::smem_u32(wsm) + (tap * KB + kb) * (NT * 64 * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kCvPlane, kCvPlane, kCvSbo);
+              const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (NT * 16), NT * 16, 128);
+              ptx::umma_f16(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
+            }
+          }
+          ptx::umma_commit(BAR(4 + stage));
+          if (kb == KB - 1) ptx::umma_commit(BAR(8 + acc));
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int quarter = warp & 3;                 // TMEM lanes this warp may read
+    const int row = quarter * 32 + lane;          // tile pixel: ty = row / 8, tx = row % 8
+    const int ty = row >> 3, tx = row & 7;
+    const size_t HW = (size_t)p.H * p.W;
+    int acc = 0, acc_phase = 0;
+    for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+      const int b = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - b * p.tiles_x * p.tiles_y;
+      const int h = (r / p.tiles_x) * kCvTileH + ty, w = (r % p.tiles_x) * kCvTileW + tx;
+      const bool live = h < p.H && w < p.W;
+      const size_t pix = (size_t)h * p.W + w;
+      ptx::mbar_wait(BAR(8 + acc), acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0, rr);
+        ptx::tmem_ld_wait();
+        if (c0 + 16 >= NT) {  // last read of this accumulator buffer
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(BAR(10 + acc));
+        }
+        if (!live || n0 + c0 >= p.Cout) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float t = __uint_as_float(rr[i]) + bias_s[c0 + i];
+          if (p.act == 1) t = fmaxf(t, 0.f);
+          else if (p.act == 2) t = t > 0.f ? t : 0.1f * t;
+          v[i] = t;
+        }
+        if (p.resid) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint4 q = __ldg(p.resid + ((size_t)b * (p.Cout / 8) + (n0 + c0) / 8 + half) * HW + pix);
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[half * 8 + 2 * i] += __uint_as_float(qq[i] << 16);
+              v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.out_mode == 0) {
+          float *y = reinterpret_cast<float *>(p.y) + ((size_t)b * p.Cout + n0 + c0) * HW + pix;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[(size_t)i * HW] = v[i];
+        } else {
+          uint4 *y = reinterpret_cast<uint4 *>(p.y) + ((size_t)b * (p.Cout / 8) + (n0 + c0) / 8) * HW + pix;
+          y[0] = make_uint4(cv_pack_bf2(v[0], v[1]), cv_pack_bf2(v[2], v[3]), cv_pack_bf2(v[4], v[5]), cv_pack_bf2(v[6], v[7]));
+          y[HW] = make_uint4(cv_pack_bf2(v[8], v[9]), cv_pack_bf2(v[10], v[11]), cv_pack_bf2(v[12], v[13]),
+                             cv_pack_bf2(v[14], v[15]));
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// weight [Cout][Cin][3][3] fp32 -> [n_tile][tap][Cin/8][NT][8] bf16 (rows beyond Cout are zero)
+__global__ void conv3x3_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int Cin,
+                                           int NT, int n_tiles) {
+  const size_t total = (size_t)n_tiles * 9 * Cin * NT;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = e % 8;
+    const int n = (e / 8) % NT;
+    const int kc = (e / 8 / NT) % (Cin / 8);
+    const int tap = (e / 8 / NT / (Cin / 8)) % 9;
+    const int nt = e / 8 / NT / (Cin / 8) / 9;
+    const int co = nt * NT + n, ci = kc * 8 + j;
+    out[e] = __float2bfloat16_rn(co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// N-tile size used for a given Cout / Cin: the largest tile that divides Cout and whose weights (9 * Cin * NT bf16)
+// stay resident in shared memory next to the A stages.
+int conv3x3_ntile(int Cout, int Cin) {
+  const int budget = 168 * 1024;
+  const int cands[5] = {144, 128, 64, 32, 16};
+  for (int c = 0; c < 5; ++c) {
+    const int nt = cands[c];
+    if (9 * Cin * nt * 2 <= budget && Cout % nt == 0) return nt;
+  }
+  return 0;
+}
+
+template <int NT>
+static int launch_conv3x3(const CUtensorMap &tm, const Conv3x3Params &p, int grid, cudaStream_t s) {
+  constexpr int kStages = 2;
+  auto kern = conv3x3_sm100_kernel<NT, kStages>;
+  const int w_bytes = 9 * p.Cin * NT * 2;
+  const size_t smem = ((w_bytes + 1023) & ~1023) + kStages * kCvStageBytes + 18 * 8 + NT * 4 + 64;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(conv3x3_sm100<%d>, %zu): %s", NT, smem, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  kern<<<grid, kCvThreads, smem, s>>>(tm, p);
+  return check_launch("cdfo_conv3x3_sm100_fwd");
+}
+
+}  // namespace cdfo
+
+using namespace cdfo;
+
+extern "C" int cdfo_conv3x3_sm100_ntile(int Cout, int Cin) { return conv3x3_ntile(Cout, Cin); }
+
+extern "C" size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin) {
+  const int nt = conv3x3_ntile(Cout, Cin);
+  if (!nt) return 0;
+  return (size_t)ceil_div(Cout, nt) * 9 * Cin * nt * 2;
+}
+
+extern "C" int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream) {
+  CDFO_REQUIRE(w && wpk, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_pack_weight: NULL pointer");
+  const int nt = conv3x3_ntile(Cout, Cin);
+  CDFO_REQUIRE(nt && Cin % 64 == 0, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100: unsupported channels %d -> %d", Cin, Cout);
+  const int n_tiles = ceil_div(Cout, nt);
+  conv3x3_pack_weight_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16 *)wpk, Cout, Cin, nt, n_tiles);
+  return check_launch("cdfo_conv3x3_sm100_pack_weight");
+}
+
+extern "C" int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
+                                      int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream) {
+  CDFO_REQUIRE(x_c8 && wpk && y, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_sm100_fwd: bad shape");
+  CDFO_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, CDFO_ERR_UNSUPPORTED,
+               "cdfo_conv3x3_sm100_fwd: Cin must be a multiple of 64 and Cout of 16 (got %d -> %d)", Cin, Cout);
+  CDFO_REQUIRE(act >= 0 && act <= 2 && (out_mode == 0 || out_mode == 1), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: act/out_mode");
+  CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0, CDFO_ERR_SHAPE,
+               "cdfo_conv3x3_sm100_fwd: pointers must be 16-byte aligned");
+  const int nt = conv3x3_ntile(Cout, Cin);
+  CDFO_REQUIRE(nt, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: no N tile fits shared memory for %d -> %d", Cin, Cout);
+  EncodeTiledFn enc = encode_tiled_fn();
+  CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv3x3_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tm;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
+  const cuuint32_t box[5] = {8, kCvHaloW, kCvHaloH, 8, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(x_c8), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+  Conv3x3Params p;
+  p.wpk = (const uint8_t *)wpk; p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = y;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.act = act; p.out_mode = out_mode;
+  p.n_tiles = ceil_div(Cout, nt);
+  p.tiles_x = ceil_div(W, kCvTileW); p.tiles_y = ceil_div(H, kCvTileH);
+  const long long mt = (long long)B * p.tiles_x * p.tiles_y;
+  CDFO_REQUIRE(mt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: too many tiles");
+  p.m_tiles = (int)mt;
+  int groups = kNumSMs / p.n_tiles;             // CTAs per N tile
+  if (groups > p.m_tiles) groups = p.m_tiles;
+  const int grid = groups * p.n_tiles;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (nt) {
+    case 16: return launch_conv3x3<16>(tm, p, grid, s);
+    case 32: return launch_conv3x3<32>(tm, p, grid, s);
+    case 64: return launch_conv3x3<64>(tm, p, grid, s);
+    case 128: return launch_conv3x3<128>(tm, p, grid, s);
+    case 144: return launch_conv3x3<144>(tm, p, grid, s);
+  }
+  return fail(CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: N tile %d", nt);
+}

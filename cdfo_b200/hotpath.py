@@ -61,6 +61,7 @@ def _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused):
     return o1, o2
 
 
+@torch.no_grad()
 def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     """DualAttAlignment.forward, arch:3455-3496 (flow [B,2,H,W])."""
     o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=True)
@@ -71,6 +72,7 @@ def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     return out + x
 
 
+@torch.no_grad()
 def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     """Learned offset residual and mask of MVDualAttAlignment WITHOUT the MV prior (arch:3339-3350 minus the
     `+ flow.flip(1).repeat(...)` term, which the DCN kernel adds itself)."""
@@ -85,6 +87,7 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     return residual, mask
 
 
+@torch.no_grad()
 def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior."""
     residual, mask = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
@@ -103,6 +106,7 @@ def _lra_mask(mod, res, u):
     return (r >= 0.5).to(res.dtype)
 
 
+@torch.no_grad()
 def long_range_attention(mod, res, x, u):
     """LLongRangAttention.forward, arch:2179-2249, u = uniform noise of gumbel_softmax (arch:2169)."""
     b, c, h, w = x.shape
@@ -133,6 +137,7 @@ def long_range_attention(mod, res, x, u):
 
 
 # ------------------------------------------------------------------------------------------ model-level stages
+@torch.no_grad()
 def align_neighbours(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb):
     """The body of the reference's neighbour loop (arch:4445-4456) for all six neighbours at once.
     Batch index = n * B + b (neighbour-major); `center` [B,64,H,W] is shared by the six."""
@@ -145,6 +150,7 @@ def align_neighbours(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb):
     return model.MV_deform_align(center_rep, fea_i, ufs_prior, mv_nb)
 
 
+@torch.no_grad()
 def temporal_fusion(model, aligned, center, B):
     """stack + tsa_fusion 1x1 + lrelu, arch:4463-4466. aligned [6B,64,H,W] neighbour-major."""
     _, c, h, w = aligned.shape
@@ -153,6 +159,7 @@ def temporal_fusion(model, aligned, center, B):
     return _lrelu(_c(model.tsa_fusion, stacked))
 
 
+@torch.no_grad()
 def tail(model, t, x_center):
     """arch:4473-4480."""
     out = _lrelu(F.pixel_shuffle(_c(model.upconv1, t), 2))

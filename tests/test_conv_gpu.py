@@ -1,0 +1,43 @@
+"""tcgen05 3x3 convolution (TMA halo, implicit GEMM) against torch conv2d in fp32 on bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, Cin, Cout, H, W, act, resid
+    (1, 64, 64, 16, 8, 0, False),       # exactly one tile
+    (2, 64, 64, 33, 21, 1, True),       # ragged tiles, ReLU, residual
+    (1, 64, 432, 24, 40, 0, False),     # conv_offset.2: three N tiles of 144
+    (1, 128, 64, 24, 40, 2, False),     # conv_expand_fea_r: two 64-channel K blocks
+    (1, 64, 256, 20, 24, 2, False),     # trunk body.0: two N tiles of 128
+    (1, 256, 64, 20, 24, 0, True),      # trunk body.2: four K blocks, N tiles of 32
+    (1, 64, 48, 18, 10, 0, False),      # N tile of 16
+    (3, 64, 64, 64, 64, 0, False),      # many tiles per CTA (pipeline wrap-around)
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv3x3_sm100(cuda_dev, case):
+    from cdfo_b200 import conv
+    B, Cin, Cout, H, W, act, use_res = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    b = torch.randn(Cout, generator=g) * 0.1
+    r = torch.randn(B, Cout, H, W, generator=g).to(torch.bfloat16).float() if use_res else None
+    ref = F.conv2d(x, w, b, 1, 1)
+    ref = F.relu(ref) if act == 1 else (F.leaky_relu(ref, 0.1) if act == 2 else ref)
+    if use_res:
+        ref = ref + r
+    d = lambda t: None if t is None else t.to(cuda_dev)
+    x8 = conv.to_c8(d(x))
+    r8 = conv.to_c8(d(r)) if use_res else None
+    wd = d(w)
+    y = conv.conv3x3(x8, wd, d(b), act, r8, out_nchw=True)
+    err = (y.cpu() - ref).abs().max().item()
+    print("conv3x3 %s: max err %.3g (max|ref| %.3g)" % (case, err, ref.abs().max().item()))
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item())
+    y8 = conv.conv3x3(x8, wd, d(b), act, r8, out_nchw=False)
+    assert (conv.from_c8(y8).cpu() - ref).abs().max().item() <= 1.2e-2 * max(1.0, ref.abs().max().item())  # bf16 output rounding
