@@ -4,7 +4,7 @@ The compute lives in libcdfo_b200.so (hand-written CUDA behind the C ABI of
 include/cdfo_b200.h); this package is the thin host side that mirrors the
 reference's operator / module interfaces.  There is no CPU fallback.
 """
-from . import _lib, config  # noqa: F401
+from . import _lib, config, conv  # noqa: F401
 from . import deform_conv_cuda  # noqa: F401
 from .dcn import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack,  # noqa: F401
                   deform_conv, deform_conv2d, modulated_deform_conv)

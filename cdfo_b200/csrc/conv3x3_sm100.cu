@@ -37,6 +37,14 @@ struct Conv3x3Params {
   int B, Cin, Cout, H, W;
   int act;       // 0 none, 1 relu, 2 leaky relu 0.1
   int out_mode;  // 0: NCHW fp32, 1: c8 bf16
+  // epi 0: bias -> act -> +resid.
+  // Offset/mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3341-3350): output channels arrive permuted as triples
+  // (dy_k, dx_k, m_k), k = g*9 + tap, and leave as one fp16x4 "field" (dy, dx, m, 0) per (k, pixel): y [B][Cout/3][H][W] x 8 B
+  // epi 1: (mag*tanh(dy), mag*tanh(dx), m)                                   (first head evaluation)
+  // epi 2: (aux.dy + mag*tanh(dy), aux.dx + mag*tanh(dx), sigmoid(aux.m + m)) (second evaluation; aux = epi-1 output)
+  int epi;
+  float mag;
+  const uint2 *aux;
   int n_tiles, tiles_x, tiles_y, m_tiles;
 };
 
@@ -170,6 +178,58 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       const size_t pix = (size_t)h * p.W + w;
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
+      if (p.epi != 0) {
+        if constexpr (NT % 48 == 0) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < NT; c0 += 48) {
+            uint32_t r0[16], r1[16], r2[16];
+            const uint32_t ta = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0;
+            tmem_ld16(ta, r0);
+            tmem_ld16(ta + 16, r1);
+            tmem_ld16(ta + 32, r2);
+            ptx::tmem_ld_wait();
+            if (c0 + 48 >= NT) {
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(BAR(10 + acc));
+            }
+            if (!live) continue;
+            float v[48];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = __uint_as_float(r0[i]) + bias_s[c0 + i];
+              v[16 + i] = __uint_as_float(r1[i]) + bias_s[c0 + 16 + i];
+              v[32 + i] = __uint_as_float(r2[i]) + bias_s[c0 + 32 + i];
+            }
+            const size_t fidx = ((size_t)b * (p.Cout / 3) + (n0 + c0) / 3) * HW + pix;
+            uint2 prior[16];
+            if (p.epi == 2) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) prior[t] = __ldg(p.aux + fidx + (size_t)t * HW);
+            }
+            uint2 *y = reinterpret_cast<uint2 *>(p.y) + fidx;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              float dy, dx, m = v[3 * t + 2];
+              asm("tanh.approx.f32 %0, %1;" : "=f"(dy) : "f"(v[3 * t]));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(dx) : "f"(v[3 * t + 1]));
+              dy *= p.mag;
+              dx *= p.mag;
+              if (p.epi == 2) {
+                const float2 pd = __half22float2(*reinterpret_cast<const __half2 *>(&prior[t].x));
+                const float pm = __low2float(*reinterpret_cast<const __half2 *>(&prior[t].y));
+                dy += pd.x;                                       // offset_1 + offset_2 (arch:3347)
+                dx += pd.y;
+                m = __fdividef(1.f, 1.f + __expf(-(pm + m)));     // sigmoid(mask_1 + mask_2) (arch:3350)
+              }
+              const __half2 h0 = __floats2half2_rn(dy, dx), h1 = __floats2half2_rn(m, 0.f);
+              y[(size_t)t * HW] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+            }
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t rr[16];
@@ -301,14 +361,33 @@ extern "C" int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cou
   return check_launch("cdfo_conv3x3_sm100_pack_weight");
 }
 
+static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
+                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream);
+
 extern "C" int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                                       int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream) {
+  return conv3x3_run(x_c8, wpk, bias, resid_c8, y, B, Cin, Cout, H, W, act, out_mode, 0, 0.f, nullptr, stream);
+}
+
+extern "C" int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, const void *first,
+                                             void *out, int B, int Cin, int dg, int H, int W, float magnitude,
+                                             void *stream) {
+  CDFO_REQUIRE(dg > 0 && (dg * 27) % 144 == 0, CDFO_ERR_UNSUPPORTED,
+               "cdfo_mv_offset_head_sm100_fwd: deformable_groups * 27 must be a multiple of 144 (got dg = %d)", dg);
+  CDFO_REQUIRE(conv3x3_ntile(dg * 27, Cin) == 144, CDFO_ERR_UNSUPPORTED,
+               "cdfo_mv_offset_head_sm100_fwd: needs the 144-channel N tile (Cin = %d too large)", Cin);
+  CDFO_REQUIRE(((uintptr_t)out & 7) == 0 && ((uintptr_t)first & 7) == 0, CDFO_ERR_SHAPE, "cdfo_mv_offset_head_sm100_fwd: alignment");
+  return conv3x3_run(z_c8, wpk, bias, nullptr, out, B, Cin, dg * 27, H, W, 0, 0, first ? 2 : 1, magnitude, first, stream);
+}
+
+static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
+                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_sm100_fwd: bad shape");
   CDFO_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, CDFO_ERR_UNSUPPORTED,
                "cdfo_conv3x3_sm100_fwd: Cin must be a multiple of 64 and Cout of 16 (got %d -> %d)", Cin, Cout);
   CDFO_REQUIRE(act >= 0 && act <= 2 && (out_mode == 0 || out_mode == 1), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: act/out_mode");
-  CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0, CDFO_ERR_SHAPE,
+  CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & (epi ? 7 : 15)) == 0, CDFO_ERR_SHAPE,
                "cdfo_conv3x3_sm100_fwd: pointers must be 16-byte aligned");
   const int nt = conv3x3_ntile(Cout, Cin);
   CDFO_REQUIRE(nt, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: no N tile fits shared memory for %d -> %d", Cin, Cout);
@@ -326,6 +405,7 @@ extern "C" int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const f
   Conv3x3Params p;
   p.wpk = (const uint8_t *)wpk; p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = y;
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.act = act; p.out_mode = out_mode;
+  p.epi = epi; p.mag = mag; p.aux = (const uint2 *)aux;
   p.n_tiles = ceil_div(Cout, nt);
   p.tiles_x = ceil_div(W, kCvTileW); p.tiles_y = ceil_div(H, kCvTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;

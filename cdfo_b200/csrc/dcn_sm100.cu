@@ -44,10 +44,15 @@ struct DcnSm100Params {
   void *y;
   int B, H, W, dg, out_mode;
   int gshift;  // deformable group of channel quad q is q >> gshift
+  int x_batch;               // x holds x_batch samples; output sample b reads x[b % x_batch]
+  long long off_bstride, msk_bstride;  // elements between consecutive samples of offset / mask
   int tiles_x, tiles_per_img, num_tiles;
 };
 
 constexpr size_t dcn_sm100_smem_bytes() { return kWBytes + kStages * kABytes + 256 + 16 * 8 + 16; }
+
+// Tag for offset/mask given as packed fields [B][dg*9][H*W] x fp16x4 (dy, dx, mask, 0) -- what the fused head writes.
+struct FieldsH4 { uint2 v; };
 
 template <typename OffT> __device__ __forceinline__ float ld_stream(const OffT *p);
 template <> __device__ __forceinline__ float ld_stream<float>(const float *p) { return __ldcs(p); }
@@ -78,6 +83,7 @@ template <typename OffT, int kProdWarps>
 __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_sm100_kernel(const DcnSm100Params p) {
   constexpr int kProdThreads = kProdWarps * 32;
   constexpr int kQuads = 16 / (kProdThreads / kTileM);  // channel quads handled per thread per tap (4)
+  constexpr bool kPacked = sizeof(OffT) == sizeof(uint2);
   static_assert(kQuads == 4, "producer mapping assumes 512 producer threads");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *wsm = smem;
@@ -208,9 +214,9 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_sm100_ke
       const int h = tc.h0 + ty, w = tc.w0 + tx;
       const bool live = h < p.H && w < p.W;
       const int pixc = min(h, p.H - 1) * p.W + min(w, p.W - 1);  // ragged tiles: clamp the address, zero the mask
-      s.off = offset + (size_t)tc.b * p.dg * 18 * P + pixc;
-      s.msk = mask + (size_t)tc.b * p.dg * 9 * P + pixc;
-      s.x = p.x + ((size_t)tc.b * 16 + quad0) * plane_q + Wp + 1;  // + border shift
+      s.off = offset + (size_t)tc.b * p.off_bstride + pixc;
+      s.msk = mask + (size_t)tc.b * p.msk_bstride + pixc;
+      s.x = p.x + ((size_t)(tc.b % p.x_batch) * 16 + quad0) * plane_q + Wp + 1;  // + border shift
       s.hb = (float)(h - 1);
       s.wb = (float)(w - 1);
       s.live = live ? 1.f : 0.f;
@@ -221,10 +227,19 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_sm100_ke
     auto load_tap = [&](const PixState &s, int tap, float (&o)[kQuads * 3]) {
 #pragma unroll
       for (int qi = 0; qi < kQuads; ++qi) {
-        const OffT *po = s.off + goff[qi] + tap * 2 * P;
-        o[qi * 3 + 0] = ld_stream(po);
-        o[qi * 3 + 1] = ld_stream(po + P);
-        o[qi * 3 + 2] = ld_stream(s.msk + gmsk[qi] + tap * P);
+        if constexpr (kPacked) {
+          // one 8-byte load per (pixel, group, tap): lanes = consecutive pixels -> 256 contiguous bytes per warp
+          const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(s.off) + gmsk[qi] + tap * P);
+          const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+          o[qi * 3 + 0] = d.x;
+          o[qi * 3 + 1] = d.y;
+          o[qi * 3 + 2] = __low2float(*reinterpret_cast<const __half2 *>(&raw.y));
+        } else {
+          const OffT *po = s.off + goff[qi] + tap * 2 * P;
+          o[qi * 3 + 0] = ld_stream(po);
+          o[qi * 3 + 1] = ld_stream(po + P);
+          o[qi * 3 + 2] = ld_stream(s.msk + gmsk[qi] + tap * P);
+        }
       }
     };
 
@@ -363,8 +378,9 @@ static int launch_dcn_sm100(const DcnSm100Params &p, int grid, cudaStream_t s) {
 
 extern "C" int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const void *mask, const float *mv,
                                   const void *wpk, const float *bias, void *y, int B, int H, int W, int dg,
-                                  int off_dtype, int out_mode, int num_ctas, void *stream) {
-  CDFO_REQUIRE(x_q4p && offset && mask && wpk && y, CDFO_ERR_NULL, "cdfo_dcn_sm100_fwd: NULL pointer");
+                                  int off_dtype, int out_mode, int num_ctas, int x_batch, long long off_bstride,
+                                  long long msk_bstride, void *stream) {
+  CDFO_REQUIRE(x_q4p && offset && (mask || off_dtype == CDFO_FIELDS_F16X4) && wpk && y, CDFO_ERR_NULL, "cdfo_dcn_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_dcn_sm100_fwd: bad shape");
   CDFO_REQUIRE(dg == 1 || dg == 2 || dg == 4 || dg == 8 || dg == 16, CDFO_ERR_UNSUPPORTED,
                "cdfo_dcn_sm100_fwd: deformable groups must divide 16 (got %d)", dg);
@@ -374,11 +390,15 @@ extern "C" int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const v
   DcnSm100Params p;
   p.x = (const uint2 *)x_q4p; p.offset = offset; p.mask = mask; p.mv = mv; p.wpk = (const uint8_t *)wpk;
   p.bias = bias; p.y = y; p.B = B; p.H = H; p.W = W; p.dg = dg; p.out_mode = out_mode;
+  p.x_batch = x_batch > 0 ? x_batch : B;
+  p.off_bstride = off_bstride > 0 ? off_bstride : (long long)dg * 18 * H * W;
+  p.msk_bstride = msk_bstride > 0 ? msk_bstride : (long long)dg * 9 * H * W;
+  CDFO_REQUIRE(B % p.x_batch == 0, CDFO_ERR_SHAPE, "cdfo_dcn_sm100_fwd: B (%d) must be a multiple of x_batch (%d)", B, p.x_batch);
   p.gshift = 0;
   while ((16 >> p.gshift) > dg) ++p.gshift;  // quads per deformable group = 16 / dg
   p.tiles_x = ceil_div(W, kTileW);
   p.tiles_per_img = p.tiles_x * ceil_div(H, kTileH);
-  CDFO_REQUIRE((long long)B * dg * 18 * H * W < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_dcn_sm100_fwd: offset tensor too large for 32-bit indexing");
+  CDFO_REQUIRE((long long)dg * 18 * H * W < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_dcn_sm100_fwd: offset planes too large for 32-bit indexing");
   const long long nt = (long long)p.tiles_per_img * B;
   CDFO_REQUIRE(nt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_dcn_sm100_fwd: too many tiles");
   p.num_tiles = (int)nt;
@@ -387,5 +407,9 @@ extern "C" int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const v
   cudaStream_t s = (cudaStream_t)stream;
   if (off_dtype == CDFO_F32) return launch_dcn_sm100<float, 16>(p, grid, s);
   if (off_dtype == CDFO_F16) return launch_dcn_sm100<__half, 16>(p, grid, s);
-  return fail(CDFO_ERR_UNSUPPORTED, "cdfo_dcn_sm100_fwd: offset dtype must be fp32 or fp16");
+  if (off_dtype == CDFO_FIELDS_F16X4) {
+    if (off_bstride <= 0) p.off_bstride = (long long)dg * 9 * H * W;
+    return launch_dcn_sm100<FieldsH4, 16>(p, grid, s);
+  }
+  return fail(CDFO_ERR_UNSUPPORTED, "cdfo_dcn_sm100_fwd: offset dtype must be fp32, fp16 or packed fp16x4 fields");
 }

@@ -1,4 +1,5 @@
 """Host side of the tcgen05 DCN kernel (cdfo_dcn_sm100_fwd): operand packing, weight cache, launch."""
+import ctypes
 import weakref
 
 import torch
@@ -44,17 +45,34 @@ def pack_q4p(x: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
-def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ctas=0):
+def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ctas=0, fused_fields=None):
     """x_q4p [B,16,H+3,W+3,4] bf16; offset [B,dg*18,H,W], mask [B,dg*9,H,W] fp32 or fp16; mv [B,2,H,W] fp32 or None.
     Returns [B,64,H,W] fp32 (out_c8=False) or [B,8,H,W,8] bf16."""
-    B, _, Hp, Wp, _ = x_q4p.shape
+    xB, _, Hp, Wp, _ = x_q4p.shape
     H, W = Hp - 3, Wp - 3
+    if fused_fields is not None:
+        # packed fields [B, dg*9, H, W, 4] fp16 = (dy, dx, mask, 0) per (group*9 + tap, pixel): the fused head's output
+        if fused_fields.dtype != torch.float16 or not fused_fields.is_contiguous() or fused_fields.dim() != 5 or \
+                tuple(fused_fields.shape[2:]) != (H, W, 4):
+            raise _lib.CdfoError("dcn_sm100: fused_fields must be a contiguous fp16 [B, dg*9, H, W, 4] tensor")
+        B, dg = fused_fields.size(0), fused_fields.size(1) // 9
+        return _launch(x_q4p, fused_fields, None, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, xB, 0, 0, FIELDS_F16X4)
+    B = offset.size(0)
     dg = offset.size(1) // 18
     if offset.dtype != mask.dtype or offset.dtype not in (torch.float32, torch.float16):
         raise _lib.CdfoError("dcn_sm100: offset/mask must both be fp32 or fp16")
     if tuple(offset.shape) != (B, dg * 18, H, W) or tuple(mask.shape) != (B, dg * 9, H, W):
         raise _lib.CdfoError("dcn_sm100: offset/mask shape mismatch")
     offset, mask = offset.contiguous(), mask.contiguous()
+    return _launch(x_q4p, offset, mask, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, xB, 0, 0)
+
+
+FIELDS_F16X4 = 16  # CDFO_FIELDS_F16X4
+
+
+def _launch(x_q4p, offset, mask, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, xB, off_bs, msk_bs, off_code=None):
+    if B % xB:
+        raise _lib.CdfoError("dcn_sm100: batch %d is not a multiple of the x batch %d" % (B, xB))
     if mv is not None:
         mv = mv.contiguous().float()
     if bias is not None:
@@ -69,8 +87,9 @@ def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ct
         ev[0].record()
     _lib.call("cdfo_dcn_sm100_fwd", 
         _lib.ptr(x_q4p), _lib.ptr(offset), _lib.ptr(mask), _lib.ptr(mv), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(y),
-        B, H, W, dg, _lib.dtype_code(offset), 1 if out_c8 else 0, int(num_ctas), _lib.stream_ptr(x_q4p.device))
+        B, H, W, dg, _lib.dtype_code(offset) if off_code is None else off_code, 1 if out_c8 else 0, int(num_ctas), int(xB),
+        ctypes.c_longlong(off_bs), ctypes.c_longlong(msk_bs), _lib.stream_ptr(x_q4p.device))
     if ev is not None:
         ev[1].record()
-        event_log.append((ev[0], ev[1], B * H * W, offset.element_size()))
+        event_log.append((ev[0], ev[1], B * H * W, 8 if off_code == FIELDS_F16X4 else offset.element_size()))
     return y

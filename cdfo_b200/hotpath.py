@@ -5,10 +5,12 @@ reference runs at the cited lines.  `backend` switches per stage between the han
 libcdfo_b200 ("cuda") and an interim cuDNN/ATen composition ("aten") that exists only for stages whose
 fused kernel has not landed yet; DESIGN.md lists which stage is where.  Everything is CUDA-only.
 """
+import ctypes
+
 import torch
 import torch.nn.functional as F
 
-from . import _lib, dcn_sm100
+from . import _lib, conv, dcn_sm100
 from .priors import flow_warp_chw
 
 # stage -> "cuda" | "aten"
@@ -64,6 +66,7 @@ def _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused):
 @torch.no_grad()
 def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     """DualAttAlignment.forward, arch:3455-3496 (flow [B,2,H,W])."""
+    x = _expand_batch(x, extra_feat.size(0))
     o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=True)
     out = F.relu(F.conv2d(torch.cat([o1 + o2, x], 1), mod.fusion_out._modules["0"].weight))
     out = out * _gate(mod.CALayer.conv_du, out)
@@ -72,27 +75,69 @@ def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     return out + x
 
 
+def _expand_batch(x, B):
+    """x [xB, ...] shared by B = k * xB samples (sample b uses x[b % xB])."""
+    return x if x.size(0) == B else x.repeat(B // x.size(0), 1, 1, 1)
+
+
+_head_cache = {}
+
+
+def _head_weights(c2, dg):
+    """conv_offset[-1] with its output channels permuted into (dy_k, dx_k, m_k) triples, k = g*9 + tap
+    (reference channels 2k, 2k+1, dg*18 + k: the chunk/cat of arch:3341-3345), packed for the tcgen05 conv."""
+    key = id(c2.weight)
+    hit = _head_cache.get(key)
+    if hit is not None and hit[0] == (c2.weight._version, c2.bias._version):
+        return hit[1], hit[2]
+    k = torch.arange(dg * 9, device=c2.weight.device)
+    perm = torch.stack([2 * k, 2 * k + 1, dg * 18 + k], dim=1).reshape(-1)
+    w = c2.weight.detach().index_select(0, perm).contiguous()
+    wpk = conv.pack_weight(w)
+    bias = c2.bias.detach().index_select(0, perm).contiguous().float()
+    _head_cache[key] = ((c2.weight._version, c2.bias._version), wpk, bias, w)
+    return wpk, bias
+
+
 @torch.no_grad()
 def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     """Learned offset residual and mask of MVDualAttAlignment WITHOUT the MV prior (arch:3339-3350 minus the
-    `+ flow.flip(1).repeat(...)` term, which the DCN kernel adds itself)."""
-    o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=False)
+    `+ flow.flip(1).repeat(...)` term, which the DCN kernel adds itself), as packed fields
+    [B, dg*9, H, W, 4] fp16 = (10*tanh(dy1) + 10*tanh(dy2), same for dx, sigmoid(m1 + m2), 0) per k = g*9 + tap.
+    Both conv_offset layers run in the tcgen05 convolution kernel; tanh / sum / sigmoid are its epilogue."""
+    B = extra_feat.size(0)
+    o1, o2 = _dual_mdta(mod, _expand_batch(x, B), extra_feat, pred_feat, flow, relu_fused=False)
     c0, c2 = mod.conv_offset._modules["0"], mod.conv_offset._modules["2"]
-    h1 = _c(c2, _lrelu(_c(c0, o1, padding=1)), padding=1)
-    h2 = _c(c2, _lrelu(_c(c0, o2, padding=1)), padding=1)
-    n = h1.size(1) // 3
-    mag = float(mod.max_residue_magnitude)
-    residual = mag * torch.tanh(h1[:, :2 * n]) + mag * torch.tanh(h2[:, :2 * n])
-    mask = torch.sigmoid(h1[:, 2 * n:] + h2[:, 2 * n:])
-    return residual, mask
+    z = conv.conv3x3(conv.to_c8(torch.cat([o1, o2], 0)), c0.weight, c0.bias, conv.ACT_LRELU)   # [2B, 8, H, W, 8]
+    H, W = z.shape[2:4]
+    dg = mod.deformable_groups
+    wpk, bias = _head_weights(c2, dg)
+    first = torch.empty((B, dg * 9, H, W, 4), dtype=torch.float16, device=z.device)
+    fields = torch.empty_like(first)
+    args = (B, 64, dg, H, W, ctypes.c_float(float(mod.max_residue_magnitude)), _lib.stream_ptr(z.device))
+    _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[:B]), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(None),
+              _lib.ptr(first), *args)
+    _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[B:]), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(first),
+              _lib.ptr(fields), *args)
+    return fields
+
+
+def unpack_fields(fields):
+    """Packed fields -> (residual [B, dg*18, H, W], mask [B, dg*9, H, W]) fp32 in the reference's channel order."""
+    B, K, H, W, _ = fields.shape
+    f = fields.float()
+    residual = torch.stack([f[..., 0], f[..., 1]], dim=2).reshape(B, 2 * K, H, W)
+    return residual, f[..., 2].contiguous()
 
 
 @torch.no_grad()
 def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
-    """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior."""
-    residual, mask = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
+    """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior.
+    `x` may hold fewer samples than the other arguments (sample b uses x[b % x.size(0)]): the model's six
+    neighbour calls share the centre-frame feature (arch:4456)."""
+    fields = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
     xq = dcn_sm100.pack_q4p(x)
-    return dcn_sm100.dcn_sm100(xq, residual, mask, dcn_sm100.pack_weight(mod.weight), mod.bias, mv=flow)
+    return dcn_sm100.dcn_sm100(xq, None, None, dcn_sm100.pack_weight(mod.weight), mod.bias, mv=flow, fused_fields=fields)
 
 
 # ------------------------------------------------------------------------------------------ A8
@@ -144,10 +189,9 @@ def align_neighbours(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb):
     ufs_prior = _c(model.conv_expand_ufs, ufs_nb, padding=1)
     rms_prior = _c(model.conv_expand_rms, rms_nb, padding=1)
     x_n = long_range_attention(model.RDAB, rms_prior, fea_nb + rms_prior, u_nb)
-    fea_i = _c(model.conv_expand_fea_r, torch.cat([fea_nb, x_n], 1), padding=1)
-    reps = fea_nb.size(0) // center.size(0)
-    center_rep = center.repeat(reps, 1, 1, 1)
-    return model.MV_deform_align(center_rep, fea_i, ufs_prior, mv_nb)
+    fr = model.conv_expand_fea_r
+    fea_i = conv.conv3x3(conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
+    return model.MV_deform_align(center, fea_i, ufs_prior, mv_nb)
 
 
 @torch.no_grad()

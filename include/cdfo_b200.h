@@ -45,6 +45,9 @@ typedef enum cdfo_status {
 } cdfo_status;
 
 typedef enum cdfo_dtype { CDFO_F32 = 0, CDFO_F16 = 1, CDFO_BF16 = 2 } cdfo_dtype;
+/* offset/mask given to cdfo_dcn_sm100_fwd as packed fields [B, dg*9, H, W] x fp16x4 (dy, dx, mask, 0): `offset` points
+ * at them, `mask` is ignored. */
+#define CDFO_FIELDS_F16X4 16
 
 /* Message of the last failing call on this thread ("" if none). */
 const char *cdfo_last_error(void);
@@ -91,10 +94,15 @@ int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, 
  *           (dy += mv_y, dx += mv_x), i.e. offset + flow.flip(1).repeat(...) of arch/SIDECVSR_our.py:3347
  *   wpk    73728 bytes from cdfo_dcn_sm100_pack_weight; bias [64] fp32 or NULL
  *   y      out_mode 0: [B, 64, H, W] fp32 (reference layout); out_mode 1: [B, 8, H, W, 8] bf16
- *   num_ctas <= 0: one persistent CTA per SM. */
+ *   num_ctas <= 0: one persistent CTA per SM.
+ *   x_batch: x_q4p holds x_batch samples and output sample b samples x[b % x_batch] (<= 0: x_batch = B); the model's six
+ *           neighbour calls of a frame all sample the SAME centre-frame feature (arch/SIDECVSR_our.py:4456).
+ *   off_bstride / msk_bstride: elements between consecutive samples of offset / mask (<= 0: dense), so that both
+ *           can live in one [B, dg*27, H, W] buffer as cdfo_mv_offset_head_sm100_fwd writes them. */
 int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const void *mask, const float *mv,
                        const void *wpk, const float *bias, void *y, int B, int H, int W, int dg,
-                       int off_dtype, int out_mode, int num_ctas, void *stream);
+                       int off_dtype, int out_mode, int num_ctas, int x_batch, long long off_bstride,
+                       long long msk_bstride, void *stream);
 /* weight [64, 64, 3, 3] fp32 (reference layout) -> bf16 B operand [tap, ci/8, co, 8]. */
 int cdfo_dcn_sm100_pack_weight(const float *w, void *wpk, void *stream);
 /* NCHW fp32 -> [B, C/4, H+3, W+3, 4] bf16 with the zero border described above (C % 4 == 0). */
@@ -107,6 +115,16 @@ int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, 
  *   added after the activation; y: out_mode 0 = [B, Cout, H, W] fp32, 1 = [B, Cout/8, H, W, 8] bf16. */
 int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                            int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream);
+/* ---- offset / mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3274, :3339-3350) fused into the conv epilogue ----
+ * The caller packs conv_offset[-1] with its output channels permuted into triples (dy_k, dx_k, m_k), k = g*9 + tap
+ * (reference channels 2k, 2k+1, dg*18 + k).  out = "fields" [B, dg*9, H, W] x fp16x4 (dy, dx, m, 0):
+ *   first == NULL : (magnitude*tanh(dy), magnitude*tanh(dx), m)                                  (evaluation on out_1)
+ *   first != NULL : (first.dy + magnitude*tanh(dy), first.dx + magnitude*tanh(dx), sigmoid(first.m + m))
+ *                   (evaluation on out_2; first = the previous call's output) = offset_1 + offset_2 and the mask;
+ *   the MV prior (+ flow.flip(1).repeat) is added by cdfo_dcn_sm100_fwd (off_dtype = CDFO_FIELDS_F16X4).
+ *   z_c8 [B, Cin/8, H, W, 8] bf16. */
+int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, const void *first, void *out,
+                                  int B, int Cin, int dg, int H, int W, float magnitude, void *stream);
 int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream);
 size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin);
 int cdfo_conv3x3_sm100_ntile(int Cout, int Cin);

@@ -52,7 +52,8 @@ def test_module_mv_dcn_alignment(cuda_dev):
     g = G.load("modules_golden.npz")
     d = _dev(G.module_inputs(), cuda_dev)
     m = _model("O2", cuda_dev)
-    res, msk = hotpath.mv_offset_fields(m.MV_deform_align, d["x"], d["extra"], d["pred"], d["flow"])
+    fields = hotpath.mv_offset_fields(m.MV_deform_align, d["x"], d["extra"], d["pred"], d["flow"])
+    res, msk = hotpath.unpack_fields(fields)
     off = res + d["flow"].flip(1).repeat(1, 144, 1, 1)
     e_off = np.abs(torch.cat([off[:, :18], off[:, -18:]], 1).cpu().numpy() - g["mv_offset_g0g15"]).max()
     e_msk = np.abs(torch.cat([msk[:, :9], msk[:, -9:]], 1).cpu().numpy() - g["mv_mask_g0g15"]).max()

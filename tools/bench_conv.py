@@ -1,0 +1,49 @@
+"""Micro-benchmark: tcgen05 3x3 conv vs cuDNN (bf16 channels_last) at the model's shapes (c3 = 272x480)."""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cdfo_b200 import conv  # noqa: E402
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def main():
+    dev = torch.device("cuda:0")
+    H, W = 272, 480
+    out = []
+    for (B, Cin, Cout, h, w) in [(12, 64, 64, H, W), (12, 64, 432, H, W), (12, 128, 64, H, W), (2, 64, 256, H, W),
+                                 (2, 256, 64, H, W), (2, 64, 256, 2 * H, 2 * W), (2, 256, 64, 2 * H, 2 * W)]:
+        x = torch.randn(B, Cin, h, w, device=dev)
+        wt = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
+        b = torch.randn(Cout, device=dev)
+        x8 = conv.to_c8(x)
+        t_ours = timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU))
+        xcl = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wcl = wt.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        bb = b.to(torch.bfloat16)
+        t_cudnn = timeit(lambda: F.leaky_relu(F.conv2d(xcl, wcl, bb, 1, 1), 0.1))
+        flops = 2.0 * B * h * w * Cin * Cout * 9
+        out.append({"shape": [B, Cin, Cout, h, w], "ours_us": round(t_ours, 1), "ours_TFLOPs": round(flops / t_ours / 1e6, 1),
+                    "cudnn_bf16_us": round(t_cudnn, 1), "cudnn_TFLOPs": round(flops / t_cudnn / 1e6, 1)})
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()

@@ -51,16 +51,17 @@ def main():
         res["features_1frame"], _ = t(lambda: m._features(x1, x1))
         res["prior_convs"], (up, rp) = t(lambda: (hotpath._c(m.conv_expand_ufs, ufs_nb, padding=1), hotpath._c(m.conv_expand_rms, rms_nb, padding=1)))
         res["RDAB"], x_n = t(lambda: hotpath.long_range_attention(m.RDAB, rp, fea_nb + rp, u))
-        res["conv_expand_fea_r"], fea_i = t(lambda: hotpath._c(m.conv_expand_fea_r, torch.cat([fea_nb, x_n], 1), padding=1))
+        fr = m.conv_expand_fea_r
+        res["conv_expand_fea_r"], fea_i = t(lambda: cdfo_b200.conv.conv3x3(cdfo_b200.conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, 0, out_nchw=True))
         cr = center.repeat(6, 1, 1, 1)
         al = m.MV_deform_align
         relu = a.variant != "O2"
         res["align.dual_mdta"], (o1, o2) = t(lambda: hotpath._dual_mdta(al, cr, fea_i, up, mv, relu))
         if a.variant == "O2":
-            res["align.offset_fields_total"], (rsd, msk) = t(lambda: hotpath.mv_offset_fields(al, cr, fea_i, up, mv))
-            res["align.pack_q4p"], xq = t(lambda: cdfo_b200.dcn_sm100.pack_q4p(cr))
-            res["align.dcn_sm100"], aligned = t(lambda: cdfo_b200.dcn_sm100.dcn_sm100(xq, rsd, msk, cdfo_b200.dcn_sm100.pack_weight(al.weight), al.bias, mv=mv))
-        res["align.total"], aligned = t(lambda: al(cr, fea_i, up, mv))
+            res["align.offset_fields_total"], fields = t(lambda: hotpath.mv_offset_fields(al, center, fea_i, up, mv))
+            res["align.pack_q4p"], xq = t(lambda: cdfo_b200.dcn_sm100.pack_q4p(center))
+            res["align.dcn_sm100"], aligned = t(lambda: cdfo_b200.dcn_sm100.dcn_sm100(xq, None, None, cdfo_b200.dcn_sm100.pack_weight(al.weight), al.bias, mv=mv, fused_fields=fields))
+        res["align.total"], aligned = t(lambda: al(center, fea_i, up, mv))
         res["fusion"], fused = t(lambda: hotpath.temporal_fusion(m, aligned, center, S))
         res["trunk"], tr = t(lambda: m._trunk(fused))
         res["tail"], _ = t(lambda: hotpath.tail(m, tr, x1))
