@@ -33,11 +33,12 @@ def lib():
         _lib = ctypes.CDLL(SO_PATH)
         _lib.cdfo_last_error.restype = ctypes.c_char_p
         _lib.cdfo_conv3x3_sm100_weight_bytes.restype = ctypes.c_size_t
+        _lib.cdfo_lra_workspace_bytes.restype = ctypes.c_size_t
     return _lib
 
 
 # number of CUDA kernels each C-ABI entry launches (for bench.py's gpu_launches claim)
-_LAUNCHES = {"cdfo_mv_end_fix": 3}
+_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5}
 launch_count = 0
 
 

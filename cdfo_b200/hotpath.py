@@ -141,44 +141,47 @@ def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
 
 
 # ------------------------------------------------------------------------------------------ A8
-def _lra_mask(mod, res, u):
-    v = F.relu(_c(mod.conv_du_re._modules["0"], res))
-    v = F.relu(_c(mod.conv_du_re._modules["2"], v, stride=2, padding=2))
-    v = v.mean(dim=(2, 3), keepdim=True)
-    v = F.relu(_c(mod.conv_du_re2._modules["0"], v))     # [B,C,1,1]; bilinear upsampling of a 1x1 map is a broadcast
-    g = -torch.log(-torch.log(u))
-    r = torch.softmax(v + g, dim=1)
-    return (r >= 0.5).to(res.dtype)
+_lra_tables = {}
+
+
+def _lra_tap_tables(mod):
+    """kw[9], kh[9], K1[64], R[64,64] of csrc/lra.cu from directW1_conv / directH1_conv (cached per weight version)."""
+    key = (id(mod.directW1_conv.weight), mod.directW1_conv.weight._version, mod.directH1_conv.weight._version)
+    hit = _lra_tables.get(id(mod))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    kw = mod.directW1_conv.weight.detach().reshape(9).double()
+    kh = mod.directH1_conv.weight.detach().reshape(9).double()
+    c = torch.arange(64, device=kw.device)
+    tix = c.view(64, 1) - c.view(1, 64) + 4                 # tix[c_star][c] = tap index of a bump centred at c_star
+    tapm = torch.where((tix >= 0) & (tix <= 8), kw[tix.clamp(0, 8)], torch.zeros((), dtype=kw.dtype, device=kw.device))
+    k1 = tapm.sum(dim=1)                                     # K1[c_star]
+    r = tapm @ tapm.t()                                      # R[c1][c2]
+    tab = torch.cat([kw, kh, k1, r.reshape(-1)]).float().contiguous()
+    _lra_tables[id(mod)] = (key, tab)
+    return tab
 
 
 @torch.no_grad()
 def long_range_attention(mod, res, x, u):
-    """LLongRangAttention.forward, arch:2179-2249, u = uniform noise of gumbel_softmax (arch:2169)."""
-    b, c, h, w = x.shape
-    mask = _lra_mask(mod, res, u)
-    qv = _c(mod.input_conv, x)
-    q, v = qv[:, :c], qv[:, c:]
-    wk, wb = mod.directW1_conv.weight, mod.directW1_conv.bias
-    hk, hb = mod.directH1_conv.weight, mod.directH1_conv.bias
-    q_r = (mask * q).permute(0, 2, 3, 1).reshape(b * h, 1, w, c)
-    v_r = v.permute(0, 2, 3, 1).reshape(b * h, 1, w, c)
-    sq = F.conv2d(q_r, wk, wb, padding=(0, 4)).squeeze(1)
-    v_r = F.conv2d(v_r, wk, wb, padding=(0, 4)).squeeze(1)
-    v_r = torch.softmax(sq @ sq.transpose(-2, -1), dim=-1) @ v_r
-    q_c = sq.reshape(b, h, w, c).permute(0, 2, 1, 3).reshape(b * w, 1, h, c)
-    q_c = F.conv2d(q_c, hk, hb, padding=(4, 0)).squeeze(1)
-    v_c = v_r.reshape(b, h, w, c).permute(0, 2, 1, 3).reshape(b * w, h, c)
-    long_out = torch.softmax(q_c @ q_c.transpose(-2, -1), dim=-1) @ v_c
-    long_out = long_out.reshape(b, w, h, c).permute(0, 3, 2, 1)
-    ws = mod.window_size
-
-    def windows(t):
-        return t.reshape(b, c, h // ws, ws, w // ws, ws).permute(0, 2, 4, 3, 5, 1).reshape(-1, ws * ws, c)
-
-    sq_w = windows((1.0 - mask) * q)
-    loc = torch.softmax(sq_w @ sq_w.transpose(-2, -1), dim=-1) @ windows(v)
-    loc = loc.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, h, w)
-    return _c(mod.fuse, torch.cat([long_out, loc], 1)) + x
+    """LLongRangAttention.forward, arch:2179-2249, u = uniform noise of gumbel_softmax (arch:2169).
+    Mask logits (a global pooling of two small convolutions of the residual prior) and the 1x1 input_conv are
+    ATen/cuDNN calls; the mask, the row / column / window attentions and the fuse convolution are csrc/lra.cu."""
+    B, C, H, W = x.shape
+    v = F.relu(_c(mod.conv_du_re._modules["0"], res))
+    v = F.relu(_c(mod.conv_du_re._modules["2"], v, stride=2, padding=2))
+    v = v.mean(dim=(2, 3), keepdim=True)
+    vmax = F.relu(_c(mod.conv_du_re2._modules["0"], v)).reshape(B, C).contiguous()   # bilinear up of a 1x1 map = broadcast
+    x = x.contiguous()
+    qv = _c(mod.input_conv, x).contiguous()
+    out = torch.empty_like(x)
+    nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(_lra_tap_tables(mod)),
+              ctypes.c_float(float(mod.directW1_conv.bias)), ctypes.c_float(float(mod.directH1_conv.bias)),
+              _lib.ptr(mod.fuse.weight.detach().reshape(64, 128).contiguous()), _lib.ptr(mod.fuse.bias.detach().contiguous()),
+              _lib.ptr(out), _lib.ptr(ws), B, H, W, _lib.stream_ptr(x.device))
+    return out
 
 
 # ------------------------------------------------------------------------------------------ model-level stages

@@ -128,6 +128,18 @@ int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float
 int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream);
 size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin);
 int cdfo_conv3x3_sm100_ntile(int Cout, int Cin);
+/* ---- A8: LLongRangAttention.forward (arch/SIDECVSR_our.py:2179-2249) after its 1x1 input_conv and the pooled mask logits ----
+ *   qv     [B,128,H,W] fp32 = input_conv(x) (q = first 64 channels, v = last 64)          arch:2206,2211
+ *   u      [B,64,H,W]  fp32 uniform noise of gumbel_softmax (torch.rand_like, arch:2169)
+ *   vmax   [B,64]      fp32 = conv_du_re2(avg_pool(conv_du_re(res)))                        arch:2183-2185
+ *   x      [B,64,H,W]  fp32 residual input;  out [B,64,H,W] fp32 = fuse(cat[long, loc]) + x  arch:2246-2249
+ *   tables [9 + 9 + 64 + 4096] fp32: directW1_conv taps, directH1_conv taps, K1, R (see csrc/lra.cu); beta / bh their biases
+ *   fuse_w [64,128] fp32, fuse_b [64];  workspace: cdfo_lra_workspace_bytes(B, H, W) bytes;  H, W multiples of 8.
+ * No score tensor is materialised (the reference writes ~3.1 kB of fp32 scores per pixel and call). */
+int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *tables, float beta,
+                 float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B, int H, int W,
+                 void *stream);
+size_t cdfo_lra_workspace_bytes(int B, int H, int W);
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
 
