@@ -194,80 +194,174 @@ __global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ flash-style block
+// 256 threads compute, for a block of 64 queries against n_keys keys, softmax(Q K^T) V with an online softmax, fp32.
+// Q / K / V rows have 64 features, row stride kLd floats in shared memory.  Register tile 4 x 4 per thread:
+// thread (ty, tx) owns query rows {ty + 16 i} and key columns {tx + 16 j} of every 64 x 64 score tile, and query rows
+// {ty + 16 i} x channels {4 tx .. 4 tx + 3} of the output: 8 LDS.128 feed 64 FMAs (the v1 kernels were LDS-bound at 2:1).
+constexpr int kLd = 68;   // 68 % 32 == 4: eight consecutive rows hit distinct 16-byte bank groups
+
+// key_chunk(kb) must make *Kptr point at keys kb*64 .. kb*64+63 and rows [0, 64) of Vs hold their values (rows beyond
+// n_keys may hold anything finite: their probabilities are forced to 0), ending with a __syncthreads() if it wrote.
+template <typename LoadKV, typename Store>
+__device__ __forceinline__ void flash_block_fp32_kptr(const float *Qs, const float *const *Kptr, const float *Vs, float *Ps,
+                                                      int n_keys, LoadKV key_chunk, Store store) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[i][c] = 0.f;
+  }
+  const int n_chunks = (n_keys + 63) >> 6;
+  for (int kb = 0; kb < n_chunks; ++kb) {
+    key_chunk(kb);
+    const float *Ks = *Kptr;
+    float sacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) {
+      float4 a[4], bq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(Qs + (ty + 16 * i) * kLd + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bq[j] = *reinterpret_cast<const float4 *>(Ks + (tx + 16 * j) * kLd + k);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sacc[i][j] = fmaf(a[i].x, bq[j].x, sacc[i][j]);
+          sacc[i][j] = fmaf(a[i].y, bq[j].y, sacc[i][j]);
+          sacc[i][j] = fmaf(a[i].z, bq[j].z, sacc[i][j]);
+          sacc[i][j] = fmaf(a[i].w, bq[j].w, sacc[i][j]);
+        }
+    }
+    // online softmax: rows are shared by the 16 lanes with equal ty
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kb * 64 + tx + 16 * j >= n_keys) sacc[i][j] = -INFINITY;
+        mx = fmaxf(mx, sacc[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m_run[i], mx);
+      const float scale = expf(m_run[i] - m_new);   // exp(-inf) = 0 on the first chunk
+      m_run[i] = m_new;
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = expf(sacc[i][j] - m_new);
+        Ps[(ty + 16 * i) * kLd + tx + 16 * j] = pv;
+        ps += pv;
+      }
+      l_run[i] = l_run[i] * scale + ps;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[i][c] *= scale;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 4) {
+      float4 pr[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pr[i] = *reinterpret_cast<const float4 *>(Ps + (ty + 16 * i) * kLd + j);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) vv[jj] = *reinterpret_cast<const float4 *>(Vs + (j + jj) * kLd + 4 * tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pe[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          o[i][0] = fmaf(pe[jj], vv[jj].x, o[i][0]);
+          o[i][1] = fmaf(pe[jj], vv[jj].y, o[i][1]);
+          o[i][2] = fmaf(pe[jj], vv[jj].z, o[i][2]);
+          o[i][3] = fmaf(pe[jj], vv[jj].w, o[i][3]);
+        }
+      }
+    }
+    __syncthreads();   // Ps / Ks / Vs are rewritten by the next chunk
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float l = l_run[i];
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = 1.f / l;
+    store(ty + 16 * i, 4 * tx, make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ columns
 // CTA per (b, w): q_c[h] = bh + sum_t kh[t] sq[h+t-4] (zero rows outside the frame), sq[h'] = beta + bump(h').
+// Shared memory: Q for the whole column [Hp][kLd] (Hp = H rounded up to 64), one 64-row V chunk, one P tile.
 constexpr int kColThreads = 256;
 __global__ void __launch_bounds__(kColThreads) lra_col_kernel(const float *__restrict__ vrow_t, const uint8_t *__restrict__ midx,
                                                              const float *__restrict__ qsel, float *__restrict__ long_out,
                                                              LraTables t, int H, int W) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y, w = blockIdx.x;
   const int HW = H * W;
-  float *bufA = sm;               // [H][65]: sq, later V
-  float *Q = bufA + H * 65;       // [H][65]
-  float *pw = Q + H * 65;         // [8][H] per-warp probabilities
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Hp = (H + 63) & ~63;
+  float *Q = sm;                  // [Hp][kLd]
+  float *Vc = Q + Hp * kLd;       // [64][kLd]   (first used as scratch for sq)
+  float *Ps = Vc + 64 * kLd;      // [64][kLd]
+  float *sq = Ps + 64 * kLd;      // [H + 8][64]: sq rows -4 .. H+3 (zero outside the frame)
+  const int tid = threadIdx.x;
   float kh[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) kh[i] = t.kh[i];
 
-  for (int e = tid; e < H * 64; e += kColThreads) {   // sq[h][c] = beta + bump
-    const int h = e >> 6, c = e & 63;
-    const int cm = midx[(size_t)b * HW + h * W + w];
-    float v = t.beta;
-    if (cm != 255) {
-      const int ti = cm - c + 4;
-      if (ti >= 0 && ti <= 8) v = fmaf(__ldg(t.kw + ti), qsel[(size_t)b * HW + h * W + w], v);
+  for (int e = tid; e < (H + 8) * 64; e += kColThreads) {   // sq[h][c] = beta + bump, zero padding rows
+    const int h = (e >> 6) - 4, c = e & 63;
+    float v = 0.f;
+    if (h >= 0 && h < H) {
+      v = t.beta;
+      const int cm = midx[(size_t)b * HW + h * W + w];
+      if (cm != 255) {
+        const int ti = cm - c + 4;
+        if (ti >= 0 && ti <= 8) v = fmaf(__ldg(t.kw + ti), qsel[(size_t)b * HW + h * W + w], v);
+      }
     }
-    bufA[h * 65 + c] = v;
+    sq[e] = v;
   }
   __syncthreads();
-  for (int e = tid; e < H * 64; e += kColThreads) {   // Q = conv9 along H
+  for (int e = tid; e < Hp * 64; e += kColThreads) {   // Q = conv9 along H (rows >= H: zero queries, never stored)
     const int h = e >> 6, c = e & 63;
-    float acc = t.bh;
+    float acc = 0.f;
+    if (h < H) {
+      acc = t.bh;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int hh = h + i - 4;
-      if (hh >= 0 && hh < H) acc = fmaf(kh[i], bufA[hh * 65 + c], acc);
+      for (int i = 0; i < 9; ++i) acc = fmaf(kh[i], sq[(h + i) * 64 + c], acc);
     }
-    Q[h * 65 + c] = acc;
+    Q[h * kLd + c] = acc;
   }
   __syncthreads();
   const float *vsrc = vrow_t + ((size_t)b * W + w) * H * 64;   // contiguous [H][64]
-  for (int e = tid; e < H * 64; e += kColThreads) bufA[(e >> 6) * 65 + (e & 63)] = vsrc[e];
-  __syncthreads();
-
-  float *p = pw + warp * H;
-  for (int h = warp; h < H; h += kColThreads / 32) {
-    const float *qh = Q + h * 65;
-    float mx = -INFINITY;
-    for (int h2 = lane; h2 < H; h2 += 32) {
-      const float *q2 = Q + h2 * 65;
-      float s = 0.f;
-#pragma unroll 16
-      for (int c = 0; c < 64; ++c) s = fmaf(qh[c], q2[c], s);
-      p[h2] = s;
-      mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float ds = 0.f;
-    for (int h2 = lane; h2 < H; h2 += 32) {
-      const float e = expf(p[h2] - mx);
-      p[h2] = e;
-      ds += e;
-    }
-    ds = warp_sum(ds);
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-    for (int h2 = 0; h2 < H; ++h2) {
-      const float e = p[h2];
-      a0 = fmaf(e, bufA[h2 * 65 + lane], a0);
-      a1 = fmaf(e, bufA[h2 * 65 + 32 + lane], a1);
-    }
-    float *o = long_out + (((size_t)b * H + h) * W + w) * 64;   // NHWC
-    o[lane] = a0 / ds;
-    o[32 + lane] = a1 / ds;
-    __syncwarp();
+  for (int q0 = 0; q0 < H; q0 += 64) {
+    auto load_chunk = [&](int kb) {
+      for (int e = tid; e < 64 * 16; e += kColThreads) {
+        const int r = e >> 4, c4 = (e & 15) * 4;
+        const int h = kb * 64 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < H) v = *reinterpret_cast<const float4 *>(vsrc + (size_t)h * 64 + c4);
+        *reinterpret_cast<float4 *>(Vc + r * kLd + c4) = v;
+      }
+      __syncthreads();
+    };
+    // the keys of chunk kb are rows kb*64 .. of Q itself (scores are q_c q_c^T, arch:2228)
+    const float *Kcur = Q;
+    auto key_chunk = [&](int kb) { Kcur = Q + kb * 64 * kLd; load_chunk(kb); };
+    flash_block_fp32_kptr(Q + q0 * kLd, &Kcur, Vc, Ps, H, key_chunk, [&](int r, int c4, float4 v) {
+      const int h = q0 + r;
+      if (h < H) *reinterpret_cast<float4 *>(long_out + (((size_t)b * H + h) * W + w) * 64 + c4) = v;
+    });
   }
 }
 
@@ -276,49 +370,28 @@ __global__ void __launch_bounds__(kColThreads) lra_col_kernel(const float *__res
 constexpr int kWinThreads = 256;
 __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
                                                              float *__restrict__ loc_out, int H, int W) {
-  __shared__ float q[64 * 65];
-  __shared__ float v[64 * 65];
-  __shared__ float pr[8][64];
+  extern __shared__ __align__(16) float sm[];
+  float *q = sm;                 // [64][kLd]
+  float *v = q + 64 * kLd;
+  float *Ps = v + 64 * kLd;
   const int b = blockIdx.z, wy = blockIdx.y, wx = blockIdx.x;
   const int HW = H * W;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   for (int e = tid; e < 64 * 64; e += kWinThreads) {
     const int c = e >> 6, tok = e & 63;                      // tok = dh*8 + dw
     const int h = wy * 8 + (tok >> 3), w = wx * 8 + (tok & 7);
     const size_t pix = (size_t)h * W + w;
     float qq = qv[((size_t)b * 128 + c) * HW + pix];
     if (midx[(size_t)b * HW + pix] == c) qq = 0.f;
-    q[tok * 65 + c] = qq;
-    v[tok * 65 + c] = qv[((size_t)b * 128 + 64 + c) * HW + pix];
+    q[tok * kLd + c] = qq;
+    v[tok * kLd + c] = qv[((size_t)b * 128 + 64 + c) * HW + pix];
   }
   __syncthreads();
-  for (int tok = warp; tok < 64; tok += kWinThreads / 32) {
-    const float *qt = q + tok * 65;
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll 16
-    for (int c = 0; c < 64; ++c) {
-      s0 = fmaf(qt[c], q[lane * 65 + c], s0);
-      s1 = fmaf(qt[c], q[(lane + 32) * 65 + c], s1);
-    }
-    const float mx = warp_max(fmaxf(s0, s1));
-    const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
-    const float ds = warp_sum(e0 + e1);
-    pr[warp][lane] = e0;
-    pr[warp][lane + 32] = e1;
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 16
-    for (int t2 = 0; t2 < 64; ++t2) {
-      const float e = pr[warp][t2];
-      a0 = fmaf(e, v[t2 * 65 + lane], a0);
-      a1 = fmaf(e, v[t2 * 65 + 32 + lane], a1);
-    }
+  const float *Kcur = q;
+  flash_block_fp32_kptr(q, &Kcur, v, Ps, 64, [&](int) {}, [&](int tok, int c4, float4 val) {
     const int h = wy * 8 + (tok >> 3), w = wx * 8 + (tok & 7);
-    float *o = loc_out + (((size_t)b * H + h) * W + w) * 64;
-    o[lane] = a0 / ds;
-    o[32 + lane] = a1 / ds;
-    __syncwarp();
-  }
+    *reinterpret_cast<float4 *>(loc_out + (((size_t)b * H + h) * W + w) * 64 + c4) = val;
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ fuse
@@ -397,23 +470,26 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   lra_mask_kernel<<<dim3(ceil_div(HW, 128), B), 128, 0, s>>>(u, vmax, qv, midx, qsel, HW);
 
   const size_t row_smem = ((size_t)W * 65 + 3 * W + 64 + 256 + 8 * W) * 4 + 2 * (size_t)W * 4;
-  const size_t col_smem = ((size_t)2 * H * 65 + 8 * H) * 4;
+  const int Hp = (H + 63) & ~63;
+  const size_t col_smem = ((size_t)(Hp + 128) * kLd + (size_t)(H + 8) * 64) * 4;
+  const size_t win_smem = (size_t)3 * 64 * kLd * 4;
   const size_t fuse_smem = ((size_t)128 * 65 + kFusePix * 129) * 4;
   const int kDynMax = 224 * 1024;  // 227 KB opt-in limit minus the kernels' small static shared memory
   CDFO_REQUIRE(row_smem <= (size_t)kDynMax && col_smem <= (size_t)kDynMax, CDFO_ERR_UNSUPPORTED,
-               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 730, H <= 410)", H, W);
+               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 730, H <= 320)", H, W);
   static bool attr = false;
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e2 = cudaFuncSetAttribute(lra_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e3 = cudaFuncSetAttribute(lra_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem);
+    if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(lra_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
       return fail(CDFO_ERR_CUDA, "cdfo_lra_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     attr = true;
   }
   lra_row_kernel<<<dim3(H, B), kRowThreads, row_smem, s>>>(qv, midx, qsel, vrow_t, t, H, W);
   lra_col_kernel<<<dim3(W, B), kColThreads, col_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
-  lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, 0, s>>>(qv, midx, loc_out, H, W);
+  lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, win_smem, s>>>(qv, midx, loc_out, H, W);
   lra_fuse_kernel<<<dim3(ceil_div(HW, kFusePix), B), kFuseThreads, fuse_smem, s>>>(long_out, loc_out, fuse_w, fuse_b, x, out, HW);
   return check_launch("cdfo_lra_fwd");
 }
