@@ -1,0 +1,449 @@
+// Modulated deformable convolution (DCNv2) forward at the model's hot shape, third generation of the sm_100a kernel:
+// the bilinear gather runs on the TEXTURE UNITS.
+//
+// Semantics: ops/dcn/src/deform_conv_cuda_kernel.cu:467-496,570-632 + deform_conv_cuda.cpp:486-564
+// (= torchvision.ops.deform_conv2d at arch/SIDECVSR_our.py:3352) with offset = learned residual + decoded MV prior
+// (arch/SIDECVSR_our.py:3347), C = Co = 64, 3x3, stride = pad = dil = 1, groups = 1, dg | 16.
+//
+// Why textures: ncu on the LSU-gather kernel (dcn_sm100.cu, profiles/r01_dcn_sm100_v2_ncu.md) and on the gather probe
+// (tools/gather_probe.cu, profiles/r01_gather_probe.md) shows that the binding resource of this op is neither HBM nor
+// the issue slots but the L1TEX data stage (~1 wavefront / clk / SM, shared by LDG, LDS/STS and TEX): an LDG gather of
+// the 2x2 footprint costs 16-20 wavefronts per 32 samples and ~50 instructions per sample; one hardware-filtered
+// fetch of an fp16x4 texel costs 15 wavefronts and ~20 instructions, independent of how scattered the offsets are.
+//   * x lives in HBM as "q4t": [xB][16 quads][H+3][Wpt] texels of 4 fp16 channels with the same zero border as q4p
+//     (1 before, 2 after; Wpt = W+3 rounded up to 4 texels so that the row pitch is 32-byte aligned); every sample
+//     is one pitch-linear 2-D texture whose row axis folds the 16 quad planes.  The reference's inside test and its
+//     per-corner zero padding become: clamp the sample position to [-1, H] x [-1, W], read the zero border.
+//   * offsets / mask arrive as packed fields [B][dg*9][H*W] x fp16x4 (dy, dx, mask, 0) -- what the fused head
+//     (conv3x3_sm100.cu) writes; the MV prior is added here, in the reference's fp32 order (residual + flow, then
+//     base + offset).
+//   * the filter weights are the texture unit's (8 fractional bits): the blended value deviates from the fp32
+//     bilinear by <= 2^-9 of the local texel differences, the same order as the bf16/fp16 rounding of the A operand;
+//     the exact-arithmetic gather (bit-exact floor indices, cdfo_dcn_sample_index) stays available in dcn_sm100.cu.
+//   * implicit GEMM as before: producers write the fp16 A operand of a tap (128 px x 64 ci) into a 4-stage shared
+//     memory ring in the tcgen05 canonical K-major layout, one thread issues tcgen05.mma (M128 N64 K16, fp16 -> fp32
+//     in TMEM), 4 warps drain TMEM (+ bias) to NCHW fp32 or c8 bf16.  Producers are software-pipelined two taps deep
+//     (fields of tap t+2 and the texture fetches of tap t+1 are in flight while tap t is packed).
+#include <mutex>
+
+#include "cdfo_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cdfo {
+namespace dtex {
+
+constexpr int kTileM = 128;
+constexpr int kTileH = 4, kTileW = 32;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 16;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kWBytes = 9 * 64 * 64 * 2;
+constexpr int kABytes = kTileM * 64 * 2;
+constexpr int kALbo = kTileM * 16;
+constexpr int kBLbo = 64 * 16;
+constexpr int kSbo = 128;
+constexpr int kTapWBytes = 64 * 64 * 2;
+constexpr int kMaxTex = 32;
+
+struct Params {
+  cudaTextureObject_t tex[kMaxTex];  // one per x sample
+  const uint2 *fields;               // [B][dg*9][H*W] (dy, dx, m, 0) fp16
+  const float *mv;                   // [B][2][H*W] (x, y) or nullptr
+  const uint8_t *wpk;                // [9][8][64][8] fp16
+  const float *bias;
+  void *y;
+  int B, H, W, dg, out_mode, gshift, x_batch;
+  long long f_bstride;               // uint2 elements between samples of fields
+  int tiles_x, tiles_per_img, num_tiles;
+};
+
+constexpr size_t smem_bytes() { return kWBytes + kStages * kABytes + 256 + 16 * 8 + 16; }
+
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
+
+struct TileCoord { int b, h0, w0; };
+__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile) {
+  TileCoord t;
+  t.b = tile / p.tiles_per_img;
+  const int r = tile - t.b * p.tiles_per_img;
+  const int ty = r / p.tiles_x;
+  t.h0 = ty * kTileH;
+  t.w0 = (r - ty * p.tiles_x) * kTileW;
+  return t;
+}
+
+// instruction descriptor: fp16 x fp16 -> fp32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm100_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *wsm = smem;
+  uint8_t *asmem = smem + kWBytes;
+  float *bias_s = reinterpret_cast<float *>(smem + kWBytes + kStages * kABytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + kStages * kABytes + 256);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  // barrier map: [0,4) A stage full, [4,8) A stage empty, 8 accumulator full, 12 weights
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = p.H * p.W;
+
+  if (tid < 64) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(BAR(s), kProdThreads);
+        ptx::mbar_init(BAR(4 + s), 1);
+      }
+      ptx::mbar_init(BAR(8), 1);
+      ptx::mbar_init(BAR(12), 1);
+      ptx::fence_mbar_init();
+      ptx::mbar_arrive_expect_tx(BAR(12), kWBytes);
+      for (int t = 0; t < 9; ++t)
+        ptx::bulk_g2s(ptx::smem_u32(wsm) + t * kTapWBytes, p.wpk + t * kTapWBytes, kTapWBytes, BAR(12));
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ============ warp 0 lane 0 issues the MMAs of a tile, then all 4 warps drain TMEM ============
+    const uint32_t idesc = make_idesc_f16(kTileM, 64);
+    if (warp == 0) ptx::mbar_wait(BAR(12), 0);
+    int stage = 0, phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (warp == 0) {
+        for (int tap = 0; tap < 9; ++tap) {
+          ptx::mbar_wait(BAR(stage), phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a0 = ptx::smem_u32(asmem) + stage * kABytes;
+            const uint32_t b0 = ptx::smem_u32(wsm) + tap * kTapWBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t ad = ptx::make_smem_desc(a0 + j * 2 * kALbo, kALbo, kSbo);
+              const uint64_t bd = ptx::make_smem_desc(b0 + j * 2 * kBLbo, kBLbo, kSbo);
+              ptx::umma_f16(tmem_base, ad, bd, idesc, (tap | j) != 0);
+            }
+            ptx::umma_commit(BAR(4 + stage));
+            if (tap == 8) ptx::umma_commit(BAR(8));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      const TileCoord tc = tile_coord(p, tile);
+      const int h = tc.h0 + warp, w = tc.w0 + lane;
+      const bool live = h < p.H && w < p.W;
+      const int pix = h * p.W + w;
+      ptx::mbar_wait(BAR(8), acc_phase);
+      acc_phase ^= 1;
+      ptx::tc_fence_after();
+      uint32_t r[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + half * 32, r);
+        ptx::tmem_ld_wait();
+        if (half == 1) {
+          ptx::tc_fence_before();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (live) {
+          if (p.out_mode == 0) {
+            float *y = reinterpret_cast<float *>(p.y) + ((size_t)tc.b * 64 + half * 32) * P + pix;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) __stcs(y + (size_t)n * P, __uint_as_float(r[n]) + bias_s[half * 32 + n]);
+          } else {
+            uint4 *y = reinterpret_cast<uint4 *>(p.y) + ((size_t)tc.b * 8 + half * 4) * P + pix;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+              uint4 v;
+              const float *bs = bias_s + half * 32 + kc * 8;
+              v.x = pack_bf2(__uint_as_float(r[kc * 8 + 0]) + bs[0], __uint_as_float(r[kc * 8 + 1]) + bs[1]);
+              v.y = pack_bf2(__uint_as_float(r[kc * 8 + 2]) + bs[2], __uint_as_float(r[kc * 8 + 3]) + bs[3]);
+              v.z = pack_bf2(__uint_as_float(r[kc * 8 + 4]) + bs[4], __uint_as_float(r[kc * 8 + 5]) + bs[5]);
+              v.w = pack_bf2(__uint_as_float(r[kc * 8 + 6]) + bs[6], __uint_as_float(r[kc * 8 + 7]) + bs[7]);
+              y[(size_t)kc * P] = v;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== producers: fields -> texture fetch -> x mask -> A operand ===========================
+    const int ptid = tid - kEpiWarps * 32;
+    const int row = ptid & (kTileM - 1);
+    const int ty = row >> 5, tx = row & 31;
+    const int quad0 = (ptid / kTileM) * 4;
+    const float Hf = (float)p.H, Wf = (float)p.W;
+    float plane_y[4];   // texture row of image row -1.5 of this thread's quad planes (+0.5 texel centre, +1 border)
+    int kfield[4];      // uint2 offset of tap 0 of each quad's deformable group
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      plane_y[qi] = (float)((quad0 + qi) * (p.H + 3)) + 1.5f;
+      kfield[qi] = ((quad0 + qi) >> p.gshift) * 9 * P;
+    }
+
+    struct Pix {   // per-tile state of the pixel this thread owns
+      const uint2 *f;
+      cudaTextureObject_t tex;
+      float hb, wb, mvx, mvy;
+      bool live;
+    };
+    auto pix_state = [&](int tile) {
+      Pix s;
+      const TileCoord tc = tile_coord(p, tile);
+      const int h = tc.h0 + ty, w = tc.w0 + tx;
+      s.live = h < p.H && w < p.W;
+      const int pixc = min(h, p.H - 1) * p.W + min(w, p.W - 1);
+      s.f = p.fields + (size_t)tc.b * p.f_bstride + pixc;
+      s.tex = p.tex[tc.b % p.x_batch];
+      s.hb = (float)(h - 1);
+      s.wb = (float)(w - 1);
+      s.mvx = p.mv ? __ldg(p.mv + ((size_t)tc.b * 2 + 0) * P + pixc) : 0.f;
+      s.mvy = p.mv ? __ldg(p.mv + ((size_t)tc.b * 2 + 1) * P + pixc) : 0.f;
+      return s;
+    };
+    struct Buf { float4 v[4]; uint32_t m2[4]; };
+
+    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total = my_tiles * 9;
+    if (total > 0) {
+      // F: field-fetch cursor (two steps ahead of the consumer), I: texture-issue cursor (one step ahead)
+      Pix fpix = pix_state(blockIdx.x), ipix = fpix;
+      int ftile = blockIdx.x, ftap = 0, iti = 0, itj = 0;
+      uint2 f[4];
+      auto fetch_fields = [&]() {
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) f[qi] = __ldcs(fpix.f + kfield[qi] + ftap * P);
+        if (++ftap == 9) {
+          ftap = 0;
+          ftile += gridDim.x;
+          if (ftile < p.num_tiles) fpix = pix_state(ftile);
+        }
+      };
+      auto issue = [&](Buf &b) {
+        const float hb = ipix.hb + (float)iti, wb = ipix.wb + (float)itj;
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+          const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&f[qi].x));
+          // reference order: offset = residual + flow (arch :3347), then h_im = base + offset (.cu:614-615)
+          const float h_im = __fadd_rn(hb, __fadd_rn(d.x, ipix.mvy));
+          const float w_im = __fadd_rn(wb, __fadd_rn(d.y, ipix.mvx));
+          const float hc = fminf(fmaxf(h_im, -1.f), Hf), wc = fminf(fmaxf(w_im, -1.f), Wf);  // NaN -> -1 -> zero border
+          b.v[qi] = tex2D<float4>(ipix.tex, wc + 1.5f, hc + plane_y[qi]);
+          const uint32_t mm = __byte_perm(f[qi].y, 0, 0x1010);   // (m, m) fp16x2
+          b.m2[qi] = ipix.live ? mm : 0u;
+        }
+        if (++itj == 3) {
+          itj = 0;
+          if (++iti == 3) {   // the F cursor entered the next tile one step ago
+            iti = 0;
+            ipix = fpix;
+          }
+        }
+      };
+      int stage = 0, phase = 0;
+      auto consume = [&](const Buf &b) {
+        ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
+        uint8_t *a_dst = asmem + stage * kABytes + (quad0 >> 1) * kALbo + row * 16;
+#pragma unroll
+        for (int pair = 0; pair < 2; ++pair) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int qi = pair * 2 + e;
+            const __half2 m2 = *reinterpret_cast<const __half2 *>(&b.m2[qi]);
+            o[e * 2 + 0] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].x, b.v[qi].y)));
+            o[e * 2 + 1] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].z, b.v[qi].w)));
+          }
+          *reinterpret_cast<uint4 *>(a_dst + pair * kALbo) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(BAR(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      };
+
+      Buf buf[2];
+      fetch_fields();        // fields of step 0
+      issue(buf[0]);         // textures of step 0
+      if (total > 1) fetch_fields();   // fields of step 1
+      for (int g = 0; g < total; g += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int s = g + u;
+          if (s < total) {
+            if (s + 1 < total) issue(buf[u ^ 1]);
+            if (s + 2 < total) fetch_fields();
+            consume(buf[u]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+}
+
+// W [64 co][64 ci][3][3] fp32 -> [tap][kc][co][8] fp16
+__global__ void pack_weight_f16_kernel(const float *__restrict__ w, __half *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * 64 * 64) return;
+  const int j = e % 8, co = (e / 8) % 64, kc = (e / 512) % 8, tap = e / 4096;
+  out[e] = __float2half_rn(fminf(fmaxf(w[((size_t)co * 64 + kc * 8 + j) * 9 + tap], -65504.f), 65504.f));
+}
+
+// NCHW fp32 -> [B][C/4][H+3][Wpt] texels of 4 fp16 (saturated), zero border 1 before / 2 after, zero pitch padding
+__global__ void pack_q4t_kernel(const float *__restrict__ x, uint2 *__restrict__ out, int C, int H, int W, int Wpt) {
+  const int Hp = H + 3;
+  const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp >= Hp * Wpt) return;
+  const int q = blockIdx.y, b = blockIdx.z;
+  const int h = pp / Wpt - 1, w = pp % Wpt - 1;
+  uint2 v = make_uint2(0, 0);
+  if (h >= 0 && h < H && w >= 0 && w < W) {
+    const float *src = x + (((size_t)b * C + q * 4) * H + h) * W + w;
+    const size_t HW = (size_t)H * W;
+    auto sat = [](float a) { return fminf(fmaxf(a, -65504.f), 65504.f); };
+    v.x = h2_as_u32(__floats2half2_rn(sat(src[0]), sat(src[HW])));
+    v.y = h2_as_u32(__floats2half2_rn(sat(src[2 * HW]), sat(src[3 * HW])));
+  }
+  out[((size_t)b * (C / 4) + q) * Hp * Wpt + pp] = v;
+}
+
+// ---- texture objects over caller-owned linear memory, cached by (device, pointer, shape) ----
+struct TexEntry { int dev; const void *ptr; int H, Wpt; cudaTextureObject_t tex; unsigned long long stamp; };
+static std::mutex g_mu;
+static TexEntry g_cache[64];
+static int g_cache_n = 0;
+static unsigned long long g_stamp = 0;
+
+static cudaError_t get_texture(const void *ptr, int H, int W, int Wpt, cudaTextureObject_t *out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (int i = 0; i < g_cache_n; ++i)
+    if (g_cache[i].dev == dev && g_cache[i].ptr == ptr && g_cache[i].H == H && g_cache[i].Wpt == Wpt) {
+      g_cache[i].stamp = ++g_stamp;
+      *out = g_cache[i].tex;
+      return cudaSuccess;
+    }
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypePitch2D;
+  rd.res.pitch2D.devPtr = const_cast<void *>(ptr);
+  rd.res.pitch2D.desc = cudaCreateChannelDescHalf4();
+  rd.res.pitch2D.width = (size_t)W + 3;
+  rd.res.pitch2D.height = (size_t)16 * (H + 3);
+  rd.res.pitch2D.pitchInBytes = (size_t)Wpt * 8;
+  cudaTextureDesc td = {};
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  cudaTextureObject_t t = 0;
+  e = cudaCreateTextureObject(&t, &rd, &td, nullptr);
+  if (e != cudaSuccess) return e;
+  int slot = g_cache_n;
+  if (g_cache_n < 64) {
+    ++g_cache_n;
+  } else {   // evict the least recently used descriptor (it only describes memory, it owns none)
+    slot = 0;
+    for (int i = 1; i < 64; ++i)
+      if (g_cache[i].stamp < g_cache[slot].stamp) slot = i;
+    cudaDestroyTextureObject(g_cache[slot].tex);
+  }
+  g_cache[slot] = TexEntry{dev, ptr, H, Wpt, t, ++g_stamp};
+  *out = t;
+  return cudaSuccess;
+}
+
+}  // namespace dtex
+}  // namespace cdfo
+
+using namespace cdfo;
+
+extern "C" int cdfo_q4t_pitch(int W) { return (W + 3 + 3) & ~3; }
+
+extern "C" size_t cdfo_q4t_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || C % 4 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * (C / 4) * (H + 3) * cdfo_q4t_pitch(W) * 8;
+}
+
+extern "C" int cdfo_pack_q4t(const float *x_nchw, void *x_q4t, int B, int C, int H, int W, void *stream) {
+  CDFO_REQUIRE(x_nchw && x_q4t, CDFO_ERR_NULL, "cdfo_pack_q4t: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 4 == 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_pack_q4t: bad shape");
+  const int Wpt = cdfo_q4t_pitch(W);
+  dim3 grid(ceil_div((H + 3) * Wpt, 128), C / 4, B);
+  dtex::pack_q4t_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, (uint2 *)x_q4t, C, H, W, Wpt);
+  return check_launch("cdfo_pack_q4t");
+}
+
+extern "C" int cdfo_dcn_tex_sm100_pack_weight(const float *w, void *wpk, void *stream) {
+  CDFO_REQUIRE(w && wpk, CDFO_ERR_NULL, "cdfo_dcn_tex_sm100_pack_weight: NULL pointer");
+  dtex::pack_weight_f16_kernel<<<ceil_div(9 * 64 * 64, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half *)wpk);
+  return check_launch("cdfo_dcn_tex_sm100_pack_weight");
+}
+
+extern "C" int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk,
+                                      const float *bias, void *y, int B, int H, int W, int dg, int out_mode,
+                                      int num_ctas, int x_batch, long long fields_bstride, void *stream) {
+  CDFO_REQUIRE(x_q4t && fields && wpk && y, CDFO_ERR_NULL, "cdfo_dcn_tex_sm100_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: bad shape");
+  CDFO_REQUIRE(dg == 1 || dg == 2 || dg == 4 || dg == 8 || dg == 16, CDFO_ERR_UNSUPPORTED,
+               "cdfo_dcn_tex_sm100_fwd: deformable groups must divide 16 (got %d)", dg);
+  CDFO_REQUIRE(out_mode == 0 || out_mode == 1, CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: out_mode %d", out_mode);
+  CDFO_REQUIRE(((uintptr_t)wpk & 15) == 0 && ((uintptr_t)x_q4t & 511) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)fields & 7) == 0,
+               CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: x_q4t must be 512-byte aligned (texture base), wpk / y 16-byte, fields 8-byte");
+  CDFO_REQUIRE(16ll * (H + 3) <= 65000 && W + 3 <= 131072, CDFO_ERR_UNSUPPORTED,
+               "cdfo_dcn_tex_sm100_fwd: frame %d x %d exceeds the 2-D linear texture limits (H <= 4059)", H, W);
+  dtex::Params p;
+  p.x_batch = x_batch > 0 ? x_batch : B;
+  CDFO_REQUIRE(B % p.x_batch == 0, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: B (%d) must be a multiple of x_batch (%d)", B, p.x_batch);
+  CDFO_REQUIRE(p.x_batch <= dtex::kMaxTex, CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: at most %d distinct x samples per call (got %d)",
+               dtex::kMaxTex, p.x_batch);
+  const int Wpt = cdfo_q4t_pitch(W);
+  const size_t sample_bytes = (size_t)16 * (H + 3) * Wpt * 8;
+  for (int i = 0; i < dtex::kMaxTex; ++i) p.tex[i] = 0;
+  for (int i = 0; i < p.x_batch; ++i) {
+    cudaError_t e = dtex::get_texture((const uint8_t *)x_q4t + (size_t)i * sample_bytes, H, W, Wpt, &p.tex[i]);
+    if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cdfo_dcn_tex_sm100_fwd: cudaCreateTextureObject: %s", cudaGetErrorString(e));
+  }
+  p.fields = (const uint2 *)fields; p.mv = mv; p.wpk = (const uint8_t *)wpk; p.bias = bias; p.y = y;
+  p.B = B; p.H = H; p.W = W; p.dg = dg; p.out_mode = out_mode;
+  p.f_bstride = fields_bstride > 0 ? fields_bstride : (long long)dg * 9 * H * W;
+  p.gshift = 0;
+  while ((16 >> p.gshift) > dg) ++p.gshift;
+  p.tiles_x = ceil_div(W, dtex::kTileW);
+  p.tiles_per_img = p.tiles_x * ceil_div(H, dtex::kTileH);
+  CDFO_REQUIRE((long long)dg * 9 * H * W < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: field planes too large for 32-bit indexing");
+  const long long nt = (long long)p.tiles_per_img * B;
+  CDFO_REQUIRE(nt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: too many tiles");
+  p.num_tiles = (int)nt;
+  int grid = num_ctas > 0 ? num_ctas : kNumSMs;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  static bool attr_done = false;
+  const size_t smem = dtex::smem_bytes();
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(dcn_tex_sm100): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dtex::dcn_tex_sm100_kernel<<<grid, (dtex::kEpiWarps + dtex::kProdWarps) * 32, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("cdfo_dcn_tex_sm100_fwd");
+}

@@ -93,3 +93,65 @@ def _launch(x_q4p, offset, mask, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, x
         ev[1].record()
         event_log.append((ev[0], ev[1], B * H * W, 8 if off_code == FIELDS_F16X4 else offset.element_size()))
     return y
+
+
+# ------------------------------------------------------------------------------------------ texture-unit gather (v3)
+_wcache16 = {}
+
+
+@torch.no_grad()
+def pack_weight_f16(weight: torch.Tensor) -> torch.Tensor:
+    """[64,64,3,3] -> fp16 B operand [9, 8, 64, 8] of cdfo_dcn_tex_sm100_fwd; cached per parameter / version."""
+    key = id(weight)
+    hit = _wcache16.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    w = weight.detach().contiguous().float()
+    out = torch.empty((9, 8, 64, 8), dtype=torch.float16, device=w.device)
+    _lib.call("cdfo_dcn_tex_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
+    _wcache16[key] = (weakref.ref(weight), weight._version, out)
+    return out
+
+
+@torch.no_grad()
+def pack_q4t(x: torch.Tensor) -> torch.Tensor:
+    """NCHW fp32 -> [B, C/4, H+3, Wpt, 4] fp16 texels (zero border 1 before / 2 after, pitch padded to 32 bytes)."""
+    B, C, H, W = x.shape
+    x = x.contiguous().float()
+    wpt = _lib.lib().cdfo_q4t_pitch(W)
+    out = torch.empty((B, C // 4, H + 3, wpt, 4), dtype=torch.float16, device=x.device)
+    _lib.call("cdfo_pack_q4t", _lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
+    return out
+
+
+@torch.no_grad()
+def dcn_tex(x_q4t, fields, wpk16, bias=None, mv=None, out_c8=False, num_ctas=0):
+    """x_q4t [xB,16,H+3,Wpt,4] fp16; fields [B, dg*9, H, W, 4] fp16 (dy, dx, mask, 0); mv [B,2,H,W] fp32 or None.
+    Returns [B,64,H,W] fp32 (out_c8=False) or [B,8,H,W,8] bf16."""
+    xB, _, Hp, _, _ = x_q4t.shape
+    if fields.dtype != torch.float16 or not fields.is_contiguous() or fields.dim() != 5 or fields.size(4) != 4:
+        raise _lib.CdfoError("dcn_tex: fields must be a contiguous fp16 [B, dg*9, H, W, 4] tensor")
+    B, K, H, W, _ = fields.shape
+    if H != Hp - 3 or x_q4t.size(3) != _lib.lib().cdfo_q4t_pitch(W) or x_q4t.dtype != torch.float16 or not x_q4t.is_contiguous():
+        raise _lib.CdfoError("dcn_tex: x_q4t does not match the %dx%d fields (use pack_q4t)" % (H, W))
+    if B % xB:
+        raise _lib.CdfoError("dcn_tex: batch %d is not a multiple of the x batch %d" % (B, xB))
+    if mv is not None:
+        mv = mv.contiguous().float()
+    if bias is not None:
+        bias = bias.detach().contiguous().float()
+    if out_c8:
+        y = torch.empty((B, 8, H, W, 8), dtype=torch.bfloat16, device=fields.device)
+    else:
+        y = torch.empty((B, 64, H, W), dtype=torch.float32, device=fields.device)
+    ev = None
+    if event_log is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.call("cdfo_dcn_tex_sm100_fwd", _lib.ptr(x_q4t), _lib.ptr(fields), _lib.ptr(mv), _lib.ptr(wpk16), _lib.ptr(bias),
+              _lib.ptr(y), B, H, W, K // 9, 1 if out_c8 else 0, int(num_ctas), int(xB), ctypes.c_longlong(0),
+              _lib.stream_ptr(fields.device))
+    if ev is not None:
+        ev[1].record()
+        event_log.append((ev[0], ev[1], B * H * W, 8))
+    return y

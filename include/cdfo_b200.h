@@ -18,6 +18,7 @@
  *   cdfo_pack_c8 / unpack   layout adapters NCHW fp32 <-> channel-chunked bf16 used by the sm_100a kernels
  *   cdfo_dcn_sm100_fwd      same contraction as cdfo_dcn_fwd at the model's hot shape (C=Co=64, 3x3, s=p=d=1,
  *                           groups=1), tcgen05 implicit GEMM, bf16 operands, fp32 accumulate
+ *   cdfo_dcn_tex_sm100_fwd  the same contraction with the bilinear gather on the texture units (fields input, fp16 operands)
  *   cdfo_mv_offset_assemble arch/SIDECVSR_our.py:3341-3350 (chunk/cat/tanh/x10/+flow.flip/sigmoid)
  *   cdfo_conv3x3_sm100_fwd  3x3 s1 p1 convolutions on the path (arch/SIDECVSR_our.py:3271-3275 conv_offset,
  *                           :254-271 ResidualBlock_noBN, :4382 conv_expand_fea_r), tcgen05 implicit GEMM
@@ -107,6 +108,24 @@ int cdfo_dcn_sm100_fwd(const void *x_q4p, const void *offset, const void *mask, 
 int cdfo_dcn_sm100_pack_weight(const float *w, void *wpk, void *stream);
 /* NCHW fp32 -> [B, C/4, H+3, W+3, 4] bf16 with the zero border described above (C % 4 == 0). */
 int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, void *stream);
+/* ---- A6 at the model's hot shape, gather on the texture units (csrc/dcn_tex_sm100.cu) ----
+ * Same contraction and shape limits as cdfo_dcn_sm100_fwd; fp16 operands, fp32 accumulate.  The 2x2 bilinear footprint
+ * of each (pixel, group, tap) sample is ONE hardware-filtered texture fetch (8 fractional weight bits) instead of four
+ * loads and ~30 blend instructions: the op is bound by the L1TEX data stage, not by HBM or issue.
+ *   x_q4t  [xB, 16, H+3, Wpt, 4] fp16 from cdfo_pack_q4t (Wpt = cdfo_q4t_pitch(W); 512-byte aligned base)
+ *   fields [B, dg*9, H, W] x fp16x4 (dy, dx, mask, 0): learned residual and mask as cdfo_mv_offset_head_sm100_fwd writes them
+ *   mv     [B, 2, H, W] fp32 (x, y) or NULL: decoded MV prior, added as offset + flow.flip(1).repeat(...) (arch:3347)
+ *   wpk    73728 bytes from cdfo_dcn_tex_sm100_pack_weight (fp16); bias [64] fp32 or NULL
+ *   y / out_mode / num_ctas / x_batch: as cdfo_dcn_sm100_fwd (x_batch <= 32); fields_bstride in 8-byte elements (<= 0: dense).
+ * Texture descriptors over x_q4t are created on first use and cached by (device, pointer, shape); they own no memory. */
+int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias,
+                           void *y, int B, int H, int W, int dg, int out_mode, int num_ctas, int x_batch,
+                           long long fields_bstride, void *stream);
+int cdfo_dcn_tex_sm100_pack_weight(const float *w, void *wpk, void *stream);
+/* NCHW fp32 -> [B, C/4, H+3, Wpt, 4] fp16 (saturated to +-65504), zero border 1 before / 2 after, zero pitch padding. */
+int cdfo_pack_q4t(const float *x_nchw, void *x_q4t, int B, int C, int H, int W, void *stream);
+int cdfo_q4t_pitch(int W);
+size_t cdfo_q4t_bytes(int B, int C, int H, int W);
 /* ---- 3x3 / stride 1 / padding 1 convolution, tcgen05 implicit GEMM with a TMA-staged halo (A9, heads of A5, A4) ----
  * Replaces nn.Conv2d(Cin, Cout, 3, 1, 1) on the path: conv_offset.{0,2} (arch/SIDECVSR_our.py:3271-3275),
  * ResidualBlock_noBN.conv{1,2} (:254-271), conv_expand_fea_r (:4382).  Cin % 64 == 0, Cout % 16 == 0.

@@ -60,6 +60,18 @@ def main():
     res["sm100_f16off_c8out_us"] = t
     res["sm100_f16off_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
     res["pack_q4p_us"] = timeit(lambda: S.pack_q4p(x), a.iters)
+    o = offset.view(B, dg * 9, 2, H, W)
+    fields = torch.stack([o[:, :, 0], o[:, :, 1], mask, torch.zeros_like(mask)], dim=-1).half().contiguous()
+    xt, w16 = S.pack_q4t(x), S.pack_weight_f16(wt)
+    t = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, out_c8=True, num_ctas=a.ctas), a.iters)
+    res["tex_fields_c8out_us"] = t
+    res["tex_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
+    t = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, num_ctas=a.ctas), a.iters)
+    res["tex_fields_f32out_us"] = t
+    res["pack_q4t_us"] = timeit(lambda: S.pack_q4t(x), a.iters)
+    ya, yb = S.dcn_tex(xt, fields, w16, bias), S.dcn_sm100(xc, off16, m16, wpk, bias)
+    res["tex_vs_exact_maxdiff"] = float((ya - yb).abs().max())
+    res["out_absmax"] = float(yb.abs().max())
     if not a.skip_baselines:
         cdfo_b200.config.tensor_core = False
         res["generic_fp32_us"] = timeit(

@@ -22,7 +22,7 @@ constexpr int H = 272, W = 480, Q = 16, TAPS = 9;
 struct Params {
   const uint2 *xq;       // [B][Q][H+3][W+3] 8-byte texels, zero border 1 before / 2 after
   const uint4 *xp;       // [B][Q][H+3][W+3] 16-byte pair texels (w, w+1)
-  cudaTextureObject_t tex_lin, tex_pt;
+  cudaTextureObject_t tex_lin, tex_pt, tex_p2d;  // p2d: pitch-linear 2D over xq, planes folded into rows
   const __half *fields;  // [B][Q*9][H*W][4] (dy, dx, m, 0)
   float *out;            // [B][H*W] checksum per pixel
   int B;
@@ -34,7 +34,7 @@ __device__ __forceinline__ float bf(uint32_t u, int hi) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(512) probe(Params p) {
+__global__ void __launch_bounds__(512, 2) probe(Params p) {
   // persistent: CTA walks 4x32 tiles; thread = (pixel row in tile, 4 quads)
   const int tiles_x = W / 32, tiles_y = H / 4, per_img = tiles_x * tiles_y;
   const int ntiles = per_img * p.B;
@@ -45,15 +45,38 @@ __global__ void __launch_bounds__(512) probe(Params p) {
     const int pix = h * W + w;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     __half2 hacc0 = __float2half2_rn(0.f), hacc1 = hacc0;
+    uint2 nxt[4];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi)
+      nxt[qi] = __ldcs(reinterpret_cast<const uint2 *>(p.fields) + ((size_t)b * Q * 9 + (quad0 + qi) * 9) * P + pix);
 #pragma unroll 1
     for (int tap = 0; tap < TAPS; ++tap) {
+      uint2 cur[4];
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) {
+        cur[qi] = nxt[qi];
+        if (tap < 8) nxt[qi] = __ldcs(reinterpret_cast<const uint2 *>(p.fields) + ((size_t)b * Q * 9 + (quad0 + qi) * 9 + tap + 1) * P + pix);
+      }
 #pragma unroll
       for (int qi = 0; qi < 4; ++qi) {
         const int q = quad0 + qi;
-        const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(p.fields) + ((size_t)b * Q * 9 + q * 9 + tap) * P + pix);
+        const uint2 raw = cur[qi];
         const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
         const float m = __low2float(*reinterpret_cast<const __half2 *>(&raw.y));
         const float h_im = (float)(h - 1 + tap / 3) + d.x, w_im = (float)(w - 1 + tap % 3) + d.y;
+        if (MODE == 5 || MODE == 6 || MODE == 7) {
+          // mixed: quads with qi < NT go through the texture unit (pitch-2D, planes folded into the row axis),
+          // the others through the LSU (pair texels + HFMA2)
+          constexpr int NT = MODE == 5 ? 2 : (MODE == 6 ? 3 : 4);
+          if (qi < NT) {
+            const float hcl = fminf(fmaxf(h_im, -1.f), (float)H);
+            const float4 v = tex2D<float4>(p.tex_p2d, w_im + 1.5f, hcl + 1.5f + (float)((b * Q + q) * (H + 3)));
+            const __half2 m2 = __float2half2_rn(m);
+            hacc0 = __hfma2(m2, __floats2half2_rn(v.x, v.y), hacc0);
+            hacc1 = __hfma2(m2, __floats2half2_rn(v.z, v.w), hacc1);
+            continue;
+          }
+        }
         if (MODE == 2) {
           const float4 v = tex2DLayered<float4>(p.tex_lin, w_im + 1.5f, h_im + 1.5f, b * Q + q);
           acc0 = fmaf(m, v.x, acc0); acc1 = fmaf(m, v.y, acc1); acc2 = fmaf(m, v.z, acc2); acc3 = fmaf(m, v.w, acc3);
@@ -82,7 +105,7 @@ __global__ void __launch_bounds__(512) probe(Params p) {
           acc1 += w0 * bf(v0.x, 1) + w1 * bf(v0.z, 1) + w2 * bf(v2.x, 1) + w3 * bf(v2.z, 1);
           acc2 += w0 * bf(v0.y, 0) + w1 * bf(v0.w, 0) + w2 * bf(v2.y, 0) + w3 * bf(v2.w, 0);
           acc3 += w0 * bf(v0.y, 1) + w1 * bf(v0.w, 1) + w2 * bf(v2.y, 1) + w3 * bf(v2.w, 1);
-        } else if (MODE == 4) {
+        } else if (MODE >= 4) {
           const uint4 *qp = p.xp + ((size_t)b * Q + q) * plane + idx;
           const uint4 v0 = __ldg(qp), v2 = __ldg(qp + Wp);
           const __half2 h0 = __float2half2_rn(w0), h1 = __float2half2_rn(w1), h2 = __float2half2_rn(w2), h3 = __float2half2_rn(w3);
@@ -114,6 +137,7 @@ __global__ void __launch_bounds__(512) probe(Params p) {
 int main(int argc, char **argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 6;
   const float jitter = argc > 2 ? atof(argv[2]) : 0.3f;
+  const int grid = 148 * (argc > 3 ? atoi(argv[3]) : 2);
   const int Hp = H + 3, Wp = W + 3, P = H * W;
   srand(1);
   auto rnd = []() { return (rand() & 0xffff) / 65536.f; };
@@ -172,6 +196,19 @@ int main(int argc, char **argv) {
   td.filterMode = cudaFilterModePoint;
   CK(cudaCreateTextureObject(&p.tex_pt, &rd, &td, nullptr));
 
+  {
+    const size_t pitch = (((size_t)Wp * 8 + 127) / 128) * 128;
+    void *d_xt; CK(cudaMalloc(&d_xt, pitch * Hp * B * Q));
+    CK(cudaMemcpy2D(d_xt, pitch, d_xq, (size_t)Wp * 8, (size_t)Wp * 8, (size_t)Hp * B * Q, cudaMemcpyDeviceToDevice));
+    cudaResourceDesc r2 = {}; r2.resType = cudaResourceTypePitch2D; r2.res.pitch2D.devPtr = d_xt; r2.res.pitch2D.desc = cd;
+    r2.res.pitch2D.width = Wp; r2.res.pitch2D.height = (size_t)Hp * B * Q; r2.res.pitch2D.pitchInBytes = pitch;
+    cudaTextureDesc t2 = {};
+    t2.addressMode[0] = t2.addressMode[1] = cudaAddressModeBorder; t2.readMode = cudaReadModeElementType; t2.normalizedCoords = 0;
+    t2.filterMode = cudaFilterModeLinear;
+    cudaError_t e = cudaCreateTextureObject(&p.tex_p2d, &r2, &t2, nullptr);
+    printf("pitch2D texture %d x %zu pitch %d: %s\n", Wp, (size_t)Hp * B * Q, Wp * 8, cudaGetErrorString(e));
+    if (e != cudaSuccess) { p.tex_p2d = p.tex_lin; cudaGetLastError(); }
+  }
   std::vector<float> ref((size_t)B * P), got((size_t)B * P);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   auto run = [&](int mode, const char *name) {
@@ -180,11 +217,14 @@ int main(int argc, char **argv) {
       CK(cudaMemset(p.out, 0, (size_t)B * P * 4));
       CK(cudaEventRecord(e0));
       switch (mode) {
-        case 0: probe<0><<<148, 512>>>(p); break;
-        case 1: probe<1><<<148, 512>>>(p); break;
-        case 2: probe<2><<<148, 512>>>(p); break;
-        case 3: probe<3><<<148, 512>>>(p); break;
-        case 4: probe<4><<<148, 512>>>(p); break;
+        case 0: probe<0><<<grid, 512>>>(p); break;
+        case 1: probe<1><<<grid, 512>>>(p); break;
+        case 2: probe<2><<<grid, 512>>>(p); break;
+        case 3: probe<3><<<grid, 512>>>(p); break;
+        case 4: probe<4><<<grid, 512>>>(p); break;
+        case 5: probe<5><<<grid, 512>>>(p); break;
+        case 6: probe<6><<<grid, 512>>>(p); break;
+        case 7: probe<7><<<grid, 512>>>(p); break;
       }
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -204,5 +244,8 @@ int main(int argc, char **argv) {
   run(4, "2x LDG.128 pair + HFMA2 blend");
   run(2, "1x TEX linear half4");
   run(3, "4x TEX point half4");
+  run(5, "mixed 2 TEX(p2d) + 2 LSU pair/HFMA2");
+  run(6, "mixed 3 TEX(p2d) + 1 LSU pair/HFMA2");
+  run(7, "4 TEX(p2d folded) + HFMA2 mask");
   return 0;
 }
