@@ -34,7 +34,8 @@ METRIC = "HR frames/sec, 1080p x4 LD-QP37"
 UNIT = "frames/s"
 LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
 ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
-ALGO_BYTES_PER_PX_FP32OFF = 128 + 1152 + 576 + 256  # what this build feeds: bf16 x, fp32 offset/mask, fp32 y
+# dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture (profiles/r01_dcn_tex_ncu.md), per LR pixel
+NCU_TRAFFIC_BYTES_PER_PX = (1.004401e9 + 67.159e6) / (6 * 272 * 480)
 
 
 def peaks():
@@ -245,17 +246,20 @@ def run_ours(args):
         hbm_peak, peak_src = peaks()
         durs = [a.elapsed_time(b) * 1e-3 for a, b, _, _ in dcn_log]           # seconds per launch
         px = dcn_log[0][2] if dcn_log else 0
-        per_px = ALGO_BYTES_PER_PX_FP32OFF if (dcn_log and dcn_log[0][3] == 4) else ALGO_BYTES_PER_PX_BF16
+        per_px = ALGO_BYTES_PER_PX_BF16
         avg = sum(durs) / max(1, len(durs))
         achieved = per_px * px / avg / 1e9 if durs else 0.0
+        kname = ("dcn_tex_sm100_kernel (tcgen05 implicit-GEMM DCNv2 64->64 3x3 dg=16, texture-unit gather)"
+                 if cdfo_b200.config.dcn_gather == "tex" else "dcn_sm100_kernel (tcgen05 implicit-GEMM DCNv2, LDG gather)")
         roof = {
-            "kernel": "dcn_sm100_kernel (tcgen05 implicit-GEMM DCNv2, 64->64 3x3 dg=16)", "bound": "hbm",
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "kernel": kname, "bound": "hbm",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_PX * px if NCU_TRAFFIC_BYTES_PER_PX else None,
             "peak_source": peak_src, "avg_launch_us": avg * 1e6, "launches_timed": len(durs),
             "algorithmic_bytes_per_launch": per_px * px,
-            "note": "bytes/px = %d at this build's I/O widths (bf16 x, fp32 offset+mask, fp32 y); SURVEY 8d's 2-byte-I/O "
-                    "figure is %d B/px -> frac_at_1120 = %.4f" % (per_px, ALGO_BYTES_PER_PX_BF16,
-                                                                 ALGO_BYTES_PER_PX_BF16 * px / avg / 1e9 / hbm_peak if durs else 0.0),
+            "note": "algorithmic bytes = SURVEY 8d's 1120 B per LR pixel and neighbour call (x 128 + offset 576 + mask 288 + y 128) x "
+                    "%d px per launch; this build moves 1536 B/px (fp16 x 128, packed fp16x4 fields 1152, fp32 y 256); traffic = "
+                    "dram bytes per px of the ncu --set full capture in profiles/ scaled to this launch; the binding resource is "
+                    "the L1TEX data stage, see DESIGN.md" % px,
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -10,7 +10,7 @@ import ctypes
 import torch
 import torch.nn.functional as F
 
-from . import _lib, conv, dcn_sm100
+from . import _lib, config, conv, dcn_sm100
 from .priors import flow_warp_chw
 
 # stage -> "cuda" | "aten"
@@ -136,6 +136,8 @@ def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
     `x` may hold fewer samples than the other arguments (sample b uses x[b % x.size(0)]): the model's six
     neighbour calls share the centre-frame feature (arch:4456)."""
     fields = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
+    if config.dcn_gather == "tex":
+        return dcn_sm100.dcn_tex(dcn_sm100.pack_q4t(x), fields, dcn_sm100.pack_weight_f16(mod.weight), mod.bias, mv=flow)
     xq = dcn_sm100.pack_q4p(x)
     return dcn_sm100.dcn_sm100(xq, None, None, dcn_sm100.pack_weight(mod.weight), mod.bias, mv=flow, fused_fields=fields)
 

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--smooth", type=int, default=1, help="block-constant MV-like offsets (1) or i.i.d. random (0)")
     ap.add_argument("--skip-baselines", action="store_true")
+    ap.add_argument("--only-tex", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, H, W, dg = a.B, a.H, a.W, 16
@@ -53,13 +54,14 @@ def main():
     off16, m16 = offset.half(), mask.half()
     P = H * W
     res = {"B": B, "H": H, "W": W, "smooth": a.smooth}
-    t = timeit(lambda: S.dcn_sm100(xc, offset, mask, wpk, bias, num_ctas=a.ctas), a.iters)
-    res["sm100_f32off_us"] = t
-    res["sm100_f32off_GBs_fp32io_2240"] = 2240.0 * P * B / t / 1e3
-    t = timeit(lambda: S.dcn_sm100(xc, off16, m16, wpk, bias, out_c8=True, num_ctas=a.ctas), a.iters)
-    res["sm100_f16off_c8out_us"] = t
-    res["sm100_f16off_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
-    res["pack_q4p_us"] = timeit(lambda: S.pack_q4p(x), a.iters)
+    if not a.only_tex:
+        t = timeit(lambda: S.dcn_sm100(xc, offset, mask, wpk, bias, num_ctas=a.ctas), a.iters)
+        res["sm100_f32off_us"] = t
+        res["sm100_f32off_GBs_fp32io_2240"] = 2240.0 * P * B / t / 1e3
+        t = timeit(lambda: S.dcn_sm100(xc, off16, m16, wpk, bias, out_c8=True, num_ctas=a.ctas), a.iters)
+        res["sm100_f16off_c8out_us"] = t
+        res["sm100_f16off_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
+        res["pack_q4p_us"] = timeit(lambda: S.pack_q4p(x), a.iters)
     o = offset.view(B, dg * 9, 2, H, W)
     fields = torch.stack([o[:, :, 0], o[:, :, 1], mask, torch.zeros_like(mask)], dim=-1).half().contiguous()
     xt, w16 = S.pack_q4t(x), S.pack_weight_f16(wt)
