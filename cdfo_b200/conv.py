@@ -46,9 +46,41 @@ def pack_weight(weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_derived = {}
+
+
 @torch.no_grad()
-def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False):
-    """x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw)."""
+def derived(param, kind, fn):
+    """fn(param) cached per (parameter, version, kind): weights re-laid-out for a kernel (1x1 embedded as the centre tap
+    of a 3x3, PixelShuffle channel order, padded output channels ...).  The result then has its own pack_weight entry."""
+    key = (id(param), kind)
+    hit = _derived.get(key)
+    if hit is not None and hit[0]() is param and hit[1] == param._version:
+        return hit[2]
+    out = fn(param.detach())
+    _derived[key] = (weakref.ref(param), param._version, out)
+    return out
+
+
+def centre_tap(w):
+    """[Cout, Cin, 1, 1] -> [Cout, Cin, 3, 3] with the 1x1 weight at the centre tap."""
+    out = torch.zeros((w.size(0), w.size(1), 3, 3), dtype=torch.float32, device=w.device)
+    out[:, :, 1, 1] = w.float().reshape(w.size(0), w.size(1))
+    return out
+
+
+def ps_order(t):
+    """Rows of a weight / bias reordered for the pixel-shuffle epilogue: new row (2i+j)*(Cout/4) + c <- row 4c + 2i + j."""
+    cout = t.size(0)
+    c = torch.arange(cout // 4, device=t.device)
+    idx = torch.cat([4 * c + q for q in range(4)])
+    return t.index_select(0, idx).contiguous()
+
+
+@torch.no_grad()
+def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False):
+    """x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw, or
+    [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) when pixel_shuffle and the weight rows are in ps_order)."""
     B, C8, H, W, _ = x8.shape
     Cout, Cin = weight.shape[:2]
     if C8 * 8 != Cin or tuple(weight.shape[2:]) != (3, 3):
@@ -57,12 +89,31 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False):
         raise _lib.CdfoError("conv3x3: input must be a contiguous bf16 c8 tensor")
     wpk = pack_weight(weight)
     b = None if bias is None else bias.detach().contiguous().float()
-    if out_nchw:
+    if pixel_shuffle:
+        y = torch.empty((B, Cout // 32, 2 * H, 2 * W, 8), dtype=torch.bfloat16, device=x8.device)
+    elif out_nchw:
         y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x8.device)
     else:
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
     if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16):
         raise _lib.CdfoError("conv3x3: residual must be a bf16 c8 tensor of the output shape")
     _lib.call("cdfo_conv3x3_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y),
-              B, Cin, Cout, H, W, int(act), 0 if out_nchw else 1, _lib.stream_ptr(x8.device))
+              B, Cin, Cout, H, W, int(act), 2 if pixel_shuffle else (0 if out_nchw else 1), _lib.stream_ptr(x8.device))
+    return y
+
+
+@torch.no_grad()
+def conv_last_skip(x8, weight, bias, lr):
+    """conv_last (Cin -> 1, 3x3) + bias + bilinear x4 skip of the 1-channel LR image lr [B,1,H/4,W/4] (arch:4477-4480).
+    x8 [B, Cin/8, H, W, 8] bf16 -> [B, 1, H, W] fp32."""
+    B, C8, H, W, _ = x8.shape
+    w16 = derived(weight, "pad16", lambda w: torch.cat([w.float(), torch.zeros((15,) + tuple(w.shape[1:]), device=w.device)], 0).contiguous())
+    wpk = pack_weight(w16)
+    y = torch.empty((B, 1, H, W), dtype=torch.float32, device=x8.device)
+    b = bias.detach().float().contiguous()
+    lr = lr.contiguous().float()
+    if lr.shape != (B, 1, H // 4, W // 4):
+        raise _lib.CdfoError("conv_last_skip: LR image %s does not match the %dx%d output" % (tuple(lr.shape), H, W))
+    _lib.call("cdfo_conv_last_skip_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(lr), _lib.ptr(y), B, C8 * 8, H, W,
+              _lib.stream_ptr(x8.device))
     return y

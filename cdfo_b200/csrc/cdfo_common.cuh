@@ -40,6 +40,15 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Source coordinate of flow_warp's normalise (python, arch/SIDECVSR_our.py:3093-3094) / un-normalise (ATen
+// grid_sampler, align_corners=True) round trip, replayed with explicit round-to-nearest ops so that floor() indices are
+// bit-exact against the reference arithmetic.
+__device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
+  const float v = __fadd_rn((float)pos, flow);                                              // grid + flow
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)max(size - 1, 1)), 1.0f);  // 2*v/max(s-1,1) - 1
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));                 // ((g+1)/2)*(s-1)
+}
+
 }  // namespace cdfo
 
 #define CDFO_REQUIRE(cond, code, ...)                 \

@@ -36,12 +36,15 @@ struct Conv3x3Params {
   void *y;
   int B, Cin, Cout, H, W;
   int act;       // 0 none, 1 relu, 2 leaky relu 0.1
-  int out_mode;  // 0: NCHW fp32, 1: c8 bf16
+  int out_mode;  // 0: NCHW fp32, 1: c8 bf16, 2: c8 bf16 through PixelShuffle(2): output channels arrive ordered
+                 //    n' = (2i+j)*(Cout/4) + c and leave at [B][Cout/32][2H][2W][8], pixel (2h+i, 2w+j)
   // epi 0: bias -> act -> +resid.
   // Offset/mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3341-3350): output channels arrive permuted as triples
   // (dy_k, dx_k, m_k), k = g*9 + tap, and leave as one fp16x4 "field" (dy, dx, m, 0) per (k, pixel): y [B][Cout/3][H][W] x 8 B
   // epi 1: (mag*tanh(dy), mag*tanh(dx), m)                                   (first head evaluation)
   // epi 2: (aux.dy + mag*tanh(dy), aux.dx + mag*tanh(dx), sigmoid(aux.m + m)) (second evaluation; aux = epi-1 output)
+  // epi 3: channel 0 only (+ bias) + bilinear x4 skip of a 1-channel LR image (aux = float [B][H/4][W/4], align_corners=False):
+  //        conv_last + base of the tail, arch/SIDECVSR_our.py:4477-4480; y = fp32 [B][1][H][W]
   int epi;
   float mag;
   const uint2 *aux;
@@ -178,6 +181,28 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       const size_t pix = (size_t)h * p.W + w;
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
+      if (p.epi == 3) {
+        uint32_t rr[16];
+        tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16), rr);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(BAR(10 + acc));
+        if (live) {
+          // F.interpolate(scale_factor=4, bilinear, align_corners=False): src = max((dst + 0.5) / 4 - 0.5, 0)
+          const int Hl = p.H >> 2, Wl = p.W >> 2;
+          const float sy = fmaxf(((float)h + 0.5f) * 0.25f - 0.5f, 0.f), sx = fmaxf(((float)w + 0.5f) * 0.25f - 0.5f, 0.f);
+          const int y0 = (int)sy, x0 = (int)sx;
+          const int y1 = min(y0 + 1, Hl - 1), x1 = min(x0 + 1, Wl - 1);
+          const float ly = sy - (float)y0, lx = sx - (float)x0;
+          const float *lr = reinterpret_cast<const float *>(p.aux) + (size_t)b * Hl * Wl;
+          const float base = (1.f - ly) * ((1.f - lx) * __ldg(lr + y0 * Wl + x0) + lx * __ldg(lr + y0 * Wl + x1)) +
+                             ly * ((1.f - lx) * __ldg(lr + y1 * Wl + x0) + lx * __ldg(lr + y1 * Wl + x1));
+          reinterpret_cast<float *>(p.y)[(size_t)b * HW + pix] = __uint_as_float(rr[0]) + bias_s[0] + base;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (p.epi != 0) {
         if constexpr (NT % 48 == 0) {
 #pragma unroll 1
@@ -264,6 +289,16 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
           float *y = reinterpret_cast<float *>(p.y) + ((size_t)b * p.Cout + n0 + c0) * HW + pix;
 #pragma unroll
           for (int i = 0; i < 16; ++i) y[(size_t)i * HW] = v[i];
+        } else if (p.out_mode == 2) {
+          const int cps = p.Cout >> 2;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int n = n0 + c0 + half * 8, q = n / cps, kc = (n - q * cps) >> 3;
+            uint4 *y = reinterpret_cast<uint4 *>(p.y) +
+                       (((size_t)b * (cps >> 3) + kc) * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
+            *y = make_uint4(cv_pack_bf2(v[half * 8 + 0], v[half * 8 + 1]), cv_pack_bf2(v[half * 8 + 2], v[half * 8 + 3]),
+                            cv_pack_bf2(v[half * 8 + 4], v[half * 8 + 5]), cv_pack_bf2(v[half * 8 + 6], v[half * 8 + 7]));
+          }
         } else {
           uint4 *y = reinterpret_cast<uint4 *>(p.y) + ((size_t)b * (p.Cout / 8) + (n0 + c0) / 8) * HW + pix;
           y[0] = make_uint4(cv_pack_bf2(v[0], v[1]), cv_pack_bf2(v[2], v[3]), cv_pack_bf2(v[4], v[5]), cv_pack_bf2(v[6], v[7]));
@@ -380,13 +415,22 @@ extern "C" int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, 
   return conv3x3_run(z_c8, wpk, bias, nullptr, out, B, Cin, dg * 27, H, W, 0, 0, first ? 2 : 1, magnitude, first, stream);
 }
 
+extern "C" int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const float *lr, float *y, int B,
+                                             int Cin, int H, int W, void *stream) {
+  CDFO_REQUIRE(lr, CDFO_ERR_NULL, "cdfo_conv_last_skip_sm100_fwd: NULL pointer");
+  return conv3x3_run(x_c8, wpk, bias, nullptr, y, B, Cin, 16, H, W, 0, 0, 3, 0.f, lr, stream);
+}
+
 static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
                        int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_sm100_fwd: bad shape");
   CDFO_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, CDFO_ERR_UNSUPPORTED,
                "cdfo_conv3x3_sm100_fwd: Cin must be a multiple of 64 and Cout of 16 (got %d -> %d)", Cin, Cout);
-  CDFO_REQUIRE(act >= 0 && act <= 2 && (out_mode == 0 || out_mode == 1), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: act/out_mode");
+  CDFO_REQUIRE(act >= 0 && act <= 2 && out_mode >= 0 && out_mode <= 2, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: act/out_mode");
+  CDFO_REQUIRE(out_mode != 2 || (Cout % 32 == 0 && resid_c8 == nullptr), CDFO_ERR_UNSUPPORTED,
+               "cdfo_conv3x3_sm100_fwd: pixel-shuffle output needs Cout %% 32 == 0 and no residual");
+  CDFO_REQUIRE(epi != 3 || (H % 4 == 0 && W % 4 == 0 && aux), CDFO_ERR_SHAPE, "cdfo_conv_last_skip_sm100_fwd: H, W must be multiples of 4");
   CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & (epi ? 7 : 15)) == 0, CDFO_ERR_SHAPE,
                "cdfo_conv3x3_sm100_fwd: pointers must be 16-byte aligned");
   const int nt = conv3x3_ntile(Cout, Cin);

@@ -55,6 +55,9 @@ struct Params {
   void *y;
   int B, H, W, dg, out_mode, gshift, x_batch;
   long long f_bstride;               // uint2 elements between samples of fields
+  // c8 output placement: sample s goes to 8-channel chunks [(s % y_nb) * y_cs + y_grp[s / y_nb], +8) of y
+  // (dense: y_nb = B, y_cs = 8, y_grp[0] = 0; stacked for tsa_fusion: y_nb = sequences, y_cs = 56, y_grp = frame slot * 8)
+  int y_nb, y_cs, y_grp[8];
   int tiles_x, tiles_per_img, num_tiles;
 };
 
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
 #pragma unroll
             for (int n = 0; n < 32; ++n) __stcs(y + (size_t)n * P, __uint_as_float(r[n]) + bias_s[half * 32 + n]);
           } else {
-            uint4 *y = reinterpret_cast<uint4 *>(p.y) + ((size_t)tc.b * 8 + half * 4) * P + pix;
+            uint4 *y = reinterpret_cast<uint4 *>(p.y) + ((size_t)(tc.b % p.y_nb) * p.y_cs + p.y_grp[tc.b / p.y_nb] + half * 4) * P + pix;
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
               uint4 v;
@@ -407,9 +410,29 @@ extern "C" int cdfo_dcn_tex_sm100_pack_weight(const float *w, void *wpk, void *s
   return check_launch("cdfo_dcn_tex_sm100_pack_weight");
 }
 
+static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias, void *y, int B,
+                       int H, int W, int dg, int out_mode, int num_ctas, int x_batch, long long fields_bstride, int y_nb, int y_cs,
+                       const int *y_grp, void *stream);
+
 extern "C" int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk,
                                       const float *bias, void *y, int B, int H, int W, int dg, int out_mode,
                                       int num_ctas, int x_batch, long long fields_bstride, void *stream) {
+  const int grp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  return dcn_tex_run(x_q4t, fields, mv, wpk, bias, y, B, H, W, dg, out_mode, num_ctas, x_batch, fields_bstride, B, 8, grp, stream);
+}
+
+extern "C" int cdfo_dcn_tex_sm100_stacked_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk,
+                                              const float *bias, void *y_stack, int n_seq, int n_groups, int stack_chunks,
+                                              const int *group_chunk, int H, int W, int dg, int x_batch, void *stream) {
+  CDFO_REQUIRE(n_seq > 0 && n_groups > 0 && n_groups <= 8 && group_chunk, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_stacked_fwd: 1..8 groups");
+  for (int g = 0; g < n_groups; ++g)
+    CDFO_REQUIRE(group_chunk[g] >= 0 && group_chunk[g] + 8 <= stack_chunks, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_stacked_fwd: chunk slot out of range");
+  return dcn_tex_run(x_q4t, fields, mv, wpk, bias, y_stack, n_seq * n_groups, H, W, dg, 1, 0, x_batch, 0, n_seq, stack_chunks, group_chunk, stream);
+}
+
+static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias, void *y, int B,
+                       int H, int W, int dg, int out_mode, int num_ctas, int x_batch, long long fields_bstride, int y_nb, int y_cs,
+                       const int *y_grp, void *stream) {
   CDFO_REQUIRE(x_q4t && fields && wpk && y, CDFO_ERR_NULL, "cdfo_dcn_tex_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: bad shape");
   CDFO_REQUIRE(dg == 1 || dg == 2 || dg == 4 || dg == 8 || dg == 16, CDFO_ERR_UNSUPPORTED,
@@ -433,6 +456,8 @@ extern "C" int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, con
   }
   p.fields = (const uint2 *)fields; p.mv = mv; p.wpk = (const uint8_t *)wpk; p.bias = bias; p.y = y;
   p.B = B; p.H = H; p.W = W; p.dg = dg; p.out_mode = out_mode;
+  p.y_nb = y_nb; p.y_cs = y_cs;
+  for (int g = 0; g < 8; ++g) p.y_grp[g] = y_grp[g];
   p.f_bstride = fields_bstride > 0 ? fields_bstride : (long long)dg * 9 * H * W;
   p.gshift = 0;
   while ((16 >> p.gshift) > dg) ++p.gshift;

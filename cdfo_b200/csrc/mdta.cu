@@ -1,0 +1,500 @@
+// Dual channel attention ("MDTA") of the alignment modules, fused:
+//   MVDualAttAlignment.forward  arch/SIDECVSR_our.py:3303-3337  (8 heads x 8 channels, fusion_out without ReLU)   mode 0
+//   DualAttAlignment.forward    arch/SIDECVSR_our.py:3455-3492  (4 heads x 16 channels, ReLU after fusion_out)    mode 1
+//
+// Reference chain per call (~30 ATen launches): flow_warp, cat, 1x1 conv, two global average pools + 64->4->64 gates,
+// L2-normalise q and k over H*W, per-head q k^T (contraction over H*W), * temperature, softmax over 8/16 channels,
+// attn @ v (twice, v = warped*g and pred*g), project_out 1x1 (twice).  Algebra used here:
+//   * q = x and k = fused are the same in both passes, so the softmax matrix A (block diagonal, 64 x hc) is shared;
+//   * attn @ (v * gate) followed by project_out is linear per pixel:  o1 = M1 warped,  o2 = M2 pred  with
+//     M = P . blockdiag(A) . diag(gate)  (64 x 64 per sample);  mode 1 additionally folds the second fusion_out
+//     (arch:3492):  out = ReLU(Wa (o1 + o2) + Wb x) = ReLU((Wa M1) warped + (Wa M2) pred + Wb x).
+// Three kernels, fp32 CUDA-core arithmetic (the contractions are 64-wide per pixel; the op is bound by HBM and the
+// shared-memory pipe, not by the tensor cores):
+//   1. mdta_stats_kernel   gathers warped (flow_warp index arithmetic of csrc/priors.cu), computes fused = Wf [warped; pred]
+//                          per 128-pixel tile with a register-tiled shared-memory GEMM, and accumulates in registers,
+//                          across the tiles of a persistent CTA: sum warped, sum pred, sum x^2, sum fused^2 and the
+//                          per-head Gram x_c . fused_c'.  Writes warped (needed again in 3) and per-CTA partials.
+//   2. mdta_attn_kernel    per sample: fixed-order reduction of the partials (deterministic), gates, normalisation,
+//                          temperature, softmax by warp shuffles, the M matrices (transposed for kernel 3).
+//   3. mdta_apply_kernel   per pixel o1 = M1 warped, o2 = M2 pred -> c8 bf16 [2B] (mode 0: the input of conv_offset.0)
+//                          or ReLU(MA warped + MB pred + MC x) -> NCHW fp32 + channel sums for CALayer (mode 1).
+// Bytes per pixel and call (fp32 NCHW inputs): 1 reads extra (gather) 256 + pred 256 + x 256 + flow 8, writes warped 256;
+// 3 reads warped 256 + pred 256 (+ x 256), writes 256: ~1.8-2.3 kB/px -> 0.04 ms per call at c3 at HBM peak.
+#include "cdfo_common.cuh"
+
+namespace cdfo {
+namespace mdta {
+
+constexpr int kTP = 128;       // pixels per tile
+constexpr int kLd = 132;       // row stride in floats of a [64][kTP] tile: 16-byte aligned rows, conflict-free float4 columns
+constexpr int kThreads = 256;
+constexpr int kMaxParts = 64;
+
+__host__ __device__ inline int stats_len(int hc) { return 256 + 64 * hc; }
+
+struct StatsParams {
+  const float *x, *extra, *pred, *flow, *wf;   // wf = fusion_out weight [64][128]
+  float *warped, *partial;                     // partial [B][parts][stats_len]
+  int H, W, x_batch, hc, relu;
+};
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// out[8][4] += A^T[k][cb*8 .. +7] * in[k][pg*4 .. +3] for k in [0, K)
+__device__ __forceinline__ void tile_gemm(float (&acc)[8][4], const float *__restrict__ aT, const float *__restrict__ in,
+                                          int K, int cb, int pg) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 a0 = ld4(aT + k * 64 + cb * 8), a1 = ld4(aT + k * 64 + cb * 8 + 4);
+    const float4 v = ld4(in + k * kLd + pg * 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float *Wt = sm;                    // [64][kLd] warped, later fused
+  float *Pt = Wt + 64 * kLd;         // [64][kLd] pred
+  float *Xt = Pt + 64 * kLd;         // [64][kLd] x (query)
+  float *WfT = Xt + 64 * kLd;        // [128][64] fusion_out weight, transposed
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  const int HW = p.H * p.W;
+  const int ntiles = (HW + kTP - 1) / kTP;
+  const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
+  for (int e = tid; e < 64 * 128; e += kThreads) WfT[(e & 127) * 64 + (e >> 7)] = p.wf[e];
+  const float *xs = p.x + (size_t)(b % p.x_batch) * 64 * HW;
+  const float *ex = p.extra + (size_t)b * 64 * HW;
+  const float *pr = p.pred + (size_t)b * 64 * HW;
+  float *wo = p.warped + (size_t)b * 64 * HW;
+  const int hc = p.hc, npairs = 64 * hc;
+  float rs = 0.f, g[4] = {0.f, 0.f, 0.f, 0.f};
+  const int cb = tid >> 5, pg = tid & 31;
+
+  for (int tile = t0; tile < t1; ++tile) {
+    const int p0 = tile * kTP, npx = min(kTP, HW - p0);
+    __syncthreads();   // previous tile's readers are done (and WfT is complete on the first pass)
+    {  // ---- A: gather warped, load pred and x
+      const int px = tid & 127, half = tid >> 7;
+      const int pp = p0 + px;
+      const bool valid = px < npx;
+      int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+      float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
+      if (valid) {
+        const int h = pp / p.W, w = pp - h * p.W;
+        const float ix = warp_src_coord(w, __ldg(p.flow + ((size_t)b * 2 + 0) * HW + pp), p.W);
+        const float iy = warp_src_coord(h, __ldg(p.flow + ((size_t)b * 2 + 1) * HW + pp), p.H);
+        const float fx = floorf(ix), fy = floorf(iy);
+        // clamp before the int conversion: +-inf / NaN flows (mv2mvs keeps x/0 = inf) must not index out of range
+        const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)p.W), y0 = (int)fminf(fmaxf(fy, -2.f), (float)p.H);
+        const int x1 = x0 + 1, y1 = y0 + 1;
+        const float tx1 = __fsub_rn((float)x1, ix), tx0 = __fsub_rn(ix, fx);
+        const float ty1 = __fsub_rn((float)y1, iy), ty0 = __fsub_rn(iy, fy);
+        const bool oy0 = y0 >= 0 && y0 < p.H, oy1 = y1 >= 0 && y1 < p.H, ox0 = x0 >= 0 && x0 < p.W, ox1 = x1 >= 0 && x1 < p.W;
+        const bool fin = fx == fx && fy == fy && fabsf(fx) < 1e9f && fabsf(fy) < 1e9f;
+        nw = (fin && oy0 && ox0) ? tx1 * ty1 : 0.f; ne = (fin && oy0 && ox1) ? tx0 * ty1 : 0.f;
+        sw = (fin && oy1 && ox0) ? tx1 * ty0 : 0.f; se = (fin && oy1 && ox1) ? tx0 * ty0 : 0.f;
+        const int cy0 = min(max(y0, 0), p.H - 1), cy1 = min(max(y1, 0), p.H - 1);
+        const int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x1, 0), p.W - 1);
+        o00 = cy0 * p.W + cx0; o01 = cy0 * p.W + cx1; o10 = cy1 * p.W + cx0; o11 = cy1 * p.W + cx1;
+      }
+#pragma unroll 4
+      for (int c = half * 32; c < half * 32 + 32; ++c) {
+        float v = 0.f;
+        if (valid) {
+          const float *plane = ex + (size_t)c * HW;
+          // same accumulation order as grid_sample: nw, ne, sw, se
+          v = __ldg(plane + o00) * nw;
+          v += __ldg(plane + o01) * ne;
+          v += __ldg(plane + o10) * sw;
+          v += __ldg(plane + o11) * se;
+          wo[(size_t)c * HW + pp] = v;
+        }
+        Wt[c * kLd + px] = v;
+      }
+      for (int e = tid; e < 64 * kTP; e += kThreads) {
+        const int c = e >> 7, q = e & 127;
+        const bool ok = q < npx;
+        Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
+        Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- B: row sums of warped / pred / x^2, then fused = Wf [warped; pred]
+    if (tid < 192) {
+      const int role = tid >> 6, c = tid & 63;
+      const float *row = (role == 0 ? Wt : (role == 1 ? Pt : Xt)) + c * kLd;
+      float s = 0.f;
+      if (role == 2) {
+#pragma unroll 8
+        for (int q = 0; q < kTP; q += 4) { const float4 v = ld4(row + q); s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+      } else {
+#pragma unroll 8
+        for (int q = 0; q < kTP; q += 4) { const float4 v = ld4(row + q); s += (v.x + v.y) + (v.z + v.w); }
+      }
+      rs += s;
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    tile_gemm(acc, WfT, Wt, 64, cb, pg);
+    tile_gemm(acc, WfT + 64 * 64, Pt, 64, cb, pg);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      *reinterpret_cast<float4 *>(Wt + (cb * 8 + i) * kLd + pg * 4) = v;
+    }
+    __syncthreads();
+    // ---- C: sum fused^2 and the per-head Gram
+    if (tid >= 192) {
+      const float *row = Wt + (tid - 192) * kLd;
+      float s = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < kTP; q += 4) { const float4 v = ld4(row + q); s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+      rs += s;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = tid + kThreads * j;
+      if (e < npairs) {
+        const int c = e / hc, c2 = (c / hc) * hc + (e - c * hc);
+        const float *xr = Xt + c * kLd, *fr = Wt + c2 * kLd;
+        float s = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < kTP; q += 4) {
+          const float4 a = ld4(xr + q), f = ld4(fr + q);
+          s += a.x * f.x + a.y * f.y + a.z * f.z + a.w * f.w;
+        }
+        g[j] += s;
+      }
+    }
+  }
+  float *out = p.partial + ((size_t)b * parts + part) * stats_len(hc);
+  out[tid] = rs;   // [0,64) sum warped, [64,128) sum pred, [128,192) sum x^2, [192,256) sum fused^2
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = tid + kThreads * j;
+    if (e < npairs) out[256 + e] = g[j];
+  }
+}
+
+struct AttnParams {
+  const float *partial;             // [B][parts][stats_len]
+  const float *du_w1, *du_b1, *du_w2, *du_b2;   // conv_du: [4][64], [4], [64][4], [64]
+  const float *temperature;         // [heads]
+  const float *proj;                // project_out weight [64][64]
+  const float *fold;                // mode 1: fusion_out weight [64][128] (Wa | Wb); mode 0: nullptr
+  float *mats;                      // [B][3][64][64] transposed: mats[b][m][k][o]
+  int parts, hc, HW;
+};
+
+__global__ void __launch_bounds__(256) mdta_attn_kernel(const AttnParams p) {
+  __shared__ float st[256 + 64 * 16];
+  __shared__ float gate[2][64];
+  __shared__ float hid[2][4];
+  __shared__ float A[64 * 16];       // A[c][j]: softmax over the hc channels c' = head(c)*hc + j
+  __shared__ float M[2][64 * 65];    // M[m][o][c']
+  const int tid = threadIdx.x, b = blockIdx.x, hc = p.hc, S = stats_len(hc);
+  for (int e = tid; e < S; e += 256) {
+    float s = 0.f;
+    for (int q = 0; q < p.parts; ++q) s += p.partial[((size_t)b * p.parts + q) * S + e];   // fixed order
+    st[e] = s;
+  }
+  __syncthreads();
+  const float inv_hw = 1.f / (float)p.HW;
+  if (tid < 8) {   // conv_du.0 + ReLU on the two pooled vectors
+    const int which = tid >> 2, j = tid & 3;
+    float s = p.du_b1[j];
+    for (int c = 0; c < 64; ++c) s = fmaf(p.du_w1[j * 64 + c], st[which * 64 + c] * inv_hw, s);
+    hid[which][j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int which = tid >> 6, c = tid & 63;
+    float s = p.du_b2[c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s = fmaf(p.du_w2[c * 4 + j], hid[which][j], s);
+    gate[which][c] = 1.f / (1.f + expf(-s));
+  }
+  // logits -> softmax over j (rows of hc entries); one thread per row is plenty (64 rows)
+  if (tid >= 128 && tid < 192) {
+    const int c = tid - 128, head = c / hc;
+    const float nq = fmaxf(sqrtf(st[128 + c]), 1e-12f), t = p.temperature[head];
+    float lg[16], mx = -INFINITY;
+    for (int j = 0; j < hc; ++j) {
+      const float nk = fmaxf(sqrtf(st[192 + head * hc + j]), 1e-12f);
+      lg[j] = st[256 + c * hc + j] / (nq * nk) * t;
+      mx = fmaxf(mx, lg[j]);
+    }
+    float ds = 0.f;
+    for (int j = 0; j < hc; ++j) { lg[j] = expf(lg[j] - mx); ds += lg[j]; }
+    for (int j = 0; j < hc; ++j) A[c * hc + j] = lg[j] / ds;
+  }
+  __syncthreads();
+  // M_m[o][c'] = gate_m[c'] * sum_{c in head(c')} P[o][c] A[c][c' - head*hc]
+  for (int e = tid; e < 2 * 4096; e += 256) {
+    const int m = e >> 12, o = (e >> 6) & 63, c2 = e & 63, head = c2 / hc, j = c2 - head * hc;
+    float s = 0.f;
+    for (int i = 0; i < hc; ++i) s = fmaf(p.proj[o * 64 + head * hc + i], A[(head * hc + i) * hc + j], s);
+    M[m][o * 65 + c2] = s * gate[m][c2];
+  }
+  __syncthreads();
+  float *mats = p.mats + (size_t)b * 3 * 4096;
+  if (!p.fold) {
+    for (int e = tid; e < 2 * 4096; e += 256) {
+      const int m = e >> 12, k = (e >> 6) & 63, o = e & 63;
+      mats[m * 4096 + k * 64 + o] = M[m][o * 65 + k];
+    }
+  } else {
+    for (int e = tid; e < 3 * 4096; e += 256) {
+      const int m = e >> 12, k = (e >> 6) & 63, o = e & 63;
+      float s;
+      if (m == 2) {
+        s = p.fold[o * 128 + 64 + k];                       // Wb
+      } else {
+        s = 0.f;
+        for (int i = 0; i < 64; ++i) s = fmaf(p.fold[o * 128 + i], M[m][i * 65 + k], s);   // (Wa M_m)[o][k]
+      }
+      mats[m * 4096 + k * 64 + o] = s;
+    }
+  }
+}
+
+struct ApplyParams {
+  const float *warped, *pred, *x;
+  const float *mats;      // [B][3][64][64] transposed
+  void *out;              // mode 0: c8 bf16 [2B][8][HW][8]; mode 1: NCHW fp32 [B][64][HW]
+  float *ca_partial;      // mode 1: [B][parts][64] channel sums of out
+  int H, W, B, x_batch, mode;
+};
+
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float *Wt = sm, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
+  float *MT = Xt + 64 * kLd;         // [3][64][64]
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  const int HW = p.H * p.W;
+  const int ntiles = (HW + kTP - 1) / kTP;
+  const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
+  const int nm = p.mode == 1 ? 3 : 2;
+  for (int e = tid; e < nm * 4096; e += kThreads) MT[e] = p.mats[(size_t)b * 3 * 4096 + e];
+  const float *wp = p.warped + (size_t)b * 64 * HW, *pr = p.pred + (size_t)b * 64 * HW;
+  const float *xs = p.x ? p.x + (size_t)(b % p.x_batch) * 64 * HW : nullptr;
+  const int cb = tid >> 5, pg = tid & 31;
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tile = t0; tile < t1; ++tile) {
+    const int p0 = tile * kTP, npx = min(kTP, HW - p0);
+    __syncthreads();
+    for (int e = tid; e < 64 * kTP; e += kThreads) {
+      const int c = e >> 7, q = e & 127;
+      const bool ok = q < npx;
+      Wt[c * kLd + q] = ok ? __ldg(wp + (size_t)c * HW + p0 + q) : 0.f;
+      Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
+      if (p.mode == 1) Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+    }
+    __syncthreads();
+    float a1[8][4], a2[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
+    tile_gemm(a1, MT, Wt, 64, cb, pg);
+    if (p.mode == 0) {
+      tile_gemm(a2, MT + 4096, Pt, 64, cb, pg);
+      uint4 *z = reinterpret_cast<uint4 *>(p.out);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = pg * 4 + j;
+        if (q < npx) {
+          z[((size_t)b * 8 + cb) * HW + p0 + q] = make_uint4(bf2(a1[0][j], a1[1][j]), bf2(a1[2][j], a1[3][j]),
+                                                              bf2(a1[4][j], a1[5][j]), bf2(a1[6][j], a1[7][j]));
+          z[((size_t)(p.B + b) * 8 + cb) * HW + p0 + q] = make_uint4(bf2(a2[0][j], a2[1][j]), bf2(a2[2][j], a2[3][j]),
+                                                                      bf2(a2[4][j], a2[5][j]), bf2(a2[6][j], a2[7][j]));
+        }
+      }
+    } else {
+      tile_gemm(a1, MT + 4096, Pt, 64, cb, pg);
+      tile_gemm(a1, MT + 2 * 4096, Xt, 64, cb, pg);
+      float *o = reinterpret_cast<float *>(p.out) + (size_t)b * 64 * HW;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = pg * 4 + j;
+          const float v = fmaxf(a1[i][j], 0.f);
+          if (q < npx) {
+            o[(size_t)(cb * 8 + i) * HW + p0 + q] = v;
+            csum[i] += v;
+          }
+        }
+      }
+    }
+  }
+  if (p.mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = csum[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (pg == 0) p.ca_partial[((size_t)b * parts + part) * 64 + cb * 8 + i] = s;
+    }
+  }
+}
+
+// gate[b][c] = sigmoid(W2 relu(W1 mean + b1) + b2), mean = sum of per-part channel sums / HW   (CALayer, arch:2032-2043)
+__global__ void channel_gate_kernel(const float *__restrict__ partial, int parts, float inv_hw, const float *__restrict__ w1,
+                                    const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
+                                    int C, int Cmid, float *__restrict__ gate) {
+  extern __shared__ float s[];
+  float *mean = s, *hid = s + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int q = 0; q < parts; ++q) a += partial[((size_t)b * parts + q) * C + c];
+    mean[c] = a * inv_hw;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cmid; j += blockDim.x) {
+    float a = b1 ? b1[j] : 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w1[j * C + c], mean[c], a);
+    hid[j] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2 ? b2[c] : 0.f;
+    for (int j = 0; j < Cmid; ++j) a = fmaf(w2[c * Cmid + j], hid[j], a);
+    gate[(size_t)b * C + c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// NCHW fp32 * scale[b][c] -> c8 bf16
+__global__ void pack_c8_scaled_kernel(const float *__restrict__ x, const float *__restrict__ scale, uint4 *__restrict__ out, int C,
+                                      int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  const float *src = x + ((size_t)b * C + c8 * 8) * HW + p;
+  const float *sc = scale + (size_t)b * C + c8 * 8;
+  uint32_t v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = bf2(src[(size_t)(2 * i) * HW] * sc[2 * i], src[(size_t)(2 * i + 1) * HW] * sc[2 * i + 1]);
+  out[((size_t)b * (C / 8) + c8) * HW + p] = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// c8 bf16 -> NCHW fp32, + add[b % add_batch] (NCHW fp32)
+__global__ void unpack_c8_add_kernel(const uint4 *__restrict__ in, const float *__restrict__ add, int add_batch, float *__restrict__ y,
+                                     int C, int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  const uint4 raw = in[((size_t)b * (C / 8) + c8) * HW + p];
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float *dst = y + ((size_t)b * C + c8 * 8) * HW + p;
+  const float *a = add + ((size_t)(b % add_batch) * C + c8 * 8) * HW + p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    dst[(size_t)(2 * i) * HW] = __uint_as_float(w[i] << 16) + a[(size_t)(2 * i) * HW];
+    dst[(size_t)(2 * i + 1) * HW] = __uint_as_float(w[i] & 0xffff0000u) + a[(size_t)(2 * i + 1) * HW];
+  }
+}
+
+static int parts_for(int B) {
+  int parts = (2 * kNumSMs) / (B > 0 ? B : 1);
+  if (parts < 1) parts = 1;
+  if (parts > kMaxParts) parts = kMaxParts;
+  return parts;
+}
+
+}  // namespace mdta
+}  // namespace cdfo
+
+using namespace cdfo;
+
+// workspace layout (floats): partial [B][parts][256 + 64*hc] | mats [B][3][4096] | warped [B][64][HW]
+extern "C" size_t cdfo_mdta_workspace_bytes(int B, int H, int W, int heads) {
+  if (B <= 0 || H <= 0 || W <= 0 || (heads != 4 && heads != 8)) return 0;
+  const int parts = mdta::parts_for(B), hc = 64 / heads;
+  return ((size_t)B * parts * mdta::stats_len(hc) + (size_t)B * 3 * 4096 + (size_t)B * 64 * H * W) * 4;
+}
+
+extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, const float *pred, const float *flow,
+                             const float *fusion_w, const float *du_w1, const float *du_b1, const float *du_w2,
+                             const float *du_b2, const float *temperature, const float *proj_w, int heads, int mode,
+                             void *out, float *ca_sums, void *workspace, int B, int H, int W, void *stream) {
+  CDFO_REQUIRE(x && extra && pred && flow && fusion_w && du_w1 && du_b1 && du_w2 && du_b2 && temperature && proj_w && out && workspace,
+               CDFO_ERR_NULL, "cdfo_mdta_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, CDFO_ERR_SHAPE, "cdfo_mdta_fwd: bad shape");
+  CDFO_REQUIRE(heads == 4 || heads == 8, CDFO_ERR_UNSUPPORTED, "cdfo_mdta_fwd: 4 or 8 heads over 64 channels (got %d)", heads);
+  CDFO_REQUIRE(mode == 0 || mode == 1, CDFO_ERR_UNSUPPORTED, "cdfo_mdta_fwd: mode %d", mode);
+  CDFO_REQUIRE(mode == 0 || ca_sums, CDFO_ERR_NULL, "cdfo_mdta_fwd: mode 1 needs ca_sums");
+  if (x_batch <= 0) x_batch = B;
+  CDFO_REQUIRE(B % x_batch == 0, CDFO_ERR_SHAPE, "cdfo_mdta_fwd: B (%d) must be a multiple of x_batch (%d)", B, x_batch);
+  CDFO_REQUIRE((((uintptr_t)x | (uintptr_t)extra | (uintptr_t)pred | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0, CDFO_ERR_SHAPE,
+               "cdfo_mdta_fwd: tensors must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int parts = mdta::parts_for(B), hc = 64 / heads, HW = H * W;
+  float *ws = (float *)workspace;
+  float *partial = ws;
+  float *mats = partial + (size_t)B * parts * mdta::stats_len(hc);
+  float *warped = mats + (size_t)B * 3 * 4096;
+  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 128 * 64) * 4, smem3 = (size_t)(3 * 64 * mdta::kLd + 3 * 4096) * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e1 = cudaFuncSetAttribute(mdta::mdta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaError_t e2 = cudaFuncSetAttribute(mdta::mdta_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return fail(CDFO_ERR_CUDA, "cdfo_mdta_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    attr = true;
+  }
+  mdta::StatsParams sp{x, extra, pred, flow, fusion_w, warped, partial, H, W, x_batch, hc, mode == 1 ? 1 : 0};
+  mdta::mdta_stats_kernel<<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
+  mdta::AttnParams ap{partial, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, mode == 1 ? fusion_w : nullptr, mats, parts, hc, HW};
+  mdta::mdta_attn_kernel<<<B, 256, 0, s>>>(ap);
+  mdta::ApplyParams pp{warped, pred, x, mats, out, ca_sums, H, W, B, x_batch, mode};
+  mdta::mdta_apply_kernel<<<dim3(parts, B), mdta::kThreads, smem3, s>>>(pp);
+  return check_launch("cdfo_mdta_fwd");
+}
+
+extern "C" int cdfo_mdta_parts(int B) { return mdta::parts_for(B); }
+
+extern "C" int cdfo_channel_gate_fwd(const float *partial_sums, int parts, const float *w1, const float *b1, const float *w2,
+                                     const float *b2, float *gate, int B, int C, int Cmid, int HW, void *stream) {
+  CDFO_REQUIRE(partial_sums && w1 && w2 && gate, CDFO_ERR_NULL, "cdfo_channel_gate_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && C > 0 && Cmid > 0 && parts > 0 && HW > 0 && C + Cmid <= 8192, CDFO_ERR_SHAPE, "cdfo_channel_gate_fwd: bad shape");
+  mdta::channel_gate_kernel<<<B, 128, (size_t)(C + Cmid) * 4, (cudaStream_t)stream>>>(partial_sums, parts, 1.f / (float)HW, w1, b1, w2, b2,
+                                                                                     C, Cmid, gate);
+  return check_launch("cdfo_channel_gate_fwd");
+}
+
+extern "C" int cdfo_pack_c8_scaled(const float *x_nchw, const float *scale, void *x_c8, int B, int C, int H, int W, void *stream) {
+  CDFO_REQUIRE(x_nchw && scale && x_c8, CDFO_ERR_NULL, "cdfo_pack_c8_scaled: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_pack_c8_scaled: bad shape");
+  dim3 grid(ceil_div(H * W, 128), C / 8, B);
+  mdta::pack_c8_scaled_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, scale, (uint4 *)x_c8, C, H * W);
+  return check_launch("cdfo_pack_c8_scaled");
+}
+
+extern "C" int cdfo_unpack_c8_add(const void *x_c8, const float *add_nchw, int add_batch, float *y_nchw, int B, int C, int H, int W,
+                                  void *stream) {
+  CDFO_REQUIRE(x_c8 && add_nchw && y_nchw, CDFO_ERR_NULL, "cdfo_unpack_c8_add: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_unpack_c8_add: bad shape");
+  if (add_batch <= 0) add_batch = B;
+  CDFO_REQUIRE(B % add_batch == 0, CDFO_ERR_SHAPE, "cdfo_unpack_c8_add: B must be a multiple of add_batch");
+  dim3 grid(ceil_div(H * W, 128), C / 8, B);
+  mdta::unpack_c8_add_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8, add_nchw, add_batch, y_nchw, C, H * W);
+  return check_launch("cdfo_unpack_c8_add");
+}

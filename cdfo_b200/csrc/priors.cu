@@ -48,13 +48,6 @@ __global__ void mv_slot_kernel(float *__restrict__ flows, int B, int slot_elems,
 }
 
 // ---------------------------------------------------------------- A3
-// Source coordinate of the reference's normalise (python) / un-normalise (ATen, align_corners=True) round trip.
-__device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
-  const float v = __fadd_rn((float)pos, flow);                                       // grid + flow
-  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)max(size - 1, 1)), 1.0f);  // 2*v/max(s-1,1) - 1
-  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));          // ((g+1)/2)*(s-1)
-}
-
 constexpr int kWarpCh = 8;  // channels per thread
 
 __global__ void flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ y,

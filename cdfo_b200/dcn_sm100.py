@@ -155,3 +155,27 @@ def dcn_tex(x_q4t, fields, wpk16, bias=None, mv=None, out_c8=False, num_ctas=0):
         ev[1].record()
         event_log.append((ev[0], ev[1], B * H * W, 8))
     return y
+
+
+@torch.no_grad()
+def dcn_tex_stacked(x_q4t, fields, wpk16, bias, mv, stack, group_chunk):
+    """dcn_tex writing into `stack` [n_seq, chunks, H, W, 8] bf16: sample s = g * n_seq + b of the group-major batch lands in
+    chunks [group_chunk[g], +8) of stack[b] (cdfo_dcn_tex_sm100_stacked_fwd)."""
+    xB = x_q4t.size(0)
+    B, K, H, W, _ = fields.shape
+    n_seq, chunks = stack.size(0), stack.size(1)
+    if fields.dtype != torch.float16 or not fields.is_contiguous() or stack.dtype != torch.bfloat16 or not stack.is_contiguous() or \
+            tuple(stack.shape[2:]) != (H, W, 8) or B % n_seq or len(group_chunk) != B // n_seq:
+        raise _lib.CdfoError("dcn_tex_stacked: fields / stack mismatch")
+    grp = (ctypes.c_int * len(group_chunk))(*[int(g) for g in group_chunk])
+    ev = None
+    if event_log is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.call("cdfo_dcn_tex_sm100_stacked_fwd", _lib.ptr(x_q4t), _lib.ptr(fields), _lib.ptr(None if mv is None else mv.contiguous().float()),
+              _lib.ptr(wpk16), _lib.ptr(None if bias is None else bias.detach().contiguous().float()), _lib.ptr(stack),
+              int(n_seq), len(group_chunk), int(chunks), grp, H, W, K // 9, int(xB), _lib.stream_ptr(fields.device))
+    if ev is not None:
+        ev[1].record()
+        event_log.append((ev[0], ev[1], B * H * W, 8))
+    return None

@@ -1,9 +1,8 @@
 """Execution of the hot-path modules of CVSR_V8 on the device.
 
 Each function takes the parameter-holder module (cdfo_b200/model.py) plus activations and runs the path the
-reference runs at the cited lines.  `backend` switches per stage between the hand-written kernels of
-libcdfo_b200 ("cuda") and an interim cuDNN/ATen composition ("aten") that exists only for stages whose
-fused kernel has not landed yet; DESIGN.md lists which stage is where.  Everything is CUDA-only.
+reference runs at the cited lines in the hand-written kernels of libcdfo_b200; DESIGN.md section 4 lists the few
+small stages that are still a cuDNN / ATen call.  Everything is CUDA-only.
 """
 import ctypes
 
@@ -11,13 +10,6 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib, config, conv, dcn_sm100
-from .priors import flow_warp_chw
-
-# stage -> "cuda" | "aten"
-backend = {
-    "flow_warp": "cuda",
-    "dcn": "cuda",
-}
 
 
 def _lrelu(x):
@@ -29,50 +21,58 @@ def _c(mod, x, **kw):
 
 
 # ------------------------------------------------------------------------------------------ MDTA (A4 / A5 shared)
-def _mdta(q, k, v, temperature, heads):
-    b, c, h, w = q.shape
-    sh = (b, heads, c // heads, h * w)
-    q = F.normalize(q.reshape(sh), dim=-1)
-    k = F.normalize(k.reshape(sh), dim=-1)
-    attn = ((q @ k.transpose(-2, -1)) * temperature).softmax(dim=-1)
-    return (attn @ v.reshape(sh)).reshape(b, c, h, w)
+def _f32(t):
+    return t.detach().contiguous().float()
 
 
-def _gate(seq, x):
-    y = x.mean(dim=(2, 3), keepdim=True)
-    y = F.relu(_c(seq._modules["0"], y))
-    return torch.sigmoid(_c(seq._modules["2"], y))
-
-
-def _warp(extra_feat, flow):
-    if backend["flow_warp"] == "cuda":
-        return flow_warp_chw(extra_feat.contiguous().float(), flow.contiguous().float())
-    raise _lib.CdfoError("flow_warp has no other backend")
-
-
-def _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused):
-    """warp + fusion_out + the two MDTA passes + project_out (arch:3304-3337 / :3456-3490). Returns (o1, o2)."""
-    warped = _warp(extra_feat, flow)
-    fo = mod.fusion_out._modules["0"] if relu_fused else mod.fusion_out
-    fused = F.conv2d(torch.cat([warped, pred_feat], 1), fo.weight)
-    if relu_fused:
-        fused = F.relu(fused)
-    t, hd = mod.temperature, mod.num_heads
-    o1 = F.conv2d(_mdta(x, fused, warped * _gate(mod.conv_du, warped), t, hd), mod.project_out.weight)
-    o2 = F.conv2d(_mdta(x, fused, pred_feat * _gate(mod.conv_du, pred_feat), t, hd), mod.project_out.weight)
-    return o1, o2
+def dual_mdta(mod, x, extra_feat, pred_feat, flow, mode):
+    """warp + fusion_out + the two MDTA passes + project_out (arch:3304-3337 / :3456-3492) in csrc/mdta.cu.
+    mode 0 (MVDualAttAlignment): returns c8 bf16 [2B, 8, H, W, 8] = cat([o1, o2], 0), the input of conv_offset.0.
+    mode 1 (DualAttAlignment): returns (ReLU(fusion_out(cat[o1 + o2, x])) [B,64,H,W] fp32, per-part channel sums of it).
+    `x` may hold fewer samples than the others (sample b uses x[b % x.size(0)])."""
+    B, C, H, W = extra_feat.shape
+    if C != 64 or x.size(1) != 64 or pred_feat.shape != extra_feat.shape or B % x.size(0):
+        raise _lib.CdfoError("dual_mdta: 64-channel inputs of one size expected")
+    heads = mod.num_heads
+    fo = mod.fusion_out._modules["0"] if mode == 1 else mod.fusion_out
+    du0, du2 = mod.conv_du._modules["0"], mod.conv_du._modules["2"]
+    x, extra_feat, pred_feat, flow = _f32(x), _f32(extra_feat), _f32(pred_feat), _f32(flow)
+    dev = x.device
+    ws = torch.empty(_lib.lib().cdfo_mdta_workspace_bytes(B, H, W, heads), dtype=torch.uint8, device=dev)
+    ca = None
+    if mode == 0:
+        out = torch.empty((2 * B, 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.empty((B, 64, H, W), dtype=torch.float32, device=dev)
+        ca = torch.empty((B, _lib.lib().cdfo_mdta_parts(B), 64), dtype=torch.float32, device=dev)
+    _lib.call("cdfo_mdta_fwd", _lib.ptr(x), int(x.size(0)), _lib.ptr(extra_feat), _lib.ptr(pred_feat), _lib.ptr(flow),
+              _lib.ptr(_f32(fo.weight)), _lib.ptr(_f32(du0.weight)), _lib.ptr(_f32(du0.bias)), _lib.ptr(_f32(du2.weight)),
+              _lib.ptr(_f32(du2.bias)), _lib.ptr(_f32(mod.temperature)), _lib.ptr(_f32(mod.project_out.weight)), int(heads),
+              int(mode), _lib.ptr(out), _lib.ptr(ca), _lib.ptr(ws), B, H, W, _lib.stream_ptr(dev))
+    return out if mode == 0 else (out, ca)
 
 
 @torch.no_grad()
 def dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
-    """DualAttAlignment.forward, arch:3455-3496 (flow [B,2,H,W])."""
-    x = _expand_batch(x, extra_feat.size(0))
-    o1, o2 = _dual_mdta(mod, x, extra_feat, pred_feat, flow, relu_fused=True)
-    out = F.relu(F.conv2d(torch.cat([o1 + o2, x], 1), mod.fusion_out._modules["0"].weight))
-    out = out * _gate(mod.CALayer.conv_du, out)
+    """DualAttAlignment.forward, arch:3455-3496 (flow [B,2,H,W]): MDTA kernels -> CALayer gate -> two residual
+    blocks on the tcgen05 3x3 convolution (c8 bf16, residual adds in its epilogue) -> + x."""
+    B, _, H, W = extra_feat.shape
+    out, ca = dual_mdta(mod, x, extra_feat, pred_feat, flow, mode=1)
+    dev = out.device
+    c0, c2 = mod.CALayer.conv_du._modules["0"], mod.CALayer.conv_du._modules["2"]
+    gate = torch.empty((B, 64), dtype=torch.float32, device=dev)
+    _lib.call("cdfo_channel_gate_fwd", _lib.ptr(ca), int(ca.size(1)), _lib.ptr(_f32(c0.weight)), _lib.ptr(_f32(c0.bias)),
+              _lib.ptr(_f32(c2.weight)), _lib.ptr(_f32(c2.bias)), _lib.ptr(gate), B, 64, int(c0.weight.size(0)), H * W,
+              _lib.stream_ptr(dev))
+    y8 = torch.empty((B, 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+    _lib.call("cdfo_pack_c8_scaled", _lib.ptr(out), _lib.ptr(gate), _lib.ptr(y8), B, 64, H, W, _lib.stream_ptr(dev))
     for rb in (mod.ResidualBlock, mod.ResidualBlock1):
-        out = out + _c(rb.conv2, F.relu(_c(rb.conv1, out, padding=1)), padding=1)
-    return out + x
+        t = conv.conv3x3(y8, rb.conv1.weight, rb.conv1.bias, conv.ACT_RELU)
+        y8 = conv.conv3x3(t, rb.conv2.weight, rb.conv2.bias, conv.ACT_NONE, resid8=y8)
+    xf = _f32(x)
+    res = torch.empty((B, 64, H, W), dtype=torch.float32, device=dev)
+    _lib.call("cdfo_unpack_c8_add", _lib.ptr(y8), _lib.ptr(xf), int(xf.size(0)), _lib.ptr(res), B, 64, H, W, _lib.stream_ptr(dev))
+    return res
 
 
 def _expand_batch(x, B):
@@ -106,9 +106,8 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     [B, dg*9, H, W, 4] fp16 = (10*tanh(dy1) + 10*tanh(dy2), same for dx, sigmoid(m1 + m2), 0) per k = g*9 + tap.
     Both conv_offset layers run in the tcgen05 convolution kernel; tanh / sum / sigmoid are its epilogue."""
     B = extra_feat.size(0)
-    o1, o2 = _dual_mdta(mod, _expand_batch(x, B), extra_feat, pred_feat, flow, relu_fused=False)
     c0, c2 = mod.conv_offset._modules["0"], mod.conv_offset._modules["2"]
-    z = conv.conv3x3(conv.to_c8(torch.cat([o1, o2], 0)), c0.weight, c0.bias, conv.ACT_LRELU)   # [2B, 8, H, W, 8]
+    z = conv.conv3x3(dual_mdta(mod, x, extra_feat, pred_feat, flow, mode=0), c0.weight, c0.bias, conv.ACT_LRELU)   # [2B, 8, H, W, 8]
     H, W = z.shape[2:4]
     dg = mod.deformable_groups
     wpk, bias = _head_weights(c2, dg)
@@ -131,12 +130,16 @@ def unpack_fields(fields):
 
 
 @torch.no_grad()
-def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow):
+def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow, stack=None, group_chunk=None):
     """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior.
     `x` may hold fewer samples than the other arguments (sample b uses x[b % x.size(0)]): the model's six
-    neighbour calls share the centre-frame feature (arch:4456)."""
+    neighbour calls share the centre-frame feature (arch:4456).  With `stack` ([n_seq, chunks, H, W, 8] bf16) the DCN
+    epilogue writes group g of the group-major batch into chunks [group_chunk[g], +8) of it and None is returned."""
     fields = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
     if config.dcn_gather == "tex":
+        if stack is not None:
+            return dcn_sm100.dcn_tex_stacked(dcn_sm100.pack_q4t(x), fields, dcn_sm100.pack_weight_f16(mod.weight), mod.bias, flow,
+                                             stack, group_chunk)
         return dcn_sm100.dcn_tex(dcn_sm100.pack_q4t(x), fields, dcn_sm100.pack_weight_f16(mod.weight), mod.bias, mv=flow)
     xq = dcn_sm100.pack_q4p(x)
     return dcn_sm100.dcn_sm100(xq, None, None, dcn_sm100.pack_weight(mod.weight), mod.bias, mv=flow, fused_fields=fields)
@@ -187,31 +190,42 @@ def long_range_attention(mod, res, x, u):
 
 
 # ------------------------------------------------------------------------------------------ model-level stages
+_SLOT = (0, 1, 2, 4, 5, 6)   # frame slot of neighbour n in the stacked tensor (arch:4463: frames in temporal order)
+
+
 @torch.no_grad()
-def align_neighbours(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb):
-    """The body of the reference's neighbour loop (arch:4445-4456) for all six neighbours at once.
-    Batch index = n * B + b (neighbour-major); `center` [B,64,H,W] is shared by the six."""
+def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
+    """Body of the reference's neighbour loop (arch:4445-4456) for all six neighbours at once (batch index n*B + b,
+    `center` [B,64,H,W] shared by the six), then stack + tsa_fusion 1x1 + lrelu (arch:4463-4466).
+    Returns the fused feature as c8 bf16 [B, 8, H, W, 8].  The 448-channel stack is written once, in bf16, directly by the
+    DCN epilogue (O2) and read by the tcgen05 convolution (the 1x1 is passed as a centre-tap 3x3)."""
+    H, W = center.shape[2:]
     ufs_prior = _c(model.conv_expand_ufs, ufs_nb, padding=1)
     rms_prior = _c(model.conv_expand_rms, rms_nb, padding=1)
     x_n = long_range_attention(model.RDAB, rms_prior, fea_nb + rms_prior, u_nb)
     fr = model.conv_expand_fea_r
     fea_i = conv.conv3x3(conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
-    return model.MV_deform_align(center, fea_i, ufs_prior, mv_nb)
-
-
-@torch.no_grad()
-def temporal_fusion(model, aligned, center, B):
-    """stack + tsa_fusion 1x1 + lrelu, arch:4463-4466. aligned [6B,64,H,W] neighbour-major."""
-    _, c, h, w = aligned.shape
-    a = aligned.view(6, B, c, h, w)
-    stacked = torch.cat([a[0], a[1], a[2], center, a[3], a[4], a[5]], dim=1)   # [B, 448, H, W], frame order 0..6
-    return _lrelu(_c(model.tsa_fusion, stacked))
+    stack = torch.empty((B, 56, H, W, 8), dtype=torch.bfloat16, device=center.device)
+    stack[:, 24:32] = conv.to_c8(center)
+    al = model.MV_deform_align
+    if model.alignment == "mv_dcn" and config.dcn_gather == "tex":
+        mv_dual_att_alignment(al, center, fea_i, ufs_prior, mv_nb, stack=stack, group_chunk=[8 * f for f in _SLOT])
+    else:
+        a8 = conv.to_c8(al(center, fea_i, ufs_prior, mv_nb)).view(6, B, 8, H, W, 8)
+        for n, f in enumerate(_SLOT):
+            stack[:, 8 * f:8 * f + 8] = a8[n]
+    w = conv.derived(model.tsa_fusion.weight, "3x3", conv.centre_tap)
+    return conv.conv3x3(stack, w, model.tsa_fusion.bias, conv.ACT_LRELU)
 
 
 @torch.no_grad()
 def tail(model, t, x_center):
-    """arch:4473-4480."""
-    out = _lrelu(F.pixel_shuffle(_c(model.upconv1, t), 2))
-    out = _lrelu(F.pixel_shuffle(_c(model.upconv2, out), 2))
-    out = _c(model.conv_last, out, padding=1)
-    return out + F.interpolate(x_center, scale_factor=4.0, mode="bilinear", align_corners=False)
+    """arch:4473-4480 in three launches of the tcgen05 convolution: upconv1 + PixelShuffle + lrelu, upconv2 + PixelShuffle
+    + lrelu (the shuffle is the store address of the epilogue; the 64-channel HR tensor exists once, in bf16), and
+    conv_last + bias + bilinear x4 skip.  t: [B,64,H,W] fp32 or c8 bf16 [B,8,H,W,8]."""
+    t8 = t if t.dim() == 5 else conv.to_c8(t)
+    for up in (model.upconv1, model.upconv2):
+        w = conv.derived(up.weight, "ps3x3", lambda v: conv.ps_order(conv.centre_tap(v)))
+        b = conv.derived(up.bias, "ps", conv.ps_order)
+        t8 = conv.conv3x3(t8, w, b, conv.ACT_LRELU, pixel_shuffle=True)
+    return conv.conv_last_skip(t8, model.conv_last.weight, model.conv_last.bias, x_center)

@@ -311,7 +311,10 @@ class CVSR_V8(nn.Module):
         l1 = _lrelu(self.conv_first(x))
         return self.transformer_feature_extraction(l1, self.conv_second(pms))
 
-    def _trunk(self, x):
+    def _trunk(self, x8):
+        """c8 bf16 in -> NCHW fp32 out ("next" row f1; cuDNN for now)."""
+        from . import conv
+        x = conv.from_c8(x8)
         dt = self.lowp
         if dt is not None:
             with torch.autocast("cuda", dtype=dt):
@@ -344,8 +347,7 @@ class CVSR_V8(nn.Module):
         mv_nb = mvs1[:, nb].transpose(0, 1).reshape(6 * B, 2, H, W).contiguous()
         u_nb = torch.cat([u.to(x.device, torch.float32) for u in noise], 0)
         center = fea[:, ctr]
-        aligned = hotpath.align_neighbours(self, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb)   # [6B,64,H,W]
-        fused = hotpath.temporal_fusion(self, aligned, center, B)
-        t = self._trunk(fused)
+        fused8 = hotpath.align_and_fuse(self, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B)   # c8 bf16 [B,8,H,W,8]
+        t = self._trunk(fused8)
         out = hotpath.tail(self, t, x[:, ctr])
         return out, l1

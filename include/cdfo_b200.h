@@ -121,6 +121,12 @@ int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, 
 int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias,
                            void *y, int B, int H, int W, int dg, int out_mode, int num_ctas, int x_batch,
                            long long fields_bstride, void *stream);
+/* Same kernel writing straight into the stacked input of tsa_fusion (arch/SIDECVSR_our.py:4463-4466): the batch is
+ * group-major (sample s = group * n_seq + sequence; the model's groups are the six neighbour frames), and sample s lands in
+ * the 8-channel chunks [group_chunk[group], +8) of y_stack [n_seq, stack_chunks, H, W, 8] bf16 (frame slot * 8). */
+int cdfo_dcn_tex_sm100_stacked_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias,
+                                   void *y_stack, int n_seq, int n_groups, int stack_chunks, const int *group_chunk, int H,
+                                   int W, int dg, int x_batch, void *stream);
 int cdfo_dcn_tex_sm100_pack_weight(const float *w, void *wpk, void *stream);
 /* NCHW fp32 -> [B, C/4, H+3, Wpt, 4] fp16 (saturated to +-65504), zero border 1 before / 2 after, zero pitch padding. */
 int cdfo_pack_q4t(const float *x_nchw, void *x_q4t, int B, int C, int H, int W, void *stream);
@@ -131,7 +137,11 @@ size_t cdfo_q4t_bytes(int B, int C, int H, int W);
  * ResidualBlock_noBN.conv{1,2} (:254-271), conv_expand_fea_r (:4382).  Cin % 64 == 0, Cout % 16 == 0.
  *   x_c8 [B, Cin/8, H, W, 8] bf16; wpk from cdfo_conv3x3_sm100_pack_weight (cdfo_conv3x3_sm100_weight_bytes bytes);
  *   bias [Cout] fp32 or NULL; act 0 none / 1 ReLU / 2 LeakyReLU(0.1); resid_c8 (same shape as a c8 output) or NULL is
- *   added after the activation; y: out_mode 0 = [B, Cout, H, W] fp32, 1 = [B, Cout/8, H, W, 8] bf16. */
+ *   added after the activation; y: out_mode 0 = [B, Cout, H, W] fp32, 1 = [B, Cout/8, H, W, 8] bf16,
+ *   2 = [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) of the result when the caller packed the weights / bias with output
+ *   channels ordered n' = (2i+j)*(Cout/4) + c (PixelShuffle: channel 4c+2i+j -> (c, 2h+i, 2w+j)): upconv + PixelShuffle +
+ *   LeakyReLU of the tail (arch/SIDECVSR_our.py:4473-4476) in one launch.  A 1x1 convolution is passed as a 3x3 weight
+ *   whose only non-zero tap is the centre. */
 int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                            int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream);
 /* ---- offset / mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3274, :3339-3350) fused into the conv epilogue ----
@@ -144,9 +154,35 @@ int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias,
  *   z_c8 [B, Cin/8, H, W, 8] bf16. */
 int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, const void *first, void *out,
                                   int B, int Cin, int dg, int H, int W, float magnitude, void *stream);
+/* conv_last (Cin -> 1, 3x3; weight packed with Cout padded to 16) + bias + bilinear x4 skip (align_corners=False) of the
+ * 1-channel LR image lr [B, H/4, W/4] fp32 (arch/SIDECVSR_our.py:4477-4480); x_c8 [B, Cin/8, H, W, 8] bf16; y [B, 1, H, W] fp32. */
+int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const float *lr, float *y, int B,
+                                  int Cin, int H, int W, void *stream);
 int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream);
 size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin);
 int cdfo_conv3x3_sm100_ntile(int Cout, int Cin);
+/* ---- A4 / A5: warp + fusion_out + dual MDTA + project_out (csrc/mdta.cu) ----
+ * arch/SIDECVSR_our.py:3303-3337 (mode 0: MVDualAttAlignment, heads = 8, no ReLU after fusion_out) and :3455-3492
+ * (mode 1: DualAttAlignment, heads = 4, ReLU after fusion_out, second fusion_out folded in).  All NCHW fp32:
+ *   x [x_batch,64,H,W] query (sample b uses x[b % x_batch]); extra, pred [B,64,H,W]; flow [B,2,H,W] (x, y)
+ *   fusion_w [64,128] (no bias); conv_du: du_w1 [4,64], du_b1 [4], du_w2 [64,4], du_b2 [64]; temperature [heads]; proj_w [64,64]
+ *   mode 0: out = c8 bf16 [2B, 8, H, W, 8]: samples [0,B) = project_out(attn @ (warped*g)), [B,2B) = project_out(attn @ (pred*g))
+ *   mode 1: out = NCHW fp32 [B,64,H,W] = ReLU(fusion_out(cat[o1 + o2, x])); ca_sums [B, cdfo_mdta_parts(B), 64] = per-part
+ *           channel sums of out (feed cdfo_channel_gate_fwd: CALayer pooling, arch:2032-2043)
+ *   workspace: cdfo_mdta_workspace_bytes(B, H, W, heads) bytes (holds the warped features, fp32). */
+int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, const float *pred, const float *flow,
+                  const float *fusion_w, const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2,
+                  const float *temperature, const float *proj_w, int heads, int mode, void *out, float *ca_sums,
+                  void *workspace, int B, int H, int W, void *stream);
+size_t cdfo_mdta_workspace_bytes(int B, int H, int W, int heads);
+int cdfo_mdta_parts(int B);
+/* gate [B,C] = sigmoid(W2 relu(W1 mean + b1) + b2), mean = (sum over `parts` of partial_sums [B,parts,C]) / HW; w1 [Cmid,C], w2 [C,Cmid]. */
+int cdfo_channel_gate_fwd(const float *partial_sums, int parts, const float *w1, const float *b1, const float *w2,
+                          const float *b2, float *gate, int B, int C, int Cmid, int HW, void *stream);
+/* NCHW fp32 * scale[b][c] -> c8 bf16;  c8 bf16 + add[b % add_batch] (NCHW fp32) -> NCHW fp32. */
+int cdfo_pack_c8_scaled(const float *x_nchw, const float *scale, void *x_c8, int B, int C, int H, int W, void *stream);
+int cdfo_unpack_c8_add(const void *x_c8, const float *add_nchw, int add_batch, float *y_nchw, int B, int C, int H, int W,
+                       void *stream);
 /* ---- A8: LLongRangAttention.forward (arch/SIDECVSR_our.py:2179-2249) after its 1x1 input_conv and the pooled mask logits ----
  *   qv     [B,128,H,W] fp32 = input_conv(x) (q = first 64 channels, v = last 64)          arch:2206,2211
  *   u      [B,64,H,W]  fp32 uniform noise of gumbel_softmax (torch.rand_like, arch:2169)

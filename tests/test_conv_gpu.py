@@ -41,3 +41,33 @@ def test_conv3x3_sm100(cuda_dev, case):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item())
     y8 = conv.conv3x3(x8, wd, d(b), act, r8, out_nchw=False)
     assert (conv.from_c8(y8).cpu() - ref).abs().max().item() <= 1.2e-2 * max(1.0, ref.abs().max().item())  # bf16 output rounding
+
+
+def test_pixel_shuffle_epilogue_and_conv_last_skip(cuda_dev):
+    """upconv (1x1 as a centre-tap 3x3) + PixelShuffle(2) + lrelu in the conv epilogue, and conv_last + bilinear x4 skip,
+    against the plain torch composition of arch/SIDECVSR_our.py:4473-4480 on bf16-rounded operands."""
+    import torch.nn.functional as F
+    from cdfo_b200 import conv
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 24, 40
+    t = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float()
+    w1 = (torch.randn(256, 64, 1, 1, generator=g) * 0.1).to(torch.bfloat16).float()
+    b1 = torch.randn(256, generator=g) * 0.1
+    ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(t, w1, b1), 2), 0.1)
+    d = lambda v: v.to(cuda_dev)
+    w3 = conv.ps_order(conv.centre_tap(d(w1)))
+    y8 = conv.conv3x3(conv.to_c8(d(t)), w3, conv.ps_order(d(b1)), conv.ACT_LRELU, pixel_shuffle=True)
+    assert tuple(y8.shape) == (B, 8, 2 * H, 2 * W, 8)
+    got = conv.from_c8(y8).cpu()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    # conv_last + skip on the 2x grid (any H, W multiple of 4 works): 64 -> 1, 3x3
+    wl = (torch.randn(1, 64, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+    bl = torch.randn(1, generator=g)
+    lr = torch.rand(B, 1, 2 * H // 4, 2 * W // 4, generator=g)
+    x2 = conv.from_c8(y8).cpu()       # bf16-exact input
+    ref2 = F.conv2d(x2, wl, bl, padding=1) + F.interpolate(lr, scale_factor=4.0, mode="bilinear", align_corners=False)
+    wl_d, bl_d = d(wl), d(bl)
+    got2 = conv.conv_last_skip(y8, wl_d, bl_d, d(lr)).cpu()
+    err = (got2 - ref2).abs().max().item()
+    print("conv_last+skip max err %.3g" % err)
+    assert err <= 2e-3

@@ -2,6 +2,7 @@
 import argparse, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cdfo_b200  # noqa: E402
 from cdfo_b200 import hotpath, synthetic  # noqa: E402
 from cdfo_b200.model import CVSR_V8  # noqa: E402
 
@@ -24,7 +25,7 @@ x1 = torch.rand(S, 1, H, W, device=dev, generator=g)
 fns = {
     "rdab": lambda: hotpath.long_range_attention(m.RDAB, rp, fea_nb + rp, u),
     "align": lambda: m.MV_deform_align(center, fea_nb, up, mv),
-    "trunk": lambda: m._trunk(center),
+    "trunk": lambda: m._trunk(cdfo_b200.conv.to_c8(center)),
     "tail": lambda: hotpath.tail(m, center, x1),
     "features": lambda: m._features(x1, x1),
 }

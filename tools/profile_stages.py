@@ -55,18 +55,17 @@ def main():
         res["conv_expand_fea_r"], fea_i = t(lambda: cdfo_b200.conv.conv3x3(cdfo_b200.conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, 0, out_nchw=True))
         cr = center.repeat(6, 1, 1, 1)
         al = m.MV_deform_align
-        relu = a.variant != "O2"
-        res["align.dual_mdta"], (o1, o2) = t(lambda: hotpath._dual_mdta(al, cr, fea_i, up, mv, relu))
+        res["align.dual_mdta"], _ = t(lambda: hotpath.dual_mdta(al, center, fea_i, up, mv, 0 if a.variant == "O2" else 1))
         if a.variant == "O2":
             res["align.offset_fields_total"], fields = t(lambda: hotpath.mv_offset_fields(al, center, fea_i, up, mv))
-            res["align.pack_q4p"], xq = t(lambda: cdfo_b200.dcn_sm100.pack_q4p(center))
-            res["align.dcn_sm100"], aligned = t(lambda: cdfo_b200.dcn_sm100.dcn_sm100(xq, None, None, cdfo_b200.dcn_sm100.pack_weight(al.weight), al.bias, mv=mv, fused_fields=fields))
+            res["align.pack_q4t"], xq = t(lambda: cdfo_b200.dcn_sm100.pack_q4t(center))
+            res["align.dcn_tex"], aligned = t(lambda: cdfo_b200.dcn_sm100.dcn_tex(xq, fields, cdfo_b200.dcn_sm100.pack_weight_f16(al.weight), al.bias, mv=mv))
         res["align.total"], aligned = t(lambda: al(center, fea_i, up, mv))
-        res["fusion"], fused = t(lambda: hotpath.temporal_fusion(m, aligned, center, S))
+        res["align_and_fuse_total"], fused = t(lambda: hotpath.align_and_fuse(m, center, fea_nb, ufs_nb, rms_nb, mv, u, S))
         res["trunk"], tr = t(lambda: m._trunk(fused))
         res["tail"], _ = t(lambda: hotpath.tail(m, tr, x1))
     res = {k: round(v, 3) for k, v in res.items()}
-    res["sum_ms"] = round(sum(v for k, v in res.items() if "." not in k or k == "align.total"), 2)
+    res["sum_ms"] = round(res["features_1frame"] + res["align_and_fuse_total"] + res["trunk"] + res["tail"], 2)
     res["seqs"] = S
     print(json.dumps(res))
 
