@@ -117,3 +117,19 @@ def conv_last_skip(x8, weight, bias, lr):
     _lib.call("cdfo_conv_last_skip_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(lr), _lib.ptr(y), B, C8 * 8, H, W,
               _lib.stream_ptr(x8.device))
     return y
+
+
+@torch.no_grad()
+def resample(a, mode, b=None, base=None):
+    """c8 bf16 bilinear resampling (align_corners=False): mode 0 = x0.5 of a, 1 = x2 of a, 2 = base + x0.5(a) + x2(b)."""
+    B, C8, Ha, Wa, _ = a.shape
+    Ho, Wo = (Ha // 2, Wa // 2) if mode in (0, 2) else (2 * Ha, 2 * Wa)
+    if a.dtype != torch.bfloat16 or not a.is_contiguous() or (mode != 1 and (Ha % 2 or Wa % 2)):
+        raise _lib.CdfoError("resample: contiguous bf16 c8 input with even size expected")
+    if mode == 2 and (tuple(base.shape) != (B, C8, Ho, Wo, 8) or tuple(b.shape) != (B, C8, Ho // 2, Wo // 2, 8)
+                      or not base.is_contiguous() or not b.is_contiguous()):
+        raise _lib.CdfoError("resample: base / b shapes do not match")
+    y = torch.empty((B, C8, Ho, Wo, 8), dtype=torch.bfloat16, device=a.device)
+    _lib.call("cdfo_resample_c8", _lib.ptr(a), _lib.ptr(b), _lib.ptr(base), _lib.ptr(y), B, C8 * 8, Ho, Wo, int(mode),
+              _lib.stream_ptr(a.device))
+    return y

@@ -229,3 +229,64 @@ def tail(model, t, x_center):
         b = conv.derived(up.bias, "ps", conv.ps_order)
         t8 = conv.conv3x3(t8, w, b, conv.ACT_LRELU, pixel_shuffle=True)
     return conv.conv_last_skip(t8, model.conv_last.weight, model.conv_last.bias, x_center)
+
+
+# ------------------------------------------------------------------------------------------ reconstruction trunk (8f rank 1)
+def _compose_1x1_after_3x3(w1, b1, w3, b3):
+    """conv1x1(w1, b1) o conv3x3(w3, b3) == conv3x3(w, b): exact (the 1x1 comes after, no border effect)."""
+    m = w1.float().reshape(w1.size(0), w1.size(1))
+    w = torch.einsum("om,mikl->oikl", m, w3.float()).contiguous()
+    b = m @ b3.float() + b1.float()
+    return w, b
+
+
+def _block_weights(blk):
+    """Per cross-scale block: body convs, 1x1 convs as centre taps, and the 1x1 convs that FOLLOW a body composed into it."""
+    b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
+    dn, up = blk.down._modules["0"], blk.up._modules["0"]
+    key = (id(blk), b0.weight._version, b2.weight._version, dn.weight._version, up.weight._version,
+           b2.bias._version, dn.bias._version, up.bias._version)
+    hit = _trunk_cache.get(id(blk))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    wu2, bu2 = _compose_1x1_after_3x3(up.weight.detach(), up.bias.detach(), b2.weight.detach(), b2.bias.detach())
+    wd2, bd2 = _compose_1x1_after_3x3(dn.weight.detach(), dn.bias.detach(), b2.weight.detach(), b2.bias.detach())
+    out = {"dn3": conv.centre_tap(dn.weight.detach()), "up3": conv.centre_tap(up.weight.detach()),
+           "up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
+    _trunk_cache[id(blk)] = (key, out)
+    return out
+
+
+_trunk_cache = {}
+
+
+@torch.no_grad()
+def cross_scale_block(blk, x8):
+    """Block_.forward, arch:401-406, on c8 bf16.  Bilinear x0.5 / x2 commute with the 1x1 convs (per-pixel linear maps whose
+    bias passes through weights that sum to 1), so every 1x1 runs at the lower of its two resolutions, and the 1x1 that
+    follows a body is composed into the body's second 3x3:
+        x + body(x)                         two convs at 1x (residual add in the epilogue)
+        up(body(down(x)))                   x0.5 -> 1x1 -> conv -> conv o up-1x1 at 1/2x, then x2
+        down(body(up(x)))                   1x1 at 1x -> x2 -> conv -> conv o down-1x1 at 2x, then x0.5
+    and one kernel sums the three branches."""
+    b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
+    dn, up = blk.down._modules["0"], blk.up._modules["0"]
+    wts = _block_weights(blk)
+    y = conv.conv3x3(conv.conv3x3(x8, b0.weight, b0.bias, conv.ACT_LRELU), b2.weight, b2.bias, conv.ACT_NONE, resid8=x8)
+    xd = conv.conv3x3(conv.resample(x8, 0), wts["dn3"], dn.bias, conv.ACT_NONE)
+    cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
+    xu = conv.resample(conv.conv3x3(x8, wts["up3"], up.bias, conv.ACT_NONE), 1)
+    b3 = conv.conv3x3(conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU), wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
+    return conv.resample(b3, 2, b=cu, base=y)
+
+
+@torch.no_grad()
+def recon_trunk(trunk, x8):
+    """SCNet_(7 x SCGroup_(3 x Block_)), arch:430-480, c8 bf16 in and out."""
+    y = x8
+    for grp in trunk.body._modules.values():
+        r = y
+        for blk in grp.body._modules.values():
+            r = cross_scale_block(blk, r)
+        y = conv.conv3x3(r, grp.conv.weight, grp.conv.bias, conv.ACT_NONE, resid8=y)
+    return y + x8

@@ -299,6 +299,7 @@ class CVSR_V8(nn.Module):
         self.RDAB = LLongRangAttention(64)
         self.lowp = None            # torch dtype for the non-hot-path convolutions (None: fp32)
         self.noise_generator = None
+        self.trunk_backend = "cuda"   # "cuda": tcgen05 convs + resample kernels on c8 bf16; "cudnn": torch convolutions
 
     # -- feature extraction of `n` frames ("next" row f2; cuDNN for now)
     def _features(self, x, pms):
@@ -314,6 +315,8 @@ class CVSR_V8(nn.Module):
     def _trunk(self, x8):
         """c8 bf16 in -> NCHW fp32 out ("next" row f1; cuDNN for now)."""
         from . import conv
+        if self.trunk_backend == "cuda":
+            return hotpath.recon_trunk(self.recon_trunk, x8)      # c8 bf16 out: the tail takes it as is
         x = conv.from_c8(x8)
         dt = self.lowp
         if dt is not None:
