@@ -49,6 +49,9 @@ struct Conv3x3Params {
   float mag;
   const uint2 *aux;
   int n_tiles, tiles_x, tiles_y, m_tiles;
+  // 1: the weights of the N tile do not fit shared memory next to the A stages (Cin >= 256 at NT = 64): the 9 x NT x 64
+  // weights of each 64-channel block travel with the block's A halo through the same stage (L2-resident, re-read per tile)
+  int stream_w;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -74,9 +77,11 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
   extern __shared__ __align__(1024) uint8_t smem[];
   const int KB = p.Cin / 64;                    // 64-channel blocks
   const int w_bytes = 9 * p.Cin * NT * 2;
+  constexpr int kPiece = NT * 64 * 2;           // weights of one (tap, 64-channel block)
+  const int stage_stride = p.stream_w ? ((kCvStageBytes + 9 * kPiece + 1023) & ~1023) : kCvStageBytes;
   uint8_t *wsm = smem;
-  uint8_t *asmem = smem + ((w_bytes + 1023) & ~1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(asmem + kStages * kCvStageBytes);
+  uint8_t *asmem = smem + (p.stream_w ? 0 : ((w_bytes + 1023) & ~1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(asmem + kStages * stage_stride);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
   float *bias_s = reinterpret_cast<float *>(bars + 18);
   // barrier map: [0,kStages) A full, [4,4+kStages) A empty, 8/9 accumulator full, 10/11 accumulator empty, 12 weights
@@ -101,11 +106,12 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
     ptx::mbar_init(BAR(12), 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmap);
-    // resident weights of this N tile: 9 * KB pieces of NT x 64 bf16
-    ptx::mbar_arrive_expect_tx(BAR(12), w_bytes);
-    const int piece = NT * 64 * 2;
-    const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes;
-    for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * piece, src + (size_t)i * piece, piece, BAR(12));
+    if (!p.stream_w) {
+      // resident weights of this N tile: 9 * KB pieces of NT x 64 bf16
+      ptx::mbar_arrive_expect_tx(BAR(12), w_bytes);
+      const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes;
+      for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * kPiece, src + (size_t)i * kPiece, kPiece, BAR(12));
+    }
   }
   if (warp == 1) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
@@ -126,8 +132,14 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       for (int kb = 0; kb < KB; ++kb) {
         if (lane == 0) {
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
-          ptx::mbar_arrive_expect_tx(BAR(stage), kCvStageBytes);
-          ptx::tma_load_5d(ptx::smem_u32(asmem) + stage * kCvStageBytes, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * 8, b);
+          const uint32_t dst = ptx::smem_u32(asmem) + stage * stage_stride;
+          ptx::mbar_arrive_expect_tx(BAR(stage), kCvStageBytes + (p.stream_w ? 9 * kPiece : 0));
+          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * 8, b);
+          if (p.stream_w) {
+            const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * kPiece;
+            for (int tap = 0; tap < 9; ++tap)
+              ptx::bulk_g2s(dst + kCvStageBytes + tap * kPiece, src + (size_t)tap * KB * kPiece, kPiece, BAR(stage));
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -136,7 +148,7 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = ptx::make_idesc_bf16(128, NT);
-    ptx::mbar_wait(BAR(12), 0);
+    if (!p.stream_w) ptx::mbar_wait(BAR(12), 0);
     int stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
       ptx::mbar_wait(BAR(10 + acc), acc_phase ^ 1);
@@ -145,11 +157,11 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
         ptx::mbar_wait(BAR(stage), phase);
         ptx::tc_fence_after();
         if (lane == 0) {
-          const uint32_t a0 = ptx::smem_u32(asmem) + stage * kCvStageBytes;
+          const uint32_t a0 = ptx::smem_u32(asmem) + stage * stage_stride;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t a_tap = a0 + ((tap / 3) * kCvHaloW + (tap % 3)) * 16;
-            const uint32_t b_tap = ptx::smem_u32(wsm) + (tap * KB + kb) * (NT * 64 * 2);
+            const uint32_t b_tap = p.stream_w ? a0 + kCvStageBytes + tap * kPiece : ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kCvPlane, kCvPlane, kCvSbo);
@@ -349,7 +361,7 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // N-tile size used for a given Cout / Cin: the largest tile that divides Cout and whose weights (9 * Cin * NT bf16)
 // stay resident in shared memory next to the A stages.
-int conv3x3_ntile(int Cout, int Cin) {
+static int conv3x3_ntile_resident(int Cout, int Cin) {
   const int budget = 168 * 1024;
   const int cands[5] = {144, 128, 64, 32, 16};
   for (int c = 0; c < 5; ++c) {
@@ -358,13 +370,18 @@ int conv3x3_ntile(int Cout, int Cin) {
   }
   return 0;
 }
+// Wide inputs (Cin >= 256: the trunk's 256 -> 64, tsa_fusion's 448 -> 64) would leave only a 16/32-channel resident N tile,
+// where every A tile is re-read per N tile and the MMA is bound by the shared-memory reads of A; stream the weights instead.
+bool conv3x3_streams(int Cout, int Cin) { return conv3x3_ntile_resident(Cout, Cin) < 64 && Cout % 64 == 0 && Cin >= 256; }
+int conv3x3_ntile(int Cout, int Cin) { return conv3x3_streams(Cout, Cin) ? 64 : conv3x3_ntile_resident(Cout, Cin); }
 
 template <int NT>
 static int launch_conv3x3(const CUtensorMap &tm, const Conv3x3Params &p, int grid, cudaStream_t s) {
   constexpr int kStages = 2;
   auto kern = conv3x3_sm100_kernel<NT, kStages>;
   const int w_bytes = 9 * p.Cin * NT * 2;
-  const size_t smem = ((w_bytes + 1023) & ~1023) + kStages * kCvStageBytes + 18 * 8 + NT * 4 + 64;
+  const size_t smem = (p.stream_w ? (size_t)kStages * ((kCvStageBytes + 9 * NT * 64 * 2 + 1023) & ~1023)
+                                  : (size_t)((w_bytes + 1023) & ~1023) + kStages * kCvStageBytes) + 18 * 8 + NT * 4 + 64;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -451,6 +468,7 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.act = act; p.out_mode = out_mode;
   p.epi = epi; p.mag = mag; p.aux = (const uint2 *)aux;
   p.n_tiles = ceil_div(Cout, nt);
+  p.stream_w = conv3x3_streams(Cout, Cin) ? 1 : 0;
   p.tiles_x = ceil_div(W, kCvTileW); p.tiles_y = ceil_div(H, kCvTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;
   CDFO_REQUIRE(mt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: too many tiles");

@@ -12,7 +12,9 @@ CASES = [
     (1, 64, 432, 24, 40, 0, False),     # conv_offset.2: three N tiles of 144
     (1, 128, 64, 24, 40, 2, False),     # conv_expand_fea_r: two 64-channel K blocks
     (1, 64, 256, 20, 24, 2, False),     # trunk body.0: two N tiles of 128
-    (1, 256, 64, 20, 24, 0, True),      # trunk body.2: four K blocks, N tiles of 32
+    (1, 256, 64, 20, 24, 0, True),      # trunk body.2: four K blocks, weights streamed with the A stages (N tile 64)
+    (2, 448, 64, 40, 24, 2, False),     # tsa_fusion-shaped K (7 blocks), streamed weights, several tiles per CTA
+    (1, 256, 32, 20, 24, 0, False),     # wide input, resident N tile of 32
     (1, 64, 48, 18, 10, 0, False),      # N tile of 16
     (3, 64, 64, 64, 64, 0, False),      # many tiles per CTA (pipeline wrap-around)
 ]
