@@ -202,6 +202,8 @@ def run_ours(args):
         sr_host.copy_(out8, non_blocking=True)
         return sr, l1
 
+    last_sr = [None]
+
     def timed(step_fn, steps, warmup, l1, log_dcn):
         for i in range(warmup):
             _, l1 = step_fn(i, l1)
@@ -215,7 +217,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            _, l1 = step_fn(warmup + i, l1)
+            last_sr[0], l1 = step_fn(warmup + i, l1)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -236,11 +238,15 @@ def run_ours(args):
     ms_e2e, l1, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), l1, False)
     clocks = sampler.stop() if rank == 0 else None
 
-    # the end-of-job metric gather of the real pipeline (PSNR/SSIM sums): one tiny NCCL all_reduce
-    frames = torch.tensor([float(S * args.steps)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(frames)
-    total_frames = float(frames.item())
+    # the end-of-job metric gather of the real pipeline (PSNR/SSIM sums, cdfo_b200/sharding.py): one tiny all_reduce of
+    # [n_seq, 3] fp64 = (sum of squares of the last SR frame as the error stand-in, 0, frames produced) per owned sequence
+    from cdfo_b200 import sharding
+    sums = torch.zeros((world * S, 3), device=dev, dtype=torch.float64)
+    own = sharding.sequence_shard(world * S, world, rank)
+    sums[own[0]:own[-1] + 1, 0] = last_sr[0].double().pow(2).sum(dim=(1, 2, 3))
+    sums[own[0]:own[-1] + 1, 2] = float(args.steps)
+    sums = sharding.gather_metrics(sums)
+    total_frames = float(sums[:, 2].sum().item())
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -276,7 +282,7 @@ def run_ours(args):
                                    "steady state (cached L1_fea), %d sequences per GPU per step" % (args.variant, S),
                        "lr": [H, W], "seqs_per_gpu": S, "parallelism": "sequence-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (per step > 1 GB of offsets/masks/activations; %d rotating windows)" % len(pool),
-                       "stages": "hot path: CUDA kernels + interim ATen (see DESIGN.md); trunk/feature extraction: cuDNN bf16"},
+                       "stages": "alignment / attention / fusion / trunk / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }

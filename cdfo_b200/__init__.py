@@ -8,6 +8,7 @@ from . import _lib, config, conv  # noqa: F401
 from . import deform_conv_cuda  # noqa: F401
 from .dcn import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack,  # noqa: F401
                   deform_conv, deform_conv2d, modulated_deform_conv)
+from .attentionlayer import DSTA  # noqa: F401
 from .priors import flow_warp, modify_mv_for_end_frames, mv2mvs  # noqa: F401
 
 __version__ = "0.1.0"
