@@ -40,7 +40,8 @@ struct Conv3x3Params {
                  //    n' = (2i+j)*(Cout/4) + c and leave at [B][Cout/32][2H][2W][8], pixel (2h+i, 2w+j)
   // epi 0: bias -> act -> +resid.
   // Offset/mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3341-3350): output channels arrive permuted as triples
-  // (dy_k, dx_k, m_k), k = g*9 + tap, and leave as one fp16x4 "field" (dy, dx, m, 0) per (k, pixel): y [B][Cout/3][H][W] x 8 B
+  // (dy_k, dx_k, m_k), k' = tap*dg + g, and leave as one fp16x4 "field" (dy, dx, m, 0) per (tap, pixel, group):
+  // y [B][9][dg/gp][H*W][gp] x 8 B, gp = 2 for dg = 16 else 1 (what the DCN producer reads with two coalesced 16-byte loads)
   // epi 1: (mag*tanh(dy), mag*tanh(dx), m)                                   (first head evaluation)
   // epi 2: (aux.dy + mag*tanh(dy), aux.dx + mag*tanh(dx), sigmoid(aux.m + m)) (second evaluation; aux = epi-1 output)
   // epi 3: channel 0 only (+ bias) + bilinear x4 skip of a 1-channel LR image (aux = float [B][H/4][W/4], align_corners=False):
@@ -237,13 +238,29 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
               v[16 + i] = __uint_as_float(r1[i]) + bias_s[c0 + 16 + i];
               v[32 + i] = __uint_as_float(r2[i]) + bias_s[c0 + 32 + i];
             }
-            const size_t fidx = ((size_t)b * (p.Cout / 3) + (n0 + c0) / 3) * HW + pix;
-            uint2 prior[16];
+            // fields layout [B][9 taps][dg/gp][H*W][gp] (gp = 2 for dg == 16, else 1): triple k' = tap * dg + g.  The 16
+            // consecutive triples of one thread are the 16 groups of one tap when dg == 16: 8 pair planes, 16 bytes each,
+            // consecutive lanes = consecutive pixels (coalesced); otherwise they are placed one by one (8 bytes each).
+            const int dgn = p.Cout / 27, k0 = (n0 + c0) / 3;
+            uint2 prior[16], outv[16];
+            const bool vec = dgn == 16;
+            const size_t base16 = (((size_t)b * 9 + k0 / 16) * 8 * HW + pix) * 2;   // dg == 16: pair plane 0 of this tap
             if (p.epi == 2) {
+              if (vec) {
 #pragma unroll
-              for (int t = 0; t < 16; ++t) prior[t] = __ldg(p.aux + fidx + (size_t)t * HW);
+                for (int t = 0; t < 8; ++t) {
+                  const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p.aux + base16 + (size_t)t * 2 * HW));
+                  prior[2 * t] = make_uint2(q.x, q.y);
+                  prior[2 * t + 1] = make_uint2(q.z, q.w);
+                }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  const int k = k0 + t;
+                  prior[t] = __ldg(p.aux + ((size_t)b * 9 * dgn + k) * HW + pix);
+                }
+              }
             }
-            uint2 *y = reinterpret_cast<uint2 *>(p.y) + fidx;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
               float dy, dx, m = v[3 * t + 2];
@@ -259,7 +276,19 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
                 m = __fdividef(1.f, 1.f + __expf(-(pm + m)));     // sigmoid(mask_1 + mask_2) (arch:3350)
               }
               const __half2 h0 = __floats2half2_rn(dy, dx), h1 = __floats2half2_rn(m, 0.f);
-              y[(size_t)t * HW] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+              outv[t] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+            }
+            uint2 *y = reinterpret_cast<uint2 *>(p.y);
+            if (vec) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                *reinterpret_cast<uint4 *>(y + base16 + (size_t)t * 2 * HW) = make_uint4(outv[2 * t].x, outv[2 * t].y, outv[2 * t + 1].x, outv[2 * t + 1].y);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                const int k = k0 + t;
+                y[((size_t)b * 9 * dgn + k) * HW + pix] = outv[t];
+              }
             }
           }
         }
@@ -428,7 +457,7 @@ extern "C" int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, 
                "cdfo_mv_offset_head_sm100_fwd: deformable_groups * 27 must be a multiple of 144 (got dg = %d)", dg);
   CDFO_REQUIRE(conv3x3_ntile(dg * 27, Cin) == 144, CDFO_ERR_UNSUPPORTED,
                "cdfo_mv_offset_head_sm100_fwd: needs the 144-channel N tile (Cin = %d too large)", Cin);
-  CDFO_REQUIRE(((uintptr_t)out & 7) == 0 && ((uintptr_t)first & 7) == 0, CDFO_ERR_SHAPE, "cdfo_mv_offset_head_sm100_fwd: alignment");
+  CDFO_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)first & 15) == 0, CDFO_ERR_SHAPE, "cdfo_mv_offset_head_sm100_fwd: fields must be 16-byte aligned");
   return conv3x3_run(z_c8, wpk, bias, nullptr, out, B, Cin, dg * 27, H, W, 0, 0, first ? 2 : 1, magnitude, first, stream);
 }
 

@@ -51,7 +51,7 @@ struct DcnSm100Params {
 
 constexpr size_t dcn_sm100_smem_bytes() { return kWBytes + kStages * kABytes + 256 + 16 * 8 + 16; }
 
-// Tag for offset/mask given as packed fields [B][dg*9][H*W] x fp16x4 (dy, dx, mask, 0) -- what the fused head writes.
+// Tag for offset/mask given as packed fields [B][9 taps][dg/gp][H*W][gp] x fp16x4 (dy, dx, mask, 0) -- what the fused head writes.
 struct FieldsH4 { uint2 v; };
 
 template <typename OffT> __device__ __forceinline__ float ld_stream(const OffT *p);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_sm100_ke
       const int h = tc.h0 + ty, w = tc.w0 + tx;
       const bool live = h < p.H && w < p.W;
       const int pixc = min(h, p.H - 1) * p.W + min(w, p.W - 1);  // ragged tiles: clamp the address, zero the mask
-      s.off = offset + (size_t)tc.b * p.off_bstride + pixc;
+      s.off = offset + (size_t)tc.b * p.off_bstride + (kPacked ? (size_t)pixc * (p.dg == 16 ? 2 : 1) : (size_t)pixc);
       s.msk = mask + (size_t)tc.b * p.msk_bstride + pixc;
       s.x = p.x + ((size_t)(tc.b % p.x_batch) * 16 + quad0) * plane_q + Wp + 1;  // + border shift
       s.hb = (float)(h - 1);
@@ -228,8 +228,9 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_sm100_ke
 #pragma unroll
       for (int qi = 0; qi < kQuads; ++qi) {
         if constexpr (kPacked) {
-          // one 8-byte load per (pixel, group, tap): lanes = consecutive pixels -> 256 contiguous bytes per warp
-          const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(s.off) + gmsk[qi] + tap * P);
+          // fields [B][9 taps][dg/gp][H*W][gp] x (dy, dx, m, 0), gp = 2 for dg = 16 else 1; s.off points at (b, pixel * gp)
+          const int g = (quad0 + qi) >> p.gshift, gp = p.dg == 16 ? 2 : 1;
+          const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(s.off) + ((size_t)tap * (p.dg / gp) + g / gp) * P * gp + g % gp);
           const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
           o[qi * 3 + 0] = d.x;
           o[qi * 3 + 1] = d.y;

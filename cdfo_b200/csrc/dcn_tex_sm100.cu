@@ -12,18 +12,22 @@
 // fetch of an fp16x4 texel costs 15 wavefronts and ~20 instructions, independent of how scattered the offsets are.
 //   * x lives in HBM as "q4t": [xB][16 quads][H+3][Wpt] texels of 4 fp16 channels with the same zero border as q4p
 //     (1 before, 2 after; Wpt = W+3 rounded up to 4 texels so that the row pitch is 32-byte aligned); every sample
-//     is one pitch-linear 2-D texture whose row axis folds the 16 quad planes.  The reference's inside test and its
+//     the whole tensor is ONE pitch-linear 2-D texture whose row axis folds (sample, quad plane, row).  The reference's inside test and its
 //     per-corner zero padding become: clamp the sample position to [-1, H] x [-1, W], read the zero border.
-//   * offsets / mask arrive as packed fields [B][dg*9][H*W] x fp16x4 (dy, dx, mask, 0) -- what the fused head
+//   * offsets / mask arrive as packed fields [B][9 taps][dg/gp][H*W][gp] x fp16x4 (dy, dx, mask, 0), gp = 2 for dg = 16
+//     (a warp's 32 pixels x 2 groups = 512 contiguous bytes per 16-byte load), else 1 -- what the fused head
 //     (conv3x3_sm100.cu) writes; the MV prior is added here, in the reference's fp32 order (residual + flow, then
 //     base + offset).
 //   * the filter weights are the texture unit's (8 fractional bits): the blended value deviates from the fp32
 //     bilinear by <= 2^-9 of the local texel differences, the same order as the bf16/fp16 rounding of the A operand;
 //     the exact-arithmetic gather (bit-exact floor indices, cdfo_dcn_sample_index) stays available in dcn_sm100.cu.
-//   * implicit GEMM as before: producers write the fp16 A operand of a tap (128 px x 64 ci) into a 4-stage shared
-//     memory ring in the tcgen05 canonical K-major layout, one thread issues tcgen05.mma (M128 N64 K16, fp16 -> fp32
-//     in TMEM), 4 warps drain TMEM (+ bias) to NCHW fp32 or c8 bf16.  Producers are software-pipelined two taps deep
+//   * implicit GEMM: producers write the fp16 A operand of a tap (128 px x 64 ci) with tcgen05.st into a 4-stage ring in
+//     TENSOR MEMORY (32 columns per stage, two K elements per column) -- the operand never touches shared memory, whose
+//     data stage is the bottleneck -- one thread issues tcgen05.mma with A in TMEM (M128 N64 K16, fp16 -> fp32), 4 warps
+//     drain the accumulator (+ bias) to NCHW fp32 or c8 bf16.  Producers are software-pipelined two taps deep
 //     (fields of tap t+2 and the texture fetches of tap t+1 are in flight while tap t is packed).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "cdfo_common.cuh"
@@ -44,11 +48,12 @@ constexpr int kALbo = kTileM * 16;
 constexpr int kBLbo = 64 * 16;
 constexpr int kSbo = 128;
 constexpr int kTapWBytes = 64 * 64 * 2;
-constexpr int kMaxTex = 32;
+constexpr int kTmemCols = 256;        // [0,64) accumulator, [64,192) A operand ring: 4 stages x 32 columns (128 rows x 64 fp16)
+constexpr int kAColBase = 64, kAColsPerStage = 32;
 
 struct Params {
-  cudaTextureObject_t tex[kMaxTex];  // one per x sample
-  const uint2 *fields;               // [B][dg*9][H*W] (dy, dx, m, 0) fp16
+  cudaTextureObject_t tex;           // ONE pitch-2D texture over all x samples: rows = (sample * 16 + quad) * (H + 3) + row
+  const uint2 *fields;               // [B][9 taps][dg/gp][H*W][gp] (dy, dx, m, 0) fp16, gp = 2 when dg = 16, else 1
   const float *mv;                   // [B][2][H*W] (x, y) or nullptr
   const uint8_t *wpk;                // [9][8][64][8] fp16
   const float *bias;
@@ -61,7 +66,7 @@ struct Params {
   int tiles_x, tiles_per_img, num_tiles;
 };
 
-constexpr size_t smem_bytes() { return kWBytes + kStages * kABytes + 256 + 16 * 8 + 16; }
+constexpr size_t smem_bytes() { return kWBytes + 256 + 16 * 8 + 16; }
 
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -70,6 +75,11 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
 // streaming 8-byte load that does not allocate in L1: the fields are read exactly once, and an allocating miss costs
 // the L1TEX data stage ~6.6 wavefronts per 256-byte warp request (fill + read-out) instead of the 2 of the payload.
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p) {
   uint2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
@@ -92,12 +102,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+template <bool kDG16>
 __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm100_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *wsm = smem;
-  uint8_t *asmem = smem + kWBytes;
-  float *bias_s = reinterpret_cast<float *>(smem + kWBytes + kStages * kABytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + kStages * kABytes + 256);
+  float *bias_s = reinterpret_cast<float *>(smem + kWBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + 256);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
   // barrier map: [0,4) A stage full, [4,8) A stage empty, 8 accumulator full, 12 weights
   const uint32_t bar0 = ptx::smem_u32(bars);
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
         ptx::bulk_g2s(ptx::smem_u32(wsm) + t * kTapWBytes, p.wpk + t * kTapWBytes, kTapWBytes, BAR(12));
     }
     __syncwarp();
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 64);
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -140,13 +150,12 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
           ptx::mbar_wait(BAR(stage), phase);
           ptx::tc_fence_after();
           if (lane == 0) {
-            const uint32_t a0 = ptx::smem_u32(asmem) + stage * kABytes;
+            const uint32_t a0 = tmem_base + kAColBase + stage * kAColsPerStage;   // A operand of this tap lives in TMEM
             const uint32_t b0 = ptx::smem_u32(wsm) + tap * kTapWBytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t ad = ptx::make_smem_desc(a0 + j * 2 * kALbo, kALbo, kSbo);
               const uint64_t bd = ptx::make_smem_desc(b0 + j * 2 * kBLbo, kBLbo, kSbo);
-              ptx::umma_f16(tmem_base, ad, bd, idesc, (tap | j) != 0);
+              ptx::umma_f16_ts(tmem_base, a0 + j * 8, bd, idesc, (tap | j) != 0);
             }
             ptx::umma_commit(BAR(4 + stage));
             if (tap == 8) ptx::umma_commit(BAR(8));
@@ -194,35 +203,42 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
     }
   } else {
     // =========================== producers: fields -> texture fetch -> x mask -> A operand ===========================
+    // The loop is bound by instruction issue (ncu: removing the texture fetches altogether changes nothing), so it is
+    // written for instruction count: taps fully unrolled (18 steps = 2 tiles per trip, so that the tap index, the tap's
+    // base coordinates and the double-buffer index are compile-time), one 64-bit pointer per thread for the fields
+    // (two coalesced 16-byte loads per tap when dg = 16), no liveness handling (rows of ragged tiles compute finite garbage that
+    // the epilogue never stores; MMA rows are independent), no w clamp (border addressing returns 0 outside the frame).
     const int ptid = tid - kEpiWarps * 32;
     const int row = ptid & (kTileM - 1);
     const int ty = row >> 5, tx = row & 31;
     const int quad0 = (ptid / kTileM) * 4;
-    const float Hf = (float)p.H, Wf = (float)p.W;
-    float plane_y[4];   // texture row of image row -1.5 of this thread's quad planes (+0.5 texel centre, +1 border)
-    int kfield[4];      // uint2 offset of tap 0 of each quad's deformable group
+    const float Hf = (float)p.H;
+    const int dg = p.dg;
+    int goff[4];        // this thread's deformable groups (dg < 16 only)
 #pragma unroll
-    for (int qi = 0; qi < 4; ++qi) {
-      plane_y[qi] = (float)((quad0 + qi) * (p.H + 3)) + 1.5f;
-      kfield[qi] = ((quad0 + qi) >> p.gshift) * 9 * P;
-    }
+    for (int qi = 0; qi < 4; ++qi) goff[qi] = (quad0 + qi) >> p.gshift;
+    const cudaTextureObject_t tex = p.tex;   // kernel parameter: provably warp-uniform (a per-tile handle made ptxas wrap
+                                             // every fetch in a divergence loop: ~12 extra instructions per sample)
+    const size_t tap_stride = (size_t)P * dg;   // uint2 elements between taps of one sample
+    const size_t pair_stride = (size_t)P * 2;   // dg = 16: between consecutive group pairs
 
     struct Pix {   // per-tile state of the pixel this thread owns
-      const uint2 *f;
-      cudaTextureObject_t tex;
-      float hb, wb, mvx, mvy;
-      bool live;
+      const uint2 *f;                 // fields of tap 0 (dg = 16: already at this thread's first group pair)
+      float py;                       // texture row of image row -1.5 of this thread's first quad plane (+1 border, +0.5 centre)
+      float hb[3], wb[3], mvx, mvy;   // hb[i] = h - 1 + i;  wb[j] = w - 1 + j + 1.5 (border shift + texel centre)
     };
     auto pix_state = [&](int tile) {
       Pix s;
       const TileCoord tc = tile_coord(p, tile);
       const int h = tc.h0 + ty, w = tc.w0 + tx;
-      s.live = h < p.H && w < p.W;
       const int pixc = min(h, p.H - 1) * p.W + min(w, p.W - 1);
-      s.f = p.fields + (size_t)tc.b * p.f_bstride + pixc;
-      s.tex = p.tex[tc.b % p.x_batch];
-      s.hb = (float)(h - 1);
-      s.wb = (float)(w - 1);
+      s.f = p.fields + (size_t)tc.b * p.f_bstride + (kDG16 ? ((size_t)(quad0 >> 1) * P + pixc) * 2 : (size_t)pixc);
+      s.py = (float)(((tc.b % p.x_batch) * 16 + quad0) * (p.H + 3)) + 1.5f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        s.hb[i] = (float)(h - 1 + i);
+        s.wb[i] = (float)(w - 1 + i) + 1.5f;
+      }
       s.mvx = p.mv ? __ldg(p.mv + ((size_t)tc.b * 2 + 0) * P + pixc) : 0.f;
       s.mvy = p.mv ? __ldg(p.mv + ((size_t)tc.b * 2 + 1) * P + pixc) : 0.f;
       return s;
@@ -234,72 +250,73 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
     if (total > 0) {
       // F: field-fetch cursor (two steps ahead of the consumer), I: texture-issue cursor (one step ahead)
       Pix fpix = pix_state(blockIdx.x), ipix = fpix;
-      int ftile = blockIdx.x, ftap = 0, iti = 0, itj = 0;
+      int ftile = blockIdx.x;
       uint2 f[4];
-      auto fetch_fields = [&]() {
+      auto fetch_fields = [&](int tap) {
+        const uint2 *src = fpix.f + (size_t)tap * tap_stride;
+        if (kDG16) {
+          // lanes = consecutive pixels, 16 bytes (two groups) each: 512 contiguous bytes per warp request
+          const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(src)), c = ld_stream_u4(reinterpret_cast<const uint4 *>(src + pair_stride));
+          f[0] = make_uint2(a.x, a.y); f[1] = make_uint2(a.z, a.w); f[2] = make_uint2(c.x, c.y); f[3] = make_uint2(c.z, c.w);
+        } else {
 #pragma unroll
-        for (int qi = 0; qi < 4; ++qi) f[qi] = ld_stream_u2(fpix.f + kfield[qi] + ftap * P);
-        if (++ftap == 9) {
-          ftap = 0;
-          ftile += gridDim.x;
-          if (ftile < p.num_tiles) fpix = pix_state(ftile);
+          for (int qi = 0; qi < 4; ++qi) f[qi] = ld_stream_u2(src + (size_t)goff[qi] * P);
         }
       };
-      auto issue = [&](Buf &b) {
-        const float hb = ipix.hb + (float)iti, wb = ipix.wb + (float)itj;
+      auto issue = [&](Buf &b, int ti, int tj) {
 #pragma unroll
         for (int qi = 0; qi < 4; ++qi) {
           const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&f[qi].x));
           // reference order: offset = residual + flow (arch :3347), then h_im = base + offset (.cu:614-615)
-          const float h_im = __fadd_rn(hb, __fadd_rn(d.x, ipix.mvy));
-          const float w_im = __fadd_rn(wb, __fadd_rn(d.y, ipix.mvx));
-          const float hc = fminf(fmaxf(h_im, -1.f), Hf), wc = fminf(fmaxf(w_im, -1.f), Wf);  // NaN -> -1 -> zero border
-          b.v[qi] = tex2D<float4>(ipix.tex, wc + 1.5f, hc + plane_y[qi]);
-          const uint32_t mm = __byte_perm(f[qi].y, 0, 0x1010);   // (m, m) fp16x2
-          b.m2[qi] = ipix.live ? mm : 0u;
-        }
-        if (++itj == 3) {
-          itj = 0;
-          if (++iti == 3) {   // the F cursor entered the next tile one step ago
-            iti = 0;
-            ipix = fpix;
-          }
+          const float h_im = __fadd_rn(ipix.hb[ti], __fadd_rn(d.x, ipix.mvy));
+          const float w_t = __fadd_rn(ipix.wb[tj], __fadd_rn(d.y, ipix.mvx));
+          const float hc = fminf(fmaxf(h_im, -1.f), Hf);   // stay inside this quad's plane (+ zero border); NaN -> -1 -> 0
+          b.v[qi] = tex2D<float4>(tex, w_t, hc + (ipix.py + (float)(qi * (p.H + 3))));
+          b.m2[qi] = __byte_perm(f[qi].y, 0, 0x1010);      // (m, m) fp16x2
         }
       };
       int stage = 0, phase = 0;
       auto consume = [&](const Buf &b) {
         ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
-        uint8_t *a_dst = asmem + stage * kABytes + (quad0 >> 1) * kALbo + row * 16;
+        ptx::tc_fence_after();
+        uint32_t o[8];
 #pragma unroll
-        for (int pair = 0; pair < 2; ++pair) {
-          uint32_t o[4];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int qi = pair * 2 + e;
-            const __half2 m2 = *reinterpret_cast<const __half2 *>(&b.m2[qi]);
-            o[e * 2 + 0] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].x, b.v[qi].y)));
-            o[e * 2 + 1] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].z, b.v[qi].w)));
-          }
-          *reinterpret_cast<uint4 *>(a_dst + pair * kALbo) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int qi = 0; qi < 4; ++qi) {
+          const __half2 m2 = *reinterpret_cast<const __half2 *>(&b.m2[qi]);
+          o[qi * 2 + 0] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].x, b.v[qi].y)));
+          o[qi * 2 + 1] = h2_as_u32(__hmul2(m2, __floats2half2_rn(b.v[qi].z, b.v[qi].w)));
         }
-        ptx::fence_proxy_async_smem();
+        // row = TMEM lane (this warp's quarter is (warp % 4) = row / 32), K elements quad0*4 .. +15 = columns quad0*2 .. +7
+        ptx::tmem_st8(tmem_base + ((uint32_t)(row & ~31) << 16) + kAColBase + stage * kAColsPerStage + quad0 * 2, o);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
 
       Buf buf[2];
-      fetch_fields();        // fields of step 0
-      issue(buf[0]);         // textures of step 0
-      if (total > 1) fetch_fields();   // fields of step 1
-      for (int g = 0; g < total; g += 2) {
+      fetch_fields(0);         // fields of step 0
+      issue(buf[0], 0, 0);     // textures of step 0
+      fetch_fields(1);         // fields of step 1 (every tile has 9 steps)
+      bool running = true;
+      for (int s0 = 0; running; s0 += 18) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int s = g + u;
-          if (s < total) {
-            if (s + 1 < total) issue(buf[u ^ 1]);
-            if (s + 2 < total) fetch_fields();
-            consume(buf[u]);
+        for (int u = 0; u < 18; ++u) {
+          const int s = s0 + u;
+          if (s >= total) { running = false; break; }
+          const int tap_i = (u + 1) % 9, tap_f = (u + 2) % 9;
+          if (s + 1 < total) {
+            if (tap_i == 0) ipix = fpix;        // the F cursor entered this tile one step ago
+            issue(buf[(u + 1) & 1], tap_i / 3, tap_i % 3);
           }
+          if (s + 2 < total) {
+            if (tap_f == 0) {
+              ftile += gridDim.x;
+              fpix = pix_state(ftile);
+            }
+            fetch_fields(tap_f);
+          }
+          consume(buf[u & 1]);
         }
       }
     }
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // W [64 co][64 ci][3][3] fp32 -> [tap][kc][co][8] fp16
@@ -337,19 +354,19 @@ __global__ void pack_q4t_kernel(const float *__restrict__ x, uint2 *__restrict__
 }
 
 // ---- texture objects over caller-owned linear memory, cached by (device, pointer, shape) ----
-struct TexEntry { int dev; const void *ptr; int H, Wpt; cudaTextureObject_t tex; unsigned long long stamp; };
+struct TexEntry { int dev; const void *ptr; int rows, Wpt; cudaTextureObject_t tex; unsigned long long stamp; };
 static std::mutex g_mu;
 static TexEntry g_cache[64];
 static int g_cache_n = 0;
 static unsigned long long g_stamp = 0;
 
-static cudaError_t get_texture(const void *ptr, int H, int W, int Wpt, cudaTextureObject_t *out) {
+static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaTextureObject_t *out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(g_mu);
   for (int i = 0; i < g_cache_n; ++i)
-    if (g_cache[i].dev == dev && g_cache[i].ptr == ptr && g_cache[i].H == H && g_cache[i].Wpt == Wpt) {
+    if (g_cache[i].dev == dev && g_cache[i].ptr == ptr && g_cache[i].rows == rows && g_cache[i].Wpt == Wpt) {
       g_cache[i].stamp = ++g_stamp;
       *out = g_cache[i].tex;
       return cudaSuccess;
@@ -359,7 +376,7 @@ static cudaError_t get_texture(const void *ptr, int H, int W, int Wpt, cudaTextu
   rd.res.pitch2D.devPtr = const_cast<void *>(ptr);
   rd.res.pitch2D.desc = cudaCreateChannelDescHalf4();
   rd.res.pitch2D.width = (size_t)W + 3;
-  rd.res.pitch2D.height = (size_t)16 * (H + 3);
+  rd.res.pitch2D.height = (size_t)rows;
   rd.res.pitch2D.pitchInBytes = (size_t)Wpt * 8;
   cudaTextureDesc td = {};
   td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;
@@ -378,7 +395,7 @@ static cudaError_t get_texture(const void *ptr, int H, int W, int Wpt, cudaTextu
       if (g_cache[i].stamp < g_cache[slot].stamp) slot = i;
     cudaDestroyTextureObject(g_cache[slot].tex);
   }
-  g_cache[slot] = TexEntry{dev, ptr, H, Wpt, t, ++g_stamp};
+  g_cache[slot] = TexEntry{dev, ptr, rows, Wpt, t, ++g_stamp};
   *out = t;
   return cudaSuccess;
 }
@@ -438,20 +455,19 @@ static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, c
   CDFO_REQUIRE(dg == 1 || dg == 2 || dg == 4 || dg == 8 || dg == 16, CDFO_ERR_UNSUPPORTED,
                "cdfo_dcn_tex_sm100_fwd: deformable groups must divide 16 (got %d)", dg);
   CDFO_REQUIRE(out_mode == 0 || out_mode == 1, CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: out_mode %d", out_mode);
-  CDFO_REQUIRE(((uintptr_t)wpk & 15) == 0 && ((uintptr_t)x_q4t & 511) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)fields & 7) == 0,
-               CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: x_q4t must be 512-byte aligned (texture base), wpk / y 16-byte, fields 8-byte");
-  CDFO_REQUIRE(16ll * (H + 3) <= 65000 && W + 3 <= 131072, CDFO_ERR_UNSUPPORTED,
-               "cdfo_dcn_tex_sm100_fwd: frame %d x %d exceeds the 2-D linear texture limits (H <= 4059)", H, W);
+  CDFO_REQUIRE(((uintptr_t)wpk & 15) == 0 && ((uintptr_t)x_q4t & 511) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)fields & 15) == 0,
+               CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: x_q4t must be 512-byte aligned (texture base), wpk / y / fields 16-byte");
+  CDFO_REQUIRE(W + 3 <= 131072, CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: frame width %d exceeds the 2-D linear texture limit", W);
   dtex::Params p;
   p.x_batch = x_batch > 0 ? x_batch : B;
   CDFO_REQUIRE(B % p.x_batch == 0, CDFO_ERR_SHAPE, "cdfo_dcn_tex_sm100_fwd: B (%d) must be a multiple of x_batch (%d)", B, p.x_batch);
-  CDFO_REQUIRE(p.x_batch <= dtex::kMaxTex, CDFO_ERR_UNSUPPORTED, "cdfo_dcn_tex_sm100_fwd: at most %d distinct x samples per call (got %d)",
-               dtex::kMaxTex, p.x_batch);
+  // one texture over all x samples; fp32 texture coordinates keep >= 8 fractional bits (the filter's resolution) below 65536 rows
+  CDFO_REQUIRE((long long)p.x_batch * 16 * (H + 3) <= 65000, CDFO_ERR_UNSUPPORTED,
+               "cdfo_dcn_tex_sm100_fwd: x_batch * 16 * (H + 3) = %lld rows exceed the 2-D linear texture limit (65000): split the call",
+               (long long)p.x_batch * 16 * (H + 3));
   const int Wpt = cdfo_q4t_pitch(W);
-  const size_t sample_bytes = (size_t)16 * (H + 3) * Wpt * 8;
-  for (int i = 0; i < dtex::kMaxTex; ++i) p.tex[i] = 0;
-  for (int i = 0; i < p.x_batch; ++i) {
-    cudaError_t e = dtex::get_texture((const uint8_t *)x_q4t + (size_t)i * sample_bytes, H, W, Wpt, &p.tex[i]);
+  {
+    cudaError_t e = dtex::get_texture(x_q4t, p.x_batch * 16 * (H + 3), W, Wpt, &p.tex);
     if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cdfo_dcn_tex_sm100_fwd: cudaCreateTextureObject: %s", cudaGetErrorString(e));
   }
   p.fields = (const uint2 *)fields; p.mv = mv; p.wpk = (const uint8_t *)wpk; p.bias = bias; p.y = y;
@@ -472,10 +488,13 @@ static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, c
   static bool attr_done = false;
   const size_t smem = dtex::smem_bytes();
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(dcn_tex_sm100): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  dtex::dcn_tex_sm100_kernel<<<grid, (dtex::kEpiWarps + dtex::kProdWarps) * 32, smem, (cudaStream_t)stream>>>(p);
+  const int threads = (dtex::kEpiWarps + dtex::kProdWarps) * 32;
+  if (dg == 16) dtex::dcn_tex_sm100_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  else dtex::dcn_tex_sm100_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   return check_launch("cdfo_dcn_tex_sm100_fwd");
 }

@@ -51,11 +51,8 @@ def dcn_sm100(x_q4p, offset, mask, wpk, bias=None, mv=None, out_c8=False, num_ct
     xB, _, Hp, Wp, _ = x_q4p.shape
     H, W = Hp - 3, Wp - 3
     if fused_fields is not None:
-        # packed fields [B, dg*9, H, W, 4] fp16 = (dy, dx, mask, 0) per (group*9 + tap, pixel): the fused head's output
-        if fused_fields.dtype != torch.float16 or not fused_fields.is_contiguous() or fused_fields.dim() != 5 or \
-                tuple(fused_fields.shape[2:]) != (H, W, 4):
-            raise _lib.CdfoError("dcn_sm100: fused_fields must be a contiguous fp16 [B, dg*9, H, W, 4] tensor")
-        B, dg = fused_fields.size(0), fused_fields.size(1) // 9
+        # packed fields [B, 9, dg/gp, H, W, gp, 4] fp16 = (dy, dx, mask, 0): the fused head's output
+        B, dg = _check_fields(fused_fields, H, W)
         return _launch(x_q4p, fused_fields, None, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, xB, 0, 0, FIELDS_F16X4)
     B = offset.size(0)
     dg = offset.size(1) // 18
@@ -126,12 +123,11 @@ def pack_q4t(x: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def dcn_tex(x_q4t, fields, wpk16, bias=None, mv=None, out_c8=False, num_ctas=0):
-    """x_q4t [xB,16,H+3,Wpt,4] fp16; fields [B, dg*9, H, W, 4] fp16 (dy, dx, mask, 0); mv [B,2,H,W] fp32 or None.
+    """x_q4t [xB,16,H+3,Wpt,4] fp16; fields [B, 9, H, W, dg, 4] fp16 (dy, dx, mask, 0); mv [B,2,H,W] fp32 or None.
     Returns [B,64,H,W] fp32 (out_c8=False) or [B,8,H,W,8] bf16."""
     xB, _, Hp, _, _ = x_q4t.shape
-    if fields.dtype != torch.float16 or not fields.is_contiguous() or fields.dim() != 5 or fields.size(4) != 4:
-        raise _lib.CdfoError("dcn_tex: fields must be a contiguous fp16 [B, dg*9, H, W, 4] tensor")
-    B, K, H, W, _ = fields.shape
+    H, W = fields.size(3), fields.size(4)
+    B, dg = _check_fields(fields, H, W)
     if H != Hp - 3 or x_q4t.size(3) != _lib.lib().cdfo_q4t_pitch(W) or x_q4t.dtype != torch.float16 or not x_q4t.is_contiguous():
         raise _lib.CdfoError("dcn_tex: x_q4t does not match the %dx%d fields (use pack_q4t)" % (H, W))
     if B % xB:
@@ -149,7 +145,7 @@ def dcn_tex(x_q4t, fields, wpk16, bias=None, mv=None, out_c8=False, num_ctas=0):
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     _lib.call("cdfo_dcn_tex_sm100_fwd", _lib.ptr(x_q4t), _lib.ptr(fields), _lib.ptr(mv), _lib.ptr(wpk16), _lib.ptr(bias),
-              _lib.ptr(y), B, H, W, K // 9, 1 if out_c8 else 0, int(num_ctas), int(xB), ctypes.c_longlong(0),
+              _lib.ptr(y), B, H, W, int(dg), 1 if out_c8 else 0, int(num_ctas), int(xB), ctypes.c_longlong(0),
               _lib.stream_ptr(fields.device))
     if ev is not None:
         ev[1].record()
@@ -162,7 +158,8 @@ def dcn_tex_stacked(x_q4t, fields, wpk16, bias, mv, stack, group_chunk):
     """dcn_tex writing into `stack` [n_seq, chunks, H, W, 8] bf16: sample s = g * n_seq + b of the group-major batch lands in
     chunks [group_chunk[g], +8) of stack[b] (cdfo_dcn_tex_sm100_stacked_fwd)."""
     xB = x_q4t.size(0)
-    B, K, H, W, _ = fields.shape
+    H, W = fields.size(3), fields.size(4)
+    B, dg = _check_fields(fields, H, W)
     n_seq, chunks = stack.size(0), stack.size(1)
     if fields.dtype != torch.float16 or not fields.is_contiguous() or stack.dtype != torch.bfloat16 or not stack.is_contiguous() or \
             tuple(stack.shape[2:]) != (H, W, 8) or B % n_seq or len(group_chunk) != B // n_seq:
@@ -174,8 +171,44 @@ def dcn_tex_stacked(x_q4t, fields, wpk16, bias, mv, stack, group_chunk):
         ev[0].record()
     _lib.call("cdfo_dcn_tex_sm100_stacked_fwd", _lib.ptr(x_q4t), _lib.ptr(fields), _lib.ptr(None if mv is None else mv.contiguous().float()),
               _lib.ptr(wpk16), _lib.ptr(None if bias is None else bias.detach().contiguous().float()), _lib.ptr(stack),
-              int(n_seq), len(group_chunk), int(chunks), grp, H, W, K // 9, int(xB), _lib.stream_ptr(fields.device))
+              int(n_seq), len(group_chunk), int(chunks), grp, H, W, int(dg), int(xB), _lib.stream_ptr(fields.device))
     if ev is not None:
         ev[1].record()
         event_log.append((ev[0], ev[1], B * H * W, 8))
     return None
+
+
+def _check_fields(fields, H, W):
+    """fields [B, 9, dg/gp, H, W, gp, 4] fp16 with gp = 2 when dg = 16, else 1 -> (B, dg)."""
+    if fields.dtype != torch.float16 or not fields.is_contiguous() or fields.dim() != 7 or fields.size(1) != 9 or \
+            tuple(fields.shape[3:5]) != (H, W) or fields.size(6) != 4:
+        raise _lib.CdfoError("fields must be a contiguous fp16 [B, 9, dg/gp, H, W, gp, 4] tensor")
+    dg = fields.size(2) * fields.size(5)
+    if fields.size(5) != (2 if dg == 16 else 1):
+        raise _lib.CdfoError("fields: group pairing must be 2 for 16 deformable groups and 1 otherwise")
+    return fields.size(0), dg
+
+
+def fields_shape(B, dg, H, W):
+    gp = 2 if dg == 16 else 1
+    return (B, 9, dg // gp, H, W, gp, 4)
+
+
+def pack_fields(offset, mask, dg):
+    """Reference-layout offset [B, dg*18, H, W] (channel 2*(g*9+tap) + {0: dy, 1: dx}) and mask [B, dg*9, H, W] ->
+    packed fields [B, 9, dg/gp, H, W, gp, 4] fp16 = (dy, dx, mask, 0), group g = pair * gp + e."""
+    B, _, H, W = offset.shape
+    gp = 2 if dg == 16 else 1
+    o = offset.reshape(B, dg // gp, gp, 9, 2, H, W).permute(0, 3, 1, 5, 6, 2, 4)          # [B, 9, dg/gp, H, W, gp, 2]
+    m = mask.reshape(B, dg // gp, gp, 9, H, W).permute(0, 3, 1, 4, 5, 2).unsqueeze(-1)     # [B, 9, dg/gp, H, W, gp, 1]
+    return torch.cat([o, m, torch.zeros_like(m)], dim=-1).half().contiguous()
+
+
+def unpack_fields(fields):
+    """Packed fields -> (offset [B, dg*18, H, W], mask [B, dg*9, H, W]) fp32 in the reference's channel order."""
+    B, _, npair, H, W, gp, _ = fields.shape
+    dg = npair * gp
+    f = fields.float()
+    off = f[..., :2].permute(0, 2, 5, 1, 6, 3, 4).reshape(B, dg * 18, H, W).contiguous()   # [B, pair, gp, 9, 2, H, W]
+    msk = f[..., 2].permute(0, 2, 5, 1, 3, 4).reshape(B, dg * 9, H, W).contiguous()
+    return off, msk

@@ -84,13 +84,14 @@ _head_cache = {}
 
 
 def _head_weights(c2, dg):
-    """conv_offset[-1] with its output channels permuted into (dy_k, dx_k, m_k) triples, k = g*9 + tap
-    (reference channels 2k, 2k+1, dg*18 + k: the chunk/cat of arch:3341-3345), packed for the tcgen05 conv."""
+    """conv_offset[-1] with its output channels permuted into (dy, dx, m) triples in the order k' = tap*dg + g (reference
+    channels 2k, 2k+1, dg*18 + k with k = g*9 + tap: the chunk/cat of arch:3341-3345), packed for the tcgen05 conv."""
     key = id(c2.weight)
     hit = _head_cache.get(key)
     if hit is not None and hit[0] == (c2.weight._version, c2.bias._version):
         return hit[1], hit[2]
-    k = torch.arange(dg * 9, device=c2.weight.device)
+    kp = torch.arange(dg * 9, device=c2.weight.device)
+    k = (kp % dg) * 9 + kp // dg
     perm = torch.stack([2 * k, 2 * k + 1, dg * 18 + k], dim=1).reshape(-1)
     w = c2.weight.detach().index_select(0, perm).contiguous()
     wpk = conv.pack_weight(w)
@@ -103,7 +104,7 @@ def _head_weights(c2, dg):
 def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     """Learned offset residual and mask of MVDualAttAlignment WITHOUT the MV prior (arch:3339-3350 minus the
     `+ flow.flip(1).repeat(...)` term, which the DCN kernel adds itself), as packed fields
-    [B, dg*9, H, W, 4] fp16 = (10*tanh(dy1) + 10*tanh(dy2), same for dx, sigmoid(m1 + m2), 0) per k = g*9 + tap.
+    [B, 9, dg/gp, H, W, gp, 4] fp16 = (10*tanh(dy1) + 10*tanh(dy2), same for dx, sigmoid(m1 + m2), 0) per (tap, pixel, group).
     Both conv_offset layers run in the tcgen05 convolution kernel; tanh / sum / sigmoid are its epilogue."""
     B = extra_feat.size(0)
     c0, c2 = mod.conv_offset._modules["0"], mod.conv_offset._modules["2"]
@@ -111,7 +112,7 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     H, W = z.shape[2:4]
     dg = mod.deformable_groups
     wpk, bias = _head_weights(c2, dg)
-    first = torch.empty((B, dg * 9, H, W, 4), dtype=torch.float16, device=z.device)
+    first = torch.empty(dcn_sm100.fields_shape(B, dg, H, W), dtype=torch.float16, device=z.device)
     fields = torch.empty_like(first)
     args = (B, 64, dg, H, W, ctypes.c_float(float(mod.max_residue_magnitude)), _lib.stream_ptr(z.device))
     _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[:B]), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(None),
@@ -121,12 +122,7 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     return fields
 
 
-def unpack_fields(fields):
-    """Packed fields -> (residual [B, dg*18, H, W], mask [B, dg*9, H, W]) fp32 in the reference's channel order."""
-    B, K, H, W, _ = fields.shape
-    f = fields.float()
-    residual = torch.stack([f[..., 0], f[..., 1]], dim=2).reshape(B, 2 * K, H, W)
-    return residual, f[..., 2].contiguous()
+unpack_fields = dcn_sm100.unpack_fields   # (residual [B, dg*18, H, W], mask [B, dg*9, H, W]) in the reference's channel order
 
 
 @torch.no_grad()

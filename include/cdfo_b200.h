@@ -46,8 +46,8 @@ typedef enum cdfo_status {
 } cdfo_status;
 
 typedef enum cdfo_dtype { CDFO_F32 = 0, CDFO_F16 = 1, CDFO_BF16 = 2 } cdfo_dtype;
-/* offset/mask given to cdfo_dcn_sm100_fwd as packed fields [B, dg*9, H, W] x fp16x4 (dy, dx, mask, 0): `offset` points
- * at them, `mask` is ignored. */
+/* offset/mask given to cdfo_dcn_sm100_fwd as packed fields [B, 9 taps, dg/gp, H, W, gp] x fp16x4 (dy, dx, mask, 0), gp = 2 when
+ * dg = 16 and 1 otherwise: `offset` points at them, `mask` is ignored. */
 #define CDFO_FIELDS_F16X4 16
 
 /* Message of the last failing call on this thread ("" if none). */
@@ -113,10 +113,11 @@ int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, 
  * of each (pixel, group, tap) sample is ONE hardware-filtered texture fetch (8 fractional weight bits) instead of four
  * loads and ~30 blend instructions: the op is bound by the L1TEX data stage, not by HBM or issue.
  *   x_q4t  [xB, 16, H+3, Wpt, 4] fp16 from cdfo_pack_q4t (Wpt = cdfo_q4t_pitch(W); 512-byte aligned base)
- *   fields [B, dg*9, H, W] x fp16x4 (dy, dx, mask, 0): learned residual and mask as cdfo_mv_offset_head_sm100_fwd writes them
+ *   fields [B, 9 taps, dg/gp, H, W, gp] x fp16x4 (dy, dx, mask, 0), gp = 2 when dg = 16 else 1: learned residual and mask as
+ *          cdfo_mv_offset_head_sm100_fwd writes them (a warp's 32 pixels x gp groups are contiguous; 16-byte aligned)
  *   mv     [B, 2, H, W] fp32 (x, y) or NULL: decoded MV prior, added as offset + flow.flip(1).repeat(...) (arch:3347)
  *   wpk    73728 bytes from cdfo_dcn_tex_sm100_pack_weight (fp16); bias [64] fp32 or NULL
- *   y / out_mode / num_ctas / x_batch: as cdfo_dcn_sm100_fwd (x_batch <= 32); fields_bstride in 8-byte elements (<= 0: dense).
+ *   y / out_mode / num_ctas / x_batch: as cdfo_dcn_sm100_fwd (x_batch * 16 * (H + 3) <= 65000 texture rows); fields_bstride in 8-byte elements (<= 0: dense).
  * Texture descriptors over x_q4t are created on first use and cached by (device, pointer, shape); they own no memory. */
 int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias,
                            void *y, int B, int H, int W, int dg, int out_mode, int num_ctas, int x_batch,
@@ -145,8 +146,8 @@ size_t cdfo_q4t_bytes(int B, int C, int H, int W);
 int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                            int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream);
 /* ---- offset / mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3274, :3339-3350) fused into the conv epilogue ----
- * The caller packs conv_offset[-1] with its output channels permuted into triples (dy_k, dx_k, m_k), k = g*9 + tap
- * (reference channels 2k, 2k+1, dg*18 + k).  out = "fields" [B, dg*9, H, W] x fp16x4 (dy, dx, m, 0):
+ * The caller packs conv_offset[-1] with its output channels permuted into triples (dy, dx, m) in the order k' = tap*dg + g
+ * (reference channels 2k, 2k+1, dg*18 + k with k = g*9 + tap).  out = "fields" [B, 9 taps, dg/gp, H, W, gp] x fp16x4 (dy, dx, m, 0):
  *   first == NULL : (magnitude*tanh(dy), magnitude*tanh(dx), m)                                  (evaluation on out_1)
  *   first != NULL : (first.dy + magnitude*tanh(dy), first.dx + magnitude*tanh(dx), sigmoid(first.m + m))
  *                   (evaluation on out_2; first = the previous call's output) = offset_1 + offset_2 and the mask;

@@ -106,11 +106,15 @@ def test_dcn_sm100_full_size_linearity(cuda_dev):
 
 
 def _fields(offset, mask, dg):
-    """Reference-layout offset [B, dg*18, H, W] / mask [B, dg*9, H, W] -> packed fp16 fields [B, dg*9, H, W, 4]."""
-    B, _, H, W = offset.shape
-    o = offset.view(B, dg * 9, 2, H, W)
-    f = torch.stack([o[:, :, 0], o[:, :, 1], mask, torch.zeros_like(mask)], dim=-1)
-    return f.half().contiguous()
+    """Reference-layout offset / mask -> packed fp16 fields [B, 9, H, W, dg, 4]."""
+    from cdfo_b200 import dcn_sm100 as S
+    return S.pack_fields(offset, mask, dg)
+
+
+def _ref_off_mask(fields):
+    """The fp16-rounded offset / mask the kernel really sees, back in the reference layout."""
+    from cdfo_b200 import dcn_sm100 as S
+    return S.unpack_fields(fields)
 
 
 @pytest.mark.parametrize("B,H,W,dg", [(1, 16, 24, 16), (2, 33, 47, 16), (1, 64, 64, 16), (1, 20, 20, 4), (3, 8, 8, 1)])
@@ -122,8 +126,8 @@ def test_dcn_tex_vs_oracle(cuda_dev, B, H, W, dg):
     x, offset, mask, wt, b = _case(B, H, W, dg, seed=H * W + dg)
     x, wt = x.half().float(), wt.half().float()
     fields = _fields(offset, mask, dg)
-    o16 = torch.stack([fields[..., 0], fields[..., 1]], dim=2).reshape(B, dg * 18, H, W).float()
-    ref = O.dcn_forward(x.numpy(), o16.numpy(), fields[..., 2].float().contiguous().numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
+    o16, m16 = _ref_off_mask(fields)
+    ref = O.dcn_forward(x.numpy(), o16.numpy(), m16.numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
     d = lambda t: t.to(cuda_dev)
     y = S.dcn_tex(S.pack_q4t(d(x)), d(fields), S.pack_weight_f16(d(wt)), d(b))
     err = np.abs(y.cpu().numpy() - ref).max()
@@ -140,14 +144,16 @@ def test_dcn_tex_mv_borders_shared_x_c8(cuda_dev):
     x, wt = x[:2].half().float(), wt.half().float()
     offset[:, ::3] = torch.round(offset[:, ::3])
     offset[0, 5] = 1e4
-    offset[1, 6] = float("nan")
+    offset[1, 6] = float("nan")      # dy of (group 0, tap 3)
+    offset[1, 9] = float("nan")      # dx of (group 0, tap 4)
+    offset[2, 11] = -1e4
     g = torch.Generator().manual_seed(9)
     flow = torch.randint(-64 * 3, 64 * 3, (B, 2, H, W), generator=g).float() / 128.0
     fields = _fields(offset, mask, dg)
-    o16 = torch.stack([fields[..., 0], fields[..., 1]], dim=2).reshape(B, dg * 18, H, W).float()
+    o16, m16 = _ref_off_mask(fields)
     full = o16 + flow.flip(1).repeat(1, dg * 9, 1, 1)
     xb = x.repeat(2, 1, 1, 1)                      # output sample b reads x[b % 2]
-    ref = O.dcn_forward(xb.numpy(), full.numpy(), fields[..., 2].float().contiguous().numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
+    ref = O.dcn_forward(xb.numpy(), full.numpy(), m16.numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 1, dg)
     d = lambda t: t.to(cuda_dev)
     xq = S.pack_q4t(d(x))
     y = S.dcn_tex(xq, d(fields), S.pack_weight_f16(d(wt)), d(b), mv=d(flow))
@@ -169,24 +175,18 @@ def test_dcn_tex_full_size_properties(cuda_dev):
     wt = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).half().float().to(cuda_dev)
     w16 = S.pack_weight_f16(wt)
     xq = S.pack_q4t(x1)
-    zero = torch.zeros(B, dg * 9, H, W, 4, dtype=torch.float16, device=cuda_dev)
-    zero[..., 2] = 1.0
+    zoff = torch.zeros(B, dg * 18, H, W, device=cuda_dev)
+    ones = torch.ones(B, dg * 9, H, W, device=cuda_dev)
     conv = torch.nn.functional.conv2d(x1, wt, None, 1, 1)
-    y0 = S.dcn_tex(xq, zero, w16)
+    y0 = S.dcn_tex(xq, S.pack_fields(zoff, ones, dg), w16)
     assert (y0 - conv).abs().max().item() <= 2e-3 * conv.abs().max().item()
-    ints = zero.clone()
-    ints[..., 0] = torch.randint(-3, 4, (B, dg * 9, H, W), generator=g).to(cuda_dev).half()
-    ints[..., 1] = torch.randint(-3, 4, (B, dg * 9, H, W), generator=g).to(cuda_dev).half()
-    off = torch.stack([ints[..., 0], ints[..., 1]], dim=2).reshape(B, dg * 18, H, W).float()
-    msk = ints[..., 2].float().contiguous()
+    ioff = torch.randint(-3, 4, (B, dg * 18, H, W), generator=g).float().to(cuda_dev)
     import cdfo_b200
-    gen = cdfo_b200.dcn._generic_modulated(x1, off, msk, wt, None, 1, 1, 1, 1, dg)
-    yi = S.dcn_tex(xq, ints, w16)
+    gen = cdfo_b200.dcn._generic_modulated(x1, ioff, ones, wt, None, 1, 1, 1, 1, dg)
+    yi = S.dcn_tex(xq, S.pack_fields(ioff, ones, dg), w16)
     assert (yi - gen).abs().max().item() <= 2e-3 * gen.abs().max().item()
-    rnd = zero.clone()
-    rnd[..., :2] = (torch.randn(B, dg * 9, H, W, 2, generator=g) * 2.0).to(cuda_dev).half()
-    rnd[..., 2] = torch.rand(B, dg * 9, H, W, generator=g).to(cuda_dev).half()
-    off = torch.stack([rnd[..., 0], rnd[..., 1]], dim=2).reshape(B, dg * 18, H, W).float()
-    gen = cdfo_b200.dcn._generic_modulated(x1, off, rnd[..., 2].float().contiguous(), wt, None, 1, 1, 1, 1, dg)
+    rnd = S.pack_fields((torch.randn(B, dg * 18, H, W, generator=g) * 2.0).to(cuda_dev), torch.rand(B, dg * 9, H, W, generator=g).to(cuda_dev), dg)
+    off, msk = S.unpack_fields(rnd)
+    gen = cdfo_b200.dcn._generic_modulated(x1, off, msk, wt, None, 1, 1, 1, 1, dg)
     yr = S.dcn_tex(xq, rnd, w16)
     assert (yr - gen).abs().max().item() <= 6e-3 * gen.abs().max().item()

@@ -62,8 +62,7 @@ def main():
         res["sm100_f16off_c8out_us"] = t
         res["sm100_f16off_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
         res["pack_q4p_us"] = timeit(lambda: S.pack_q4p(x), a.iters)
-    o = offset.view(B, dg * 9, 2, H, W)
-    fields = torch.stack([o[:, :, 0], o[:, :, 1], mask, torch.zeros_like(mask)], dim=-1).half().contiguous()
+    fields = S.pack_fields(offset, mask, dg)
     xt, w16 = S.pack_q4t(x), S.pack_weight_f16(wt)
     t = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, out_c8=True, num_ctas=a.ctas), a.iters)
     res["tex_fields_c8out_us"] = t

@@ -17,7 +17,7 @@ o8 = conv.to_c8(o)
 res["conv0_lrelu_2B"] = timeit(lambda: conv.conv3x3(o8, w0, b0, conv.ACT_LRELU))
 z = conv.conv3x3(o8, w0, b0, conv.ACT_LRELU)
 wpk = conv.pack_weight(w2)
-first = torch.empty((B, 144, H, W, 4), device=dev, dtype=torch.float16)
+first = torch.empty((B, 9, 8, H, W, 2, 4), device=dev, dtype=torch.float16)
 fields = torch.empty_like(first)
 args = (B, 64, dg, H, W, ctypes.c_float(10.0), _lib.stream_ptr(dev))
 res["head1"] = timeit(lambda: _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[:B]), _lib.ptr(wpk), _lib.ptr(b2), _lib.ptr(None), _lib.ptr(first), *args))
