@@ -300,20 +300,38 @@ __device__ __forceinline__ void flash_block_fp32_kptr(const float *Qs, const flo
 
 // ------------------------------------------------------------------------------------------------ columns
 // CTA per (b, w): q_c[h] = bh + sum_t kh[t] sq[h+t-4] (zero rows outside the frame), sq[h'] = beta + bump(h').
-// Shared memory: Q for the whole column [Hp][kLd] (Hp = H rounded up to 64), one 64-row V chunk, one P tile.
-constexpr int kColThreads = 256;
-__global__ void __launch_bounds__(kColThreads) lra_col_kernel(const float *__restrict__ vrow_t, const uint8_t *__restrict__ midx,
-                                                             const float *__restrict__ qsel, float *__restrict__ long_out,
-                                                             LraTables t, int H, int W) {
+// The contraction is dense here (64-d queries, H x H scores per column), so it runs on the tensor cores: warp-level
+// mma.sync m16n8k8 TF32 with fp32 accumulation, flash-style (online softmax over 64-key blocks, scores never leave
+// registers).  Each of the 9 warps owns 16-query tiles; Q (also the keys: scores are q_c q_c^T, arch:2228) and V sit in
+// shared memory as TF32-rounded fp32 with a row stride of 68 floats, which makes every fragment load conflict-free.
+// The probabilities feed the second MMA straight from the accumulator registers: the C-fragment column pair (2t, 2t+1)
+// is used as A-fragment key positions (t, t+4), and the V fragment is loaded with the same permutation of the 8 keys.
+// TF32 (10-bit mantissa) on logits of magnitude <~ 1 (q_c is a 9-tap mix of beta + sparse bumps) changes the softmax
+// weights by < 1e-3 relative; the window attention, whose logits reach +-40, stays in fp32 below.
+constexpr int kColWarps = 9, kColThreads = kColWarps * 32;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kColThreads, 1) lra_col_kernel(const float *__restrict__ vrow_t, const uint8_t *__restrict__ midx,
+                                                                const float *__restrict__ qsel, float *__restrict__ long_out,
+                                                                LraTables t, int H, int W) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y, w = blockIdx.x;
   const int HW = H * W;
-  const int Hp = (H + 63) & ~63;
-  float *Q = sm;                  // [Hp][kLd]
-  float *Vc = Q + Hp * kLd;       // [64][kLd]   (first used as scratch for sq)
-  float *Ps = Vc + 64 * kLd;      // [64][kLd]
-  float *sq = Ps + 64 * kLd;      // [H + 8][64]: sq rows -4 .. H+3 (zero outside the frame)
-  const int tid = threadIdx.x;
+  const int Hk = (H + 63) & ~63;          // keys padded to whole 64-key blocks (rows >= H are zero and masked)
+  float *Q = sm;                          // [Hk][kLd] tf32 bit patterns
+  float *V = Q + Hk * kLd;                // [Hk][kLd]; first used as scratch for sq [H + 8][64]
+  float *sq = V;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
   float kh[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) kh[i] = t.kh[i];
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(kColThreads) lra_col_kernel(const float *__res
     sq[e] = v;
   }
   __syncthreads();
-  for (int e = tid; e < Hp * 64; e += kColThreads) {   // Q = conv9 along H (rows >= H: zero queries, never stored)
+  for (int e = tid; e < Hk * 64; e += kColThreads) {   // Q = conv9 along H (rows >= H: zero)
     const int h = e >> 6, c = e & 63;
     float acc = 0.f;
     if (h < H) {
@@ -340,28 +358,98 @@ __global__ void __launch_bounds__(kColThreads) lra_col_kernel(const float *__res
 #pragma unroll
       for (int i = 0; i < 9; ++i) acc = fmaf(kh[i], sq[(h + i) * 64 + c], acc);
     }
-    Q[h * kLd + c] = acc;
+    Q[h * kLd + c] = __uint_as_float(to_tf32(acc));
+  }
+  __syncthreads();   // sq is dead: V overwrites it
+  const float *vsrc = vrow_t + ((size_t)b * W + w) * H * 64;   // contiguous [H][64]
+  for (int e = tid; e < Hk * 16; e += kColThreads) {
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < H) v = *reinterpret_cast<const float4 *>(vsrc + (size_t)r * 64 + c4);
+    v.x = __uint_as_float(to_tf32(v.x)); v.y = __uint_as_float(to_tf32(v.y));
+    v.z = __uint_as_float(to_tf32(v.z)); v.w = __uint_as_float(to_tf32(v.w));
+    *reinterpret_cast<float4 *>(V + r * kLd + c4) = v;
   }
   __syncthreads();
-  const float *vsrc = vrow_t + ((size_t)b * W + w) * H * 64;   // contiguous [H][64]
-  for (int q0 = 0; q0 < H; q0 += 64) {
-    auto load_chunk = [&](int kb) {
-      for (int e = tid; e < 64 * 16; e += kColThreads) {
-        const int r = e >> 4, c4 = (e & 15) * 4;
-        const int h = kb * 64 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h < H) v = *reinterpret_cast<const float4 *>(vsrc + (size_t)h * 64 + c4);
-        *reinterpret_cast<float4 *>(Vc + r * kLd + c4) = v;
+
+  const uint32_t *Qu = reinterpret_cast<const uint32_t *>(Q), *Vu = reinterpret_cast<const uint32_t *>(V);
+  const int n_qt = (H + 15) >> 4, n_kb = Hk >> 6;
+  for (int qt = warp; qt < n_qt; qt += kColWarps) {
+    const int q0 = qt * 16;
+    uint32_t aq[8][4];   // A fragments of the 16 x 64 query tile
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      aq[s][0] = Qu[(q0 + g) * kLd + 8 * s + tq];
+      aq[s][1] = Qu[(q0 + g + 8) * kLd + 8 * s + tq];
+      aq[s][2] = Qu[(q0 + g) * kLd + 8 * s + tq + 4];
+      aq[s][3] = Qu[(q0 + g + 8) * kLd + 8 * s + tq + 4];
+    }
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};   // rows g and g + 8
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int key0 = kb * 64;
+      float sc[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[n][i] = 0.f;
+        const uint32_t *kr = Qu + (key0 + 8 * n + g) * kLd + tq;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_tf32(sc[n], aq[s], kr[8 * s], kr[8 * s + 4]);
       }
-      __syncthreads();
-    };
-    // the keys of chunk kb are rows kb*64 .. of Q itself (scores are q_c q_c^T, arch:2228)
-    const float *Kcur = Q;
-    auto key_chunk = [&](int kb) { Kcur = Q + kb * 64 * kLd; load_chunk(kb); };
-    flash_block_fp32_kptr(Q + q0 * kLd, &Kcur, Vc, Ps, H, key_chunk, [&](int r, int c4, float4 v) {
-      const int h = q0 + r;
-      if (h < H) *reinterpret_cast<float4 *>(long_out + (((size_t)b * H + h) * W + w) * 64 + c4) = v;
-    });
+      // online softmax; C fragment: [0],[1] = row g, keys 2tq, 2tq+1 of the n-th 8-key group; [2],[3] = row g + 8
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int key = key0 + 8 * n + 2 * tq;
+        if (key >= H) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
+        if (key + 1 >= H) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
+        mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+      }
+      float scale[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);    // every block holds at least one live key (key0 < H)
+        scale[r] = expf(m_run[r] - m_new);
+        m_run[r] = m_new;
+        l_run[r] *= scale[r];
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        sc[n][0] = expf(sc[n][0] - m_run[0]); sc[n][1] = expf(sc[n][1] - m_run[0]);
+        sc[n][2] = expf(sc[n][2] - m_run[1]); sc[n][3] = expf(sc[n][3] - m_run[1]);
+        l_run[0] += sc[n][0] + sc[n][1];
+        l_run[1] += sc[n][2] + sc[n][3];
+        o[n][0] *= scale[0]; o[n][1] *= scale[0]; o[n][2] *= scale[1]; o[n][3] *= scale[1];
+      }
+      // O += P V: k-step s = the s-th 8-key group; key position tq <- key 2tq, position tq + 4 <- key 2tq + 1
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t ap[4] = {to_tf32(sc[s][0]), to_tf32(sc[s][2]), to_tf32(sc[s][1]), to_tf32(sc[s][3])};
+        const uint32_t *vr = Vu + (key0 + 8 * s + 2 * tq) * kLd + g;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) mma_tf32(o[n], ap, vr[8 * n], vr[kLd + 8 * n]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    const int h0 = q0 + g, h1 = q0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (h0 < H) *reinterpret_cast<float2 *>(long_out + (((size_t)b * H + h0) * W + w) * 64 + 8 * n + 2 * tq) = make_float2(o[n][0] * inv0, o[n][1] * inv0);
+      if (h1 < H) *reinterpret_cast<float2 *>(long_out + (((size_t)b * H + h1) * W + w) * 64 + 8 * n + 2 * tq) = make_float2(o[n][2] * inv1, o[n][3] * inv1);
+    }
   }
 }
 
@@ -470,13 +558,14 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   lra_mask_kernel<<<dim3(ceil_div(HW, 128), B), 128, 0, s>>>(u, vmax, qv, midx, qsel, HW);
 
   const size_t row_smem = ((size_t)W * 65 + 3 * W + 64 + 256 + 8 * W) * 4 + 2 * (size_t)W * 4;
-  const int Hp = (H + 63) & ~63;
-  const size_t col_smem = ((size_t)(Hp + 128) * kLd + (size_t)(H + 8) * 64) * 4;
+  const int Hk = (H + 63) & ~63;
+  const size_t col_v = (size_t)Hk * kLd > (size_t)(H + 8) * 64 ? (size_t)Hk * kLd : (size_t)(H + 8) * 64;
+  const size_t col_smem = ((size_t)Hk * kLd + col_v) * 4;
   const size_t win_smem = (size_t)3 * 64 * kLd * 4;
   const size_t fuse_smem = ((size_t)128 * 65 + kFusePix * 129) * 4;
   const int kDynMax = 224 * 1024;  // 227 KB opt-in limit minus the kernels' small static shared memory
   CDFO_REQUIRE(row_smem <= (size_t)kDynMax && col_smem <= (size_t)kDynMax, CDFO_ERR_UNSUPPORTED,
-               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 730, H <= 320)", H, W);
+               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 730, H <= 384)", H, W);
   static bool attr = false;
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
