@@ -65,48 +65,116 @@ __global__ void lra_mask_kernel(const float *__restrict__ u, const float *__rest
   qsel[(size_t)b * HW + p] = on ? qv[((size_t)b * 128 + cmax) * HW + p] : 0.f;
 }
 
+constexpr int kLd = 68;   // 68 % 32 == 4: eight consecutive rows hit distinct 16-byte bank groups
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+
+// One 64-key block of a flash pass for a 16-query tile held by one warp (mma.sync m16n8k8 TF32 fragments):
+// sc = raw scores in C-fragment layout ([n][0..1] = row g, keys 8n + 2tq, +1; [n][2..3] = row g + 8); keys >= n_keys are
+// masked here.  Updates the running max / sum and O += P V with V rows [key0, key0 + 64) of Vu (TF32 bits, stride kLd).
+// The probabilities feed the MMA from registers: C-fragment columns (2tq, 2tq+1) are used as A-fragment key positions
+// (tq, tq+4) and the V fragment is loaded with the same permutation of the 8 keys.
+__device__ __forceinline__ void flash_tile_block(float (&sc)[8][4], float (&m_run)[2], float (&l_run)[2], float (&o)[8][4],
+                                                 const uint32_t *__restrict__ Vu, int key0, int n_keys, int g, int tq) {
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int key = key0 + 8 * n + 2 * tq;
+    if (key >= n_keys) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
+    if (key + 1 >= n_keys) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
+    mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+    mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+  }
+  float scale[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    const float m_new = fmaxf(m_run[r], mx[r]);    // every block holds at least one live key (key0 < n_keys)
+    scale[r] = expf(m_run[r] - m_new);
+    m_run[r] = m_new;
+    l_run[r] *= scale[r];
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    sc[n][0] = expf(sc[n][0] - m_run[0]); sc[n][1] = expf(sc[n][1] - m_run[0]);
+    sc[n][2] = expf(sc[n][2] - m_run[1]); sc[n][3] = expf(sc[n][3] - m_run[1]);
+    l_run[0] += sc[n][0] + sc[n][1];
+    l_run[1] += sc[n][2] + sc[n][3];
+    o[n][0] *= scale[0]; o[n][1] *= scale[0]; o[n][2] *= scale[1]; o[n][3] *= scale[1];
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const uint32_t ap[4] = {to_tf32(sc[s][0]), to_tf32(sc[s][2]), to_tf32(sc[s][1]), to_tf32(sc[s][3])};
+    const uint32_t *vr = Vu + (key0 + 8 * s + 2 * tq) * kLd + g;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) mma_tf32(o[n], ap, vr[8 * n], vr[kLd + 8 * n]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ rows
 // CTA per (b, h).  v = qv[:, 64:]; output vrow_t [B][W][H][64] (token-major per column for the column pass).
-constexpr int kRowThreads = 256;
-__global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
-                                                             const float *__restrict__ qsel, float *__restrict__ vrow_t,
-                                                             LraTables t, int H, int W) {
-  extern __shared__ float sm[];
+// Unmasked queries share one softmax distribution (see the header): one weighted sum N0 for all of them.  Masked
+// queries (~20 % of the tokens) get their own softmax over the row: their scores come from the closed form (tables,
+// no dot products), and the P V products run on the tensor cores in 16-query tiles (flash_tile_block above).
+constexpr int kRowWarps = 9, kRowThreads = kRowWarps * 32;
+__global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
+                                                                const float *__restrict__ qsel, float *__restrict__ vrow_t,
+                                                                LraTables t, int H, int W) {
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y, h = blockIdx.x;
   const int HW = H * W;
-  float *vr = sm;                     // [W][65]
-  float *sw = vr + W * 65;            // [W]  beta * s_w
-  float *e0 = sw + W;                 // [W]  exp(beta s_w - m0)
-  float *qs = e0 + W;                 // [W]  q of the masked channel
-  float *n0 = qs + W;                 // [64] common numerator
-  float *red = n0 + 64;               // [256] reduction scratch
-  float *ew = red + 256;              // [8][W] per-warp exponent scratch
-  int *cs = reinterpret_cast<int *>(ew + 8 * W);  // [W] masked channel or -1
-  int *mlist = cs + W;                // [W] indices of masked tokens
+  const int Wk = (W + 63) & ~63;      // keys padded to whole 64-key blocks
+  float *vr = sm;                     // [Wk][kLd] conv1x9(v) as TF32 bits (rows >= W zero)
+  float *Rs = vr + Wk * kLd;          // [64*64] R table
+  float *sw = Rs + 4096;              // [Wk]  beta * s_w
+  float *e0 = sw + Wk;                // [Wk]  exp(beta s_w - m0)
+  float *qs = e0 + Wk;                // [Wk]  q of the masked channel
+  float *n0 = qs + Wk;                // [64] common numerator
+  float *red = n0 + 64;               // [kRowThreads] reduction scratch
+  int *cs = reinterpret_cast<int *>(red + kRowThreads);  // [Wk] masked channel or -1
+  int *mlist = cs + Wk;               // [Wk] indices of masked tokens
   __shared__ int mcount;
   __shared__ float m0_s, d0_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
   float kw[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) kw[i] = t.kw[i];
+  for (int e = tid; e < 4096; e += kRowThreads) Rs[e] = t.r[e];
 
   // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219)
   const float *vbase = qv + ((size_t)b * 128 + 64) * HW + (size_t)h * W;
-  for (int e = tid; e < 64 * W; e += kRowThreads) {
-    const int c = e / W, w = e - c * W;
-    float acc = t.beta;
+  for (int e = tid; e < 64 * Wk; e += kRowThreads) {
+    const int c = e / Wk, w = e - c * Wk;
+    float acc = 0.f;
+    if (w < W) {
+      acc = t.beta;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int cc = c + i - 4;
-      if (cc >= 0 && cc < 64) acc = fmaf(kw[i], __ldg(vbase + (size_t)cc * HW + w), acc);
+      for (int i = 0; i < 9; ++i) {
+        const int cc = c + i - 4;
+        if (cc >= 0 && cc < 64) acc = fmaf(kw[i], __ldg(vbase + (size_t)cc * HW + w), acc);
+      }
     }
-    vr[w * 65 + c] = acc;
+    vr[w * kLd + c] = acc;
   }
   if (tid == 0) mcount = 0;
   __syncthreads();
-  for (int w = tid; w < W; w += kRowThreads) {
-    const int c = midx[(size_t)b * HW + h * W + w];
-    const float q = qsel[(size_t)b * HW + h * W + w];
+  for (int w = tid; w < Wk; w += kRowThreads) {
+    int c = 255;
+    float q = 0.f;
+    if (w < W) {
+      c = midx[(size_t)b * HW + h * W + w];
+      q = qsel[(size_t)b * HW + h * W + w];
+    }
     const bool on = c != 255;
     cs[w] = on ? c : -1;
     qs[w] = q;
@@ -122,7 +190,7 @@ __global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__res
   __syncthreads();
   if (tid == 0) {
     float mm = red[0];
-    for (int i = 1; i < kRowThreads / 32; ++i) mm = fmaxf(mm, red[i]);
+    for (int i = 1; i < kRowWarps; ++i) mm = fmaxf(mm, red[i]);
     m0_s = mm;
   }
   __syncthreads();
@@ -139,13 +207,14 @@ __global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__res
   __syncthreads();
   if (tid == 0) {
     float dd = 0.f;
-    for (int i = 0; i < kRowThreads / 32; ++i) dd += red[i];
+    for (int i = 0; i < kRowWarps; ++i) dd += red[i];
     d0_s = dd;
   }
-  {  // N0[c] = sum_w' e0[w'] v_r[w'][c]: thread = (c, quarter of the row)
+  {  // N0[c] = sum_w' e0[w'] v_r[w'][c]: thread = (c, quarter of the row); exact fp32 (v_r is rounded to TF32 only afterwards)
     const int c = tid & 63, part = tid >> 6;
     float acc = 0.f;
-    for (int w = part; w < W; w += 4) acc = fmaf(e0[w], vr[w * 65 + c], acc);
+    if (part < 4)
+      for (int w = part; w < W; w += 4) acc = fmaf(e0[w], vr[w * kLd + c], acc);
     __syncthreads();
     red[tid] = acc;
     __syncthreads();
@@ -157,40 +226,59 @@ __global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__res
     const int w = e >> 6, c = e & 63;
     if (cs[w] < 0) vrow_t[(((size_t)b * W + w) * H + h) * 64 + c] = n0[c];
   }
-  // masked queries: their own softmax over w' (one warp per query)
-  float *my_e = ew + warp * W;
+  // round v_r to TF32 in place for the tensor-core pass
+  for (int e = tid; e < Wk * 64; e += kRowThreads) {
+    float *p = vr + (e >> 6) * kLd + (e & 63);
+    *p = __uint_as_float(to_tf32(*p));
+  }
+  __syncthreads();
+  // masked queries: own softmax over w'; one warp per tile of 16 masked queries
   const int nm = mcount;
-  for (int qi = warp; qi < nm; qi += kRowThreads / 32) {
-    const int w = mlist[qi];
-    const int c1 = cs[w];
-    const float q1 = qs[w];
-    float mx = -INFINITY;
-    for (int w2 = lane; w2 < W; w2 += 32) {
-      float x = sw[w2];
-      const int c2 = cs[w2];
-      if (c2 >= 0) x = fmaf(q1 * qs[w2], t.r[c1 * 64 + c2], x);
-      my_e[w2] = x;
-      mx = fmaxf(mx, x);
+  const uint32_t *Vu = reinterpret_cast<const uint32_t *>(vr);
+  for (int q0 = warp * 16; q0 < nm; q0 += kRowWarps * 16) {
+    int wq[2], c1[2];
+    float q1[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = q0 + g + 8 * r;
+      wq[r] = qi < nm ? mlist[qi] : -1;
+      c1[r] = wq[r] >= 0 ? cs[wq[r]] : 0;
+      q1[r] = wq[r] >= 0 ? qs[wq[r]] : 0.f;
     }
-    mx = warp_max(mx);
-    float ds = 0.f;
-    for (int w2 = lane; w2 < W; w2 += 32) {
-      const float e = expf(my_e[w2] - mx);
-      my_e[w2] = e;
-      ds += e;
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int key0 = 0; key0 < Wk; key0 += 64) {
+      float sc[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int k = key0 + 8 * n + 2 * tq;      // this thread's two keys of the group (C-fragment columns 2tq, 2tq + 1)
+        const float2 s2 = *reinterpret_cast<const float2 *>(sw + k), q2 = *reinterpret_cast<const float2 *>(qs + k);
+        const int2 c2 = *reinterpret_cast<const int2 *>(cs + k);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          sc[n][2 * r] = c2.x >= 0 ? fmaf(q1[r] * q2.x, Rs[c1[r] * 64 + c2.x], s2.x) : s2.x;
+          sc[n][2 * r + 1] = c2.y >= 0 ? fmaf(q1[r] * q2.y, Rs[c1[r] * 64 + c2.y], s2.y) : s2.y;
+        }
+      }
+      flash_tile_block(sc, m_run, l_run, o, Vu, key0, W, g, tq);
     }
-    ds = warp_sum(ds);
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-    for (int w2 = 0; w2 < W; ++w2) {
-      const float e = my_e[w2];
-      a0 = fmaf(e, vr[w2 * 65 + lane], a0);
-      a1 = fmaf(e, vr[w2 * 65 + 32 + lane], a1);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
-    float *o = vrow_t + (((size_t)b * W + w) * H + h) * 64;
-    o[lane] = a0 / ds;
-    o[32 + lane] = a1 / ds;
-    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (wq[r] < 0) continue;
+      const float inv = 1.f / l_run[r];
+      float *dst = vrow_t + (((size_t)b * W + wq[r]) * H + h) * 64 + 2 * tq;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) *reinterpret_cast<float2 *>(dst + 8 * n) = make_float2(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    }
   }
 }
 
@@ -199,7 +287,6 @@ __global__ void __launch_bounds__(kRowThreads) lra_row_kernel(const float *__res
 // Q / K / V rows have 64 features, row stride kLd floats in shared memory.  Register tile 4 x 4 per thread:
 // thread (ty, tx) owns query rows {ty + 16 i} and key columns {tx + 16 j} of every 64 x 64 score tile, and query rows
 // {ty + 16 i} x channels {4 tx .. 4 tx + 3} of the output: 8 LDS.128 feed 64 FMAs (the v1 kernels were LDS-bound at 2:1).
-constexpr int kLd = 68;   // 68 % 32 == 4: eight consecutive rows hit distinct 16-byte bank groups
 
 // key_chunk(kb) must make *Kptr point at keys kb*64 .. kb*64+63 and rows [0, 64) of Vs hold their values (rows beyond
 // n_keys may hold anything finite: their probabilities are forced to 0), ending with a __syncthreads() if it wrote.
@@ -310,17 +397,6 @@ __device__ __forceinline__ void flash_block_fp32_kptr(const float *Qs, const flo
 // weights by < 1e-3 relative; the window attention, whose logits reach +-40, stays in fp32 below.
 constexpr int kColWarps = 9, kColThreads = kColWarps * 32;
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 __global__ void __launch_bounds__(kColThreads, 1) lra_col_kernel(const float *__restrict__ vrow_t, const uint8_t *__restrict__ midx,
                                                                 const float *__restrict__ qsel, float *__restrict__ long_out,
                                                                 LraTables t, int H, int W) {
@@ -401,42 +477,7 @@ __global__ void __launch_bounds__(kColThreads, 1) lra_col_kernel(const float *__
 #pragma unroll
         for (int s = 0; s < 8; ++s) mma_tf32(sc[n], aq[s], kr[8 * s], kr[8 * s + 4]);
       }
-      // online softmax; C fragment: [0],[1] = row g, keys 2tq, 2tq+1 of the n-th 8-key group; [2],[3] = row g + 8
-      float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int key = key0 + 8 * n + 2 * tq;
-        if (key >= H) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
-        if (key + 1 >= H) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
-        mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
-        mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
-      }
-      float scale[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        const float m_new = fmaxf(m_run[r], mx[r]);    // every block holds at least one live key (key0 < H)
-        scale[r] = expf(m_run[r] - m_new);
-        m_run[r] = m_new;
-        l_run[r] *= scale[r];
-      }
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        sc[n][0] = expf(sc[n][0] - m_run[0]); sc[n][1] = expf(sc[n][1] - m_run[0]);
-        sc[n][2] = expf(sc[n][2] - m_run[1]); sc[n][3] = expf(sc[n][3] - m_run[1]);
-        l_run[0] += sc[n][0] + sc[n][1];
-        l_run[1] += sc[n][2] + sc[n][3];
-        o[n][0] *= scale[0]; o[n][1] *= scale[0]; o[n][2] *= scale[1]; o[n][3] *= scale[1];
-      }
-      // O += P V: k-step s = the s-th 8-key group; key position tq <- key 2tq, position tq + 4 <- key 2tq + 1
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const uint32_t ap[4] = {to_tf32(sc[s][0]), to_tf32(sc[s][2]), to_tf32(sc[s][1]), to_tf32(sc[s][3])};
-        const uint32_t *vr = Vu + (key0 + 8 * s + 2 * tq) * kLd + g;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) mma_tf32(o[n], ap, vr[8 * n], vr[kLd + 8 * n]);
-      }
+      flash_tile_block(sc, m_run, l_run, o, Vu, key0, H, g, tq);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -557,7 +598,8 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
 
   lra_mask_kernel<<<dim3(ceil_div(HW, 128), B), 128, 0, s>>>(u, vmax, qv, midx, qsel, HW);
 
-  const size_t row_smem = ((size_t)W * 65 + 3 * W + 64 + 256 + 8 * W) * 4 + 2 * (size_t)W * 4;
+  const int Wk = (W + 63) & ~63;
+  const size_t row_smem = ((size_t)Wk * kLd + 4096 + 3 * (size_t)Wk + 64 + kRowThreads + 2 * (size_t)Wk) * 4;
   const int Hk = (H + 63) & ~63;
   const size_t col_v = (size_t)Hk * kLd > (size_t)(H + 8) * 64 ? (size_t)Hk * kLd : (size_t)(H + 8) * 64;
   const size_t col_smem = ((size_t)Hk * kLd + col_v) * 4;
@@ -565,7 +607,7 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   const size_t fuse_smem = ((size_t)128 * 65 + kFusePix * 129) * 4;
   const int kDynMax = 224 * 1024;  // 227 KB opt-in limit minus the kernels' small static shared memory
   CDFO_REQUIRE(row_smem <= (size_t)kDynMax && col_smem <= (size_t)kDynMax, CDFO_ERR_UNSUPPORTED,
-               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 730, H <= 384)", H, W);
+               "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 704, H <= 384)", H, W);
   static bool attr = false;
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
