@@ -9,10 +9,10 @@
 //   * attn @ (v * gate) followed by project_out is linear per pixel:  o1 = M1 warped,  o2 = M2 pred  with
 //     M = P . blockdiag(A) . diag(gate)  (64 x 64 per sample);  mode 1 additionally folds the second fusion_out
 //     (arch:3492):  out = ReLU(Wa (o1 + o2) + Wb x) = ReLU((Wa M1) warped + (Wa M2) pred + Wb x).
-// Three kernels, fp32 CUDA-core arithmetic (the contractions are 64-wide per pixel; the op is bound by HBM and the
-// shared-memory pipe, not by the tensor cores):
+// Three kernels; the per-pixel 64 x 128 / 64 x 64 linear maps run on the tensor cores (warp-level mma.sync m16n8k8 TF32,
+// fp32 accumulate), the statistics and the softmax in fp32:
 //   1. mdta_stats_kernel   gathers warped (flow_warp index arithmetic of csrc/priors.cu), computes fused = Wf [warped; pred]
-//                          per 128-pixel tile with a register-tiled shared-memory GEMM, and accumulates in registers,
+//                          per 128-pixel tile with a TF32 tensor-core GEMM from shared memory, and accumulates in registers,
 //                          across the tiles of a persistent CTA: sum warped, sum pred, sum x^2, sum fused^2 and the
 //                          per-head Gram x_c . fused_c'.  Writes warped (needed again in 3) and per-CTA partials.
 //   2. mdta_attn_kernel    per sample: fixed-order reduction of the partials (deterministic), gates, normalisation,
@@ -27,7 +27,8 @@ namespace cdfo {
 namespace mdta {
 
 constexpr int kTP = 128;       // pixels per tile
-constexpr int kLd = 132;       // row stride in floats of a [64][kTP] tile: 16-byte aligned rows, conflict-free float4 columns
+constexpr int kLd = 136;       // row stride in floats of a [64][kTP] tile: 16-byte aligned rows; 136 % 32 == 8 makes the
+                               // B-fragment loads of the tensor-core GEMM (4 k rows x 8 pixels per warp) conflict-free
 constexpr int kThreads = 256;
 constexpr int kMaxParts = 64;
 
@@ -41,20 +42,63 @@ struct StatsParams {
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// out[8][4] += A^T[k][cb*8 .. +7] * in[k][pg*4 .. +3] for k in [0, K)
-__device__ __forceinline__ void tile_gemm(float (&acc)[8][4], const float *__restrict__ aT, const float *__restrict__ in,
-                                          int K, int cb, int pg) {
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Per-pixel linear maps on the tensor cores (warp-level mma.sync m16n8k8 TF32, fp32 accumulate):
+//   acc[64 out x 16 px of this warp] += Wm[64 out][K] * in[K][128 px]
+// Wm: TF32 bit patterns, row stride ldw with ldw % 32 == 4 (A-fragment loads conflict-free); in: fp32 tile [K][kLd], rounded
+// to TF32 at load.  Warp w owns pixels 16w .. 16w+15 (two 8-pixel n-tiles) and all four 16-channel m-tiles:
+// acc[m][n][0..1] = (channel 16m + g, pixels 16w + 8n + 2t, +1), acc[m][n][2..3] = channel 16m + g + 8.
+__device__ __forceinline__ void tile_gemm_mma(float (&acc)[4][2][4], const float *__restrict__ Wm, int ldw, const float *__restrict__ in,
+                                              int K, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t *Wu = reinterpret_cast<const uint32_t *>(Wm);
 #pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 a0 = ld4(aT + k * 64 + cb * 8), a1 = ld4(aT + k * 64 + cb * 8 + 4);
-    const float4 v = ld4(in + k * kLd + pg * 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[4] = {v.x, v.y, v.z, v.w};
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    uint32_t bf[2][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int n = 0; n < 2; ++n) {
+      bf[n][0] = to_tf32(in[(k0 + t) * kLd + warp * 16 + n * 8 + g]);
+      bf[n][1] = to_tf32(in[(k0 + t + 4) * kLd + warp * 16 + n * 8 + g]);
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t *wr = Wu + (m * 16 + g) * ldw + k0 + t;
+      const uint32_t af[4] = {wr[0], wr[8 * ldw], wr[4], wr[8 * ldw + 4]};
+      mma_tf32(acc[m][0], af, bf[0][0], bf[0][1]);
+      mma_tf32(acc[m][1], af, bf[1][0], bf[1][1]);
+    }
   }
+}
+// accumulator fragments of this warp -> tile [64][kLd] in shared memory (optionally ReLU)
+__device__ __forceinline__ void stage_frags(const float (&acc)[4][2][4], float *__restrict__ dst, int warp, int lane, bool relu) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      float2 lo = make_float2(acc[m][n][0], acc[m][n][1]), hi = make_float2(acc[m][n][2], acc[m][n][3]);
+      if (relu) { lo.x = fmaxf(lo.x, 0.f); lo.y = fmaxf(lo.y, 0.f); hi.x = fmaxf(hi.x, 0.f); hi.y = fmaxf(hi.y, 0.f); }
+      *reinterpret_cast<float2 *>(dst + (m * 16 + g) * kLd + warp * 16 + n * 8 + 2 * t) = lo;
+      *reinterpret_cast<float2 *>(dst + (m * 16 + g + 8) * kLd + warp * 16 + n * 8 + 2 * t) = hi;
+    }
+}
+__device__ __forceinline__ void zero_frags(float (&acc)[4][2][4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsParams p) {
@@ -62,23 +106,22 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
   float *Wt = sm;                    // [64][kLd] warped, later fused
   float *Pt = Wt + 64 * kLd;         // [64][kLd] pred
   float *Xt = Pt + 64 * kLd;         // [64][kLd] x (query)
-  float *WfT = Xt + 64 * kLd;        // [128][64] fusion_out weight, transposed
+  float *Wm = Xt + 64 * kLd;         // [64][132] fusion_out weight as TF32 bits
   const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
   const int HW = p.H * p.W;
   const int ntiles = (HW + kTP - 1) / kTP;
   const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
-  for (int e = tid; e < 64 * 128; e += kThreads) WfT[(e & 127) * 64 + (e >> 7)] = p.wf[e];
+  for (int e = tid; e < 64 * 128; e += kThreads) Wm[(e >> 7) * 132 + (e & 127)] = __uint_as_float(to_tf32(p.wf[e]));
   const float *xs = p.x + (size_t)(b % p.x_batch) * 64 * HW;
   const float *ex = p.extra + (size_t)b * 64 * HW;
   const float *pr = p.pred + (size_t)b * 64 * HW;
   float *wo = p.warped + (size_t)b * 64 * HW;
   const int hc = p.hc, npairs = 64 * hc;
   float rs = 0.f, g[4] = {0.f, 0.f, 0.f, 0.f};
-  const int cb = tid >> 5, pg = tid & 31;
 
   for (int tile = t0; tile < t1; ++tile) {
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
-    __syncthreads();   // previous tile's readers are done (and WfT is complete on the first pass)
+    __syncthreads();   // previous tile's readers are done (and Wm is complete on the first pass)
     {  // ---- A: gather warped, load pred and x
       const int px = tid & 127, half = tid >> 7;
       const int pp = p0 + px;
@@ -139,20 +182,12 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
       }
       rs += s;
     }
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    tile_gemm(acc, WfT, Wt, 64, cb, pg);
-    tile_gemm(acc, WfT + 64 * 64, Pt, 64, cb, pg);
+    float acc[4][2][4];
+    zero_frags(acc);
+    tile_gemm_mma(acc, Wm, 132, Wt, 64, tid >> 5, tid & 31);
+    tile_gemm_mma(acc, Wm + 64, 132, Pt, 64, tid >> 5, tid & 31);
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      *reinterpret_cast<float4 *>(Wt + (cb * 8 + i) * kLd + pg * 4) = v;
-    }
+    stage_frags(acc, Wt, tid >> 5, tid & 31, p.relu != 0);
     __syncthreads();
     // ---- C: sum fused^2 and the per-head Gram
     if (tid >= 192) {
@@ -193,7 +228,7 @@ struct AttnParams {
   const float *temperature;         // [heads]
   const float *proj;                // project_out weight [64][64]
   const float *fold;                // mode 1: fusion_out weight [64][128] (Wa | Wb); mode 0: nullptr
-  float *mats;                      // [B][3][64][64] transposed: mats[b][m][k][o]
+  float *mats;                      // [B][3][64][64]: mats[b][m][o][k]
   int parts, hc, HW;
 };
 
@@ -251,12 +286,12 @@ __global__ void __launch_bounds__(256) mdta_attn_kernel(const AttnParams p) {
   float *mats = p.mats + (size_t)b * 3 * 4096;
   if (!p.fold) {
     for (int e = tid; e < 2 * 4096; e += 256) {
-      const int m = e >> 12, k = (e >> 6) & 63, o = e & 63;
-      mats[m * 4096 + k * 64 + o] = M[m][o * 65 + k];
+      const int m = e >> 12, o = (e >> 6) & 63, k = e & 63;
+      mats[m * 4096 + o * 64 + k] = M[m][o * 65 + k];
     }
   } else {
     for (int e = tid; e < 3 * 4096; e += 256) {
-      const int m = e >> 12, k = (e >> 6) & 63, o = e & 63;
+      const int m = e >> 12, o = (e >> 6) & 63, k = e & 63;
       float s;
       if (m == 2) {
         s = p.fold[o * 128 + 64 + k];                       // Wb
@@ -264,14 +299,14 @@ __global__ void __launch_bounds__(256) mdta_attn_kernel(const AttnParams p) {
         s = 0.f;
         for (int i = 0; i < 64; ++i) s = fmaf(p.fold[o * 128 + i], M[m][i * 65 + k], s);   // (Wa M_m)[o][k]
       }
-      mats[m * 4096 + k * 64 + o] = s;
+      mats[m * 4096 + o * 64 + k] = s;
     }
   }
 }
 
 struct ApplyParams {
   const float *warped, *pred, *x;
-  const float *mats;      // [B][3][64][64] transposed
+  const float *mats;      // [B][3][64][64] (out, in)
   void *out;              // mode 0: c8 bf16 [2B][8][HW][8]; mode 1: NCHW fp32 [B][64][HW]
   float *ca_partial;      // mode 1: [B][parts][64] channel sums of out
   int H, W, B, x_batch, mode;
@@ -285,13 +320,14 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) float sm[];
   float *Wt = sm, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
-  float *MT = Xt + 64 * kLd;         // [3][64][64]
+  float *Mm = Xt + 64 * kLd;         // [3][64][68] TF32 bits
   const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
   const int HW = p.H * p.W;
   const int ntiles = (HW + kTP - 1) / kTP;
   const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
   const int nm = p.mode == 1 ? 3 : 2;
-  for (int e = tid; e < nm * 4096; e += kThreads) MT[e] = p.mats[(size_t)b * 3 * 4096 + e];
+  for (int e = tid; e < nm * 4096; e += kThreads)
+    Mm[(e >> 12) * 64 * 68 + ((e >> 6) & 63) * 68 + (e & 63)] = __uint_as_float(to_tf32(p.mats[(size_t)b * 3 * 4096 + e]));
   const float *wp = p.warped + (size_t)b * 64 * HW, *pr = p.pred + (size_t)b * 64 * HW;
   const float *xs = p.x ? p.x + (size_t)(b % p.x_batch) * 64 * HW : nullptr;
   const int cb = tid >> 5, pg = tid & 31;
@@ -307,38 +343,47 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyPara
       if (p.mode == 1) Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
     }
     __syncthreads();
-    float a1[8][4], a2[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
-    tile_gemm(a1, MT, Wt, 64, cb, pg);
+    const int warp = tid >> 5, lane = tid & 31;
+    float a1[4][2][4];
+    zero_frags(a1);
+    tile_gemm_mma(a1, Mm, 68, Wt, 64, warp, lane);
     if (p.mode == 0) {
-      tile_gemm(a2, MT + 4096, Pt, 64, cb, pg);
+      float a2[4][2][4];
+      zero_frags(a2);
+      tile_gemm_mma(a2, Mm + 64 * 68, 68, Pt, 64, warp, lane);
+      __syncthreads();                       // every warp is done reading the input tiles
+      stage_frags(a1, Wt, warp, lane, false);
+      stage_frags(a2, Pt, warp, lane, false);
+      __syncthreads();
       uint4 *z = reinterpret_cast<uint4 *>(p.out);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int q = pg * 4 + j;
         if (q < npx) {
-          z[((size_t)b * 8 + cb) * HW + p0 + q] = make_uint4(bf2(a1[0][j], a1[1][j]), bf2(a1[2][j], a1[3][j]),
-                                                              bf2(a1[4][j], a1[5][j]), bf2(a1[6][j], a1[7][j]));
-          z[((size_t)(p.B + b) * 8 + cb) * HW + p0 + q] = make_uint4(bf2(a2[0][j], a2[1][j]), bf2(a2[2][j], a2[3][j]),
-                                                                      bf2(a2[4][j], a2[5][j]), bf2(a2[6][j], a2[7][j]));
+          const float *r1 = Wt + cb * 8 * kLd + q, *r2 = Pt + cb * 8 * kLd + q;
+          z[((size_t)b * 8 + cb) * HW + p0 + q] = make_uint4(bf2(r1[0], r1[kLd]), bf2(r1[2 * kLd], r1[3 * kLd]),
+                                                              bf2(r1[4 * kLd], r1[5 * kLd]), bf2(r1[6 * kLd], r1[7 * kLd]));
+          z[((size_t)(p.B + b) * 8 + cb) * HW + p0 + q] = make_uint4(bf2(r2[0], r2[kLd]), bf2(r2[2 * kLd], r2[3 * kLd]),
+                                                                      bf2(r2[4 * kLd], r2[5 * kLd]), bf2(r2[6 * kLd], r2[7 * kLd]));
         }
       }
     } else {
-      tile_gemm(a1, MT + 4096, Pt, 64, cb, pg);
-      tile_gemm(a1, MT + 2 * 4096, Xt, 64, cb, pg);
+      tile_gemm_mma(a1, Mm + 64 * 68, 68, Pt, 64, warp, lane);
+      tile_gemm_mma(a1, Mm + 2 * 64 * 68, 68, Xt, 64, warp, lane);
+      __syncthreads();
+      stage_frags(a1, Wt, warp, lane, true);
+      __syncthreads();
       float *o = reinterpret_cast<float *>(p.out) + (size_t)b * 64 * HW;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        const float4 v = *reinterpret_cast<const float4 *>(Wt + (cb * 8 + i) * kLd + pg * 4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = pg * 4 + j;
-          const float v = fmaxf(a1[i][j], 0.f);
           if (q < npx) {
-            o[(size_t)(cb * 8 + i) * HW + p0 + q] = v;
-            csum[i] += v;
+            o[(size_t)(cb * 8 + i) * HW + p0 + q] = vv[j];
+            csum[i] += vv[j];
           }
         }
       }
@@ -451,7 +496,7 @@ extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, co
   float *partial = ws;
   float *mats = partial + (size_t)B * parts * mdta::stats_len(hc);
   float *warped = mats + (size_t)B * 3 * 4096;
-  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 128 * 64) * 4, smem3 = (size_t)(3 * 64 * mdta::kLd + 3 * 4096) * 4;
+  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 64 * 132) * 4, smem3 = (size_t)(3 * 64 * mdta::kLd + 3 * 64 * 68) * 4;
   static bool attr = false;
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(mdta::mdta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
