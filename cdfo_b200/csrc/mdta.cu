@@ -12,7 +12,7 @@
 // Three kernels; the per-pixel 64 x 128 / 64 x 64 linear maps run on the tensor cores (warp-level mma.sync m16n8k8 TF32,
 // fp32 accumulate), the statistics and the softmax in fp32:
 //   1. mdta_stats_kernel   gathers warped (flow_warp index arithmetic of csrc/priors.cu), computes fused = Wf [warped; pred]
-//                          per 128-pixel tile with a TF32 tensor-core GEMM from shared memory, and accumulates in registers,
+//                          per 64-pixel tile with a TF32 tensor-core GEMM from shared memory, and accumulates in registers,
 //                          across the tiles of a persistent CTA: sum warped, sum pred, sum x^2, sum fused^2 and the
 //                          per-head Gram x_c . fused_c'.  Writes warped (needed again in 3) and per-CTA partials.
 //   2. mdta_attn_kernel    per sample: fixed-order reduction of the partials (deterministic), gates, normalisation,
@@ -26,8 +26,10 @@
 namespace cdfo {
 namespace mdta {
 
-constexpr int kTP = 128;       // pixels per tile
-constexpr int kLd = 136;       // row stride in floats of a [64][kTP] tile: 16-byte aligned rows; 136 % 32 == 8 makes the
+constexpr int kTP = 64;        // pixels per tile: small enough that two CTAs fit an SM, so one CTA's load phase (global latency)
+                               // overlaps the other's GEMM / statistics phases
+constexpr int kTPShift = 6;
+constexpr int kLd = 72;        // row stride in floats of a [64][kTP] tile: 16-byte aligned rows; 72 % 32 == 8 makes the
                                // B-fragment loads of the tensor-core GEMM (4 k rows x 8 pixels per warp) conflict-free
 constexpr int kThreads = 256;
 constexpr int kMaxParts = 64;
@@ -54,25 +56,25 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // Per-pixel linear maps on the tensor cores (warp-level mma.sync m16n8k8 TF32, fp32 accumulate):
-//   acc[64 out x 16 px of this warp] += Wm[64 out][K] * in[K][128 px]
+//   acc[32 out x 16 px of this warp] += Wm[64 out][K] * in[K][64 px]
 // Wm: TF32 bit patterns, row stride ldw with ldw % 32 == 4 (A-fragment loads conflict-free); in: fp32 tile [K][kLd], rounded
-// to TF32 at load.  Warp w owns pixels 16w .. 16w+15 (two 8-pixel n-tiles) and all four 16-channel m-tiles:
-// acc[m][n][0..1] = (channel 16m + g, pixels 16w + 8n + 2t, +1), acc[m][n][2..3] = channel 16m + g + 8.
-__device__ __forceinline__ void tile_gemm_mma(float (&acc)[4][2][4], const float *__restrict__ Wm, int ldw, const float *__restrict__ in,
+// to TF32 at load.  Warp w owns pixels 16 (w & 3) .. +15 (two 8-pixel n-tiles) and the two 16-channel m-tiles 2 (w >> 2), +1:
+// acc[m][n][0..1] = (channel 16 (2 (w >> 2) + m) + g, pixels 16 (w & 3) + 8n + 2t, +1), acc[m][n][2..3] = that channel + 8.
+__device__ __forceinline__ void tile_gemm_mma(float (&acc)[2][2][4], const float *__restrict__ Wm, int ldw, const float *__restrict__ in,
                                               int K, int warp, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2, t = lane & 3, px0 = (warp & 3) * 16, m0 = (warp >> 2) * 2;
   const uint32_t *Wu = reinterpret_cast<const uint32_t *>(Wm);
 #pragma unroll 4
   for (int k0 = 0; k0 < K; k0 += 8) {
     uint32_t bf[2][2];
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
-      bf[n][0] = to_tf32(in[(k0 + t) * kLd + warp * 16 + n * 8 + g]);
-      bf[n][1] = to_tf32(in[(k0 + t + 4) * kLd + warp * 16 + n * 8 + g]);
+      bf[n][0] = to_tf32(in[(k0 + t) * kLd + px0 + n * 8 + g]);
+      bf[n][1] = to_tf32(in[(k0 + t + 4) * kLd + px0 + n * 8 + g]);
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const uint32_t *wr = Wu + (m * 16 + g) * ldw + k0 + t;
+    for (int m = 0; m < 2; ++m) {
+      const uint32_t *wr = Wu + ((m0 + m) * 16 + g) * ldw + k0 + t;
       const uint32_t af[4] = {wr[0], wr[8 * ldw], wr[4], wr[8 * ldw + 4]};
       mma_tf32(acc[m][0], af, bf[0][0], bf[0][1]);
       mma_tf32(acc[m][1], af, bf[1][0], bf[1][1]);
@@ -80,28 +82,28 @@ __device__ __forceinline__ void tile_gemm_mma(float (&acc)[4][2][4], const float
   }
 }
 // accumulator fragments of this warp -> tile [64][kLd] in shared memory (optionally ReLU)
-__device__ __forceinline__ void stage_frags(const float (&acc)[4][2][4], float *__restrict__ dst, int warp, int lane, bool relu) {
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void stage_frags(const float (&acc)[2][2][4], float *__restrict__ dst, int warp, int lane, bool relu) {
+  const int g = lane >> 2, t = lane & 3, px0 = (warp & 3) * 16, m0 = (warp >> 2) * 2;
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
       float2 lo = make_float2(acc[m][n][0], acc[m][n][1]), hi = make_float2(acc[m][n][2], acc[m][n][3]);
       if (relu) { lo.x = fmaxf(lo.x, 0.f); lo.y = fmaxf(lo.y, 0.f); hi.x = fmaxf(hi.x, 0.f); hi.y = fmaxf(hi.y, 0.f); }
-      *reinterpret_cast<float2 *>(dst + (m * 16 + g) * kLd + warp * 16 + n * 8 + 2 * t) = lo;
-      *reinterpret_cast<float2 *>(dst + (m * 16 + g + 8) * kLd + warp * 16 + n * 8 + 2 * t) = hi;
+      *reinterpret_cast<float2 *>(dst + ((m0 + m) * 16 + g) * kLd + px0 + n * 8 + 2 * t) = lo;
+      *reinterpret_cast<float2 *>(dst + ((m0 + m) * 16 + g + 8) * kLd + px0 + n * 8 + 2 * t) = hi;
     }
 }
-__device__ __forceinline__ void zero_frags(float (&acc)[4][2][4]) {
+__device__ __forceinline__ void zero_frags(float (&acc)[2][2][4]) {
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsParams p) {
+__global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsParams p) {
   extern __shared__ __align__(16) float sm[];
   float *Wt = sm;                    // [64][kLd] warped, later fused
   float *Pt = Wt + 64 * kLd;         // [64][kLd] pred
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
     __syncthreads();   // previous tile's readers are done (and Wm is complete on the first pass)
     {  // ---- A: gather warped, load pred and x
-      const int px = tid & 127, half = tid >> 7;
+      const int px = tid & (kTP - 1), part = tid >> kTPShift;   // 4 parts x 16 channels
       const int pp = p0 + px;
       const bool valid = px < npx;
       int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
         o00 = cy0 * p.W + cx0; o01 = cy0 * p.W + cx1; o10 = cy1 * p.W + cx0; o11 = cy1 * p.W + cx1;
       }
 #pragma unroll 4
-      for (int c = half * 32; c < half * 32 + 32; ++c) {
+      for (int c = part * 16; c < part * 16 + 16; ++c) {
         float v = 0.f;
         if (valid) {
           const float *plane = ex + (size_t)c * HW;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
         Wt[c * kLd + px] = v;
       }
       for (int e = tid; e < 64 * kTP; e += kThreads) {
-        const int c = e >> 7, q = e & 127;
+        const int c = e >> kTPShift, q = e & (kTP - 1);
         const bool ok = q < npx;
         Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
         Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_stats_kernel(const StatsPara
       }
       rs += s;
     }
-    float acc[4][2][4];
+    float acc[2][2][4];
     zero_frags(acc);
     tile_gemm_mma(acc, Wm, 132, Wt, 64, tid >> 5, tid & 31);
     tile_gemm_mma(acc, Wm + 64, 132, Pt, 64, tid >> 5, tid & 31);
@@ -317,7 +319,7 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(kThreads, 2) mdta_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) float sm[];
   float *Wt = sm, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
   float *Mm = Xt + 64 * kLd;         // [3][64][68] TF32 bits
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyPara
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
     __syncthreads();
     for (int e = tid; e < 64 * kTP; e += kThreads) {
-      const int c = e >> 7, q = e & 127;
+      const int c = e >> kTPShift, q = e & (kTP - 1);
       const bool ok = q < npx;
       Wt[c * kLd + q] = ok ? __ldg(wp + (size_t)c * HW + p0 + q) : 0.f;
       Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
@@ -344,11 +346,11 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyPara
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    float a1[4][2][4];
+    float a1[2][2][4];
     zero_frags(a1);
     tile_gemm_mma(a1, Mm, 68, Wt, 64, warp, lane);
     if (p.mode == 0) {
-      float a2[4][2][4];
+      float a2[2][2][4];
       zero_frags(a2);
       tile_gemm_mma(a2, Mm + 64 * 68, 68, Pt, 64, warp, lane);
       __syncthreads();                       // every warp is done reading the input tiles
@@ -357,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyPara
       __syncthreads();
       uint4 *z = reinterpret_cast<uint4 *>(p.out);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = pg * 4 + j;
+      for (int j = 0; j < 2; ++j) {
+        const int q = pg * 2 + j;
         if (q < npx) {
           const float *r1 = Wt + cb * 8 * kLd + q, *r2 = Pt + cb * 8 * kLd + q;
           z[((size_t)b * 8 + cb) * HW + p0 + q] = make_uint4(bf2(r1[0], r1[kLd]), bf2(r1[2 * kLd], r1[3 * kLd]),
@@ -376,11 +378,11 @@ __global__ void __launch_bounds__(kThreads, 1) mdta_apply_kernel(const ApplyPara
       float *o = reinterpret_cast<float *>(p.out) + (size_t)b * 64 * HW;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 v = *reinterpret_cast<const float4 *>(Wt + (cb * 8 + i) * kLd + pg * 4);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const float2 v = *reinterpret_cast<const float2 *>(Wt + (cb * 8 + i) * kLd + pg * 2);
+        const float vv[2] = {v.x, v.y};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int q = pg * 4 + j;
+        for (int j = 0; j < 2; ++j) {
+          const int q = pg * 2 + j;
           if (q < npx) {
             o[(size_t)(cb * 8 + i) * HW + p0 + q] = vv[j];
             csum[i] += vv[j];
