@@ -49,6 +49,10 @@ __device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
   return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));                 // ((g+1)/2)*(s-1)
 }
 
+// csrc/pointwise.cu: tensor-core 1x1 convolution (see cdfo_pointwise_conv_fwd in include/cdfo_b200.h)
+int pointwise_conv(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1, const float *resid2,
+                   float *out, int B, int K, int Co, int HW, int act, int mode, cudaStream_t s);
+
 }  // namespace cdfo
 
 #define CDFO_REQUIRE(cond, code, ...)                 \

@@ -13,7 +13,7 @@
 //   lra_row_kernel    per (b, h): v -> conv1x9 over channels -> softmax(W) -> vrow, stored column-major for the next pass
 //   lra_col_kernel    per (b, w): Q from the compact mask info (9-tap along H), softmax(H) . vrow -> long_out (NHWC)
 //   lra_win_kernel    per 8x8 window: q with the masked channel zeroed, softmax(64) . v -> loc_out (NHWC)
-//   lra_fuse_kernel   1x1 conv(128 -> 64) over [long_out, loc_out] + bias + x -> NCHW fp32
+//   fuse              1x1 conv(128 -> 64) over [long_out, loc_out] + bias + x -> NCHW fp32 (csrc/pointwise.cu, tensor cores)
 // All arithmetic fp32 (the 0.5 threshold makes the mask discontinuous: keep it and the softmax exponents exact).
 #include "cdfo_common.cuh"
 
@@ -523,52 +523,6 @@ __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__res
   });
 }
 
-// ------------------------------------------------------------------------------------------------ fuse
-// out[b][co][p] = bias[co] + sum_c Wf[co][c] long[p][c] + sum_c Wf[co][64+c] loc[p][c] + x[b][co][p]   (arch:2246-2249)
-constexpr int kFuseThreads = 256, kFusePix = 64;
-__global__ void __launch_bounds__(kFuseThreads) lra_fuse_kernel(const float *__restrict__ long_out, const float *__restrict__ loc_out,
-                                                               const float *__restrict__ wf, const float *__restrict__ bf,
-                                                               const float *__restrict__ x, float *__restrict__ out, int HW) {
-  extern __shared__ float sm[];
-  float *ws = sm;                    // [128][65]: ws[k][co] = Wf[co][k]
-  float *in = ws + 128 * 65;         // [kFusePix][129]
-  const int b = blockIdx.y, p0 = blockIdx.x * kFusePix;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 128; e += kFuseThreads) {
-    const int co = e >> 7, k = e & 127;
-    ws[k * 65 + co] = wf[e];
-  }
-  for (int e = tid; e < kFusePix * 64; e += kFuseThreads) {
-    const int pp = e >> 6, c = e & 63;
-    const int p = p0 + pp;
-    float a = 0.f, l = 0.f;
-    if (p < HW) {
-      a = long_out[((size_t)b * HW + p) * 64 + c];
-      l = loc_out[((size_t)b * HW + p) * 64 + c];
-    }
-    in[pp * 129 + c] = a;
-    in[pp * 129 + 64 + c] = l;
-  }
-  __syncthreads();
-  const int pp = tid & 63, cq = tid >> 6;   // thread: pixel pp, output channels cq*16 .. cq*16+15
-  float acc[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = bf[cq * 16 + i];
-  for (int k = 0; k < 128; ++k) {
-    const float a = in[pp * 129 + k];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = fmaf(ws[k * 65 + cq * 16 + i], a, acc[i]);
-  }
-  const int p = p0 + pp;
-  if (p < HW) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const size_t o = ((size_t)b * 64 + cq * 16 + i) * HW + p;
-      out[o] = acc[i] + x[o];
-    }
-  }
-}
-
 }  // namespace cdfo
 
 using namespace cdfo;
@@ -579,9 +533,9 @@ extern "C" size_t cdfo_lra_workspace_bytes(int B, int H, int W) {
   return P * (1 + 4) + 3 * P * 64 * 4 + 256;   // midx + qsel + vrow_t + long_out + loc_out
 }
 
-extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *tables, float beta,
-                            float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B, int H,
-                            int W, void *stream) {
+extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                            float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B,
+                            int H, int W, void *stream) {
   CDFO_REQUIRE(qv && u && vmax && x && tables && fuse_w && fuse_b && out && workspace, CDFO_ERR_NULL, "cdfo_lra_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, CDFO_ERR_SHAPE,
                "cdfo_lra_fwd: H and W must be multiples of the window size 8 (got %d x %d)", H, W);
@@ -604,7 +558,6 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   const size_t col_v = (size_t)Hk * kLd > (size_t)(H + 8) * 64 ? (size_t)Hk * kLd : (size_t)(H + 8) * 64;
   const size_t col_smem = ((size_t)Hk * kLd + col_v) * 4;
   const size_t win_smem = (size_t)3 * 64 * kLd * 4;
-  const size_t fuse_smem = ((size_t)128 * 65 + kFusePix * 129) * 4;
   const int kDynMax = 224 * 1024;  // 227 KB opt-in limit minus the kernels' small static shared memory
   CDFO_REQUIRE(row_smem <= (size_t)kDynMax && col_smem <= (size_t)kDynMax, CDFO_ERR_UNSUPPORTED,
                "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 704, H <= 384)", H, W);
@@ -612,8 +565,7 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e2 = cudaFuncSetAttribute(lra_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
-    cudaError_t e3 = cudaFuncSetAttribute(lra_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem);
-    if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(lra_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem);
+    cudaError_t e3 = cudaFuncSetAttribute(lra_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
       return fail(CDFO_ERR_CUDA, "cdfo_lra_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     attr = true;
@@ -621,6 +573,7 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   lra_row_kernel<<<dim3(H, B), kRowThreads, row_smem, s>>>(qv, midx, qsel, vrow_t, t, H, W);
   lra_col_kernel<<<dim3(W, B), kColThreads, col_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
   lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, win_smem, s>>>(qv, midx, loc_out, H, W);
-  lra_fuse_kernel<<<dim3(ceil_div(HW, kFusePix), B), kFuseThreads, fuse_smem, s>>>(long_out, loc_out, fuse_w, fuse_b, x, out, HW);
-  return check_launch("cdfo_lra_fwd");
+  if (int rc = check_launch("cdfo_lra_fwd")) return rc;
+  // fuse: 1x1 conv(128 -> 64) over cat[long, local] (pixel-major) + bias + x (+ x2): tensor-core pointwise kernel
+  return pointwise_conv(long_out, loc_out, fuse_w, fuse_b, x, x2, out, B, 128, 64, HW, 0, 1, s);
 }

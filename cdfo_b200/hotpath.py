@@ -163,24 +163,37 @@ def _lra_tap_tables(mod):
     return tab
 
 
+def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
+    """cdfo_pointwise_conv_fwd: tensor-core 1x1 convolution on NCHW fp32 (mode 0: x = in1 + in2; mode 1: pixel-major cat)."""
+    B, K, H, W = in1.shape
+    Co = weight.size(0)
+    out = torch.empty((B, Co, H, W), dtype=torch.float32, device=in1.device)
+    _lib.call("cdfo_pointwise_conv_fwd", _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(_f32(weight).reshape(Co, -1)), _lib.ptr(None if bias is None else _f32(bias)),
+              _lib.ptr(resid1), _lib.ptr(resid2), _lib.ptr(out), B, K, Co, H, W, int(act), int(mode), _lib.stream_ptr(in1.device))
+    return out
+
+
 @torch.no_grad()
-def long_range_attention(mod, res, x, u):
-    """LLongRangAttention.forward, arch:2179-2249, u = uniform noise of gumbel_softmax (arch:2169).
-    Mask logits (a global pooling of two small convolutions of the residual prior) and the 1x1 input_conv are
-    ATen/cuDNN calls; the mask, the row / column / window attentions and the fuse convolution are csrc/lra.cu."""
+def long_range_attention(mod, res, x, u, x2=None):
+    """LLongRangAttention.forward, arch:2179-2249, on the input x (+ x2: the model's `fea + rms_prior`, arch:4449, is formed
+    inside the kernels and never written); u = uniform noise of gumbel_softmax (arch:2169).
+    The 1x1 convolutions (conv_du_re.0, input_conv, fuse) are tensor-core pointwise kernels, the mask / row / column /
+    window attentions csrc/lra.cu; only the stride-2 3x3 of the mask logits and its global mean are cuDNN / ATen calls."""
     B, C, H, W = x.shape
-    v = F.relu(_c(mod.conv_du_re._modules["0"], res))
+    res, x = _f32(res), _f32(x)
+    x2 = None if x2 is None else _f32(x2)
+    du0 = mod.conv_du_re._modules["0"]
+    v = _pointwise(res, None, du0.weight, du0.bias, act=1)
     v = F.relu(_c(mod.conv_du_re._modules["2"], v, stride=2, padding=2))
     v = v.mean(dim=(2, 3), keepdim=True)
     vmax = F.relu(_c(mod.conv_du_re2._modules["0"], v)).reshape(B, C).contiguous()   # bilinear up of a 1x1 map = broadcast
-    x = x.contiguous()
-    qv = _c(mod.input_conv, x).contiguous()
+    qv = _pointwise(x, x2, mod.input_conv.weight, mod.input_conv.bias, act=0)
     out = torch.empty_like(x)
     nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(_lra_tap_tables(mod)),
+    _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(x2), _lib.ptr(_lra_tap_tables(mod)),
               ctypes.c_float(float(mod.directW1_conv.bias)), ctypes.c_float(float(mod.directH1_conv.bias)),
-              _lib.ptr(mod.fuse.weight.detach().reshape(64, 128).contiguous()), _lib.ptr(mod.fuse.bias.detach().contiguous()),
+              _lib.ptr(_f32(mod.fuse.weight).reshape(64, 128)), _lib.ptr(_f32(mod.fuse.bias)),
               _lib.ptr(out), _lib.ptr(ws), B, H, W, _lib.stream_ptr(x.device))
     return out
 
@@ -198,7 +211,7 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     H, W = center.shape[2:]
     ufs_prior = _c(model.conv_expand_ufs, ufs_nb, padding=1)
     rms_prior = _c(model.conv_expand_rms, rms_nb, padding=1)
-    x_n = long_range_attention(model.RDAB, rms_prior, fea_nb + rms_prior, u_nb)
+    x_n = long_range_attention(model.RDAB, rms_prior, fea_nb, u_nb, x2=rms_prior)
     fr = model.conv_expand_fea_r
     fea_i = conv.conv3x3(conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
     stack = torch.empty((B, 56, H, W, 8), dtype=torch.bfloat16, device=center.device)

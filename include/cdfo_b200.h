@@ -192,13 +192,20 @@ int cdfo_resample_c8(const void *a, const void *b, const void *base, void *y, in
  *   qv     [B,128,H,W] fp32 = input_conv(x) (q = first 64 channels, v = last 64)          arch:2206,2211
  *   u      [B,64,H,W]  fp32 uniform noise of gumbel_softmax (torch.rand_like, arch:2169)
  *   vmax   [B,64]      fp32 = conv_du_re2(avg_pool(conv_du_re(res)))                        arch:2183-2185
- *   x      [B,64,H,W]  fp32 residual input;  out [B,64,H,W] fp32 = fuse(cat[long, loc]) + x  arch:2246-2249
+ *   x, x2  [B,64,H,W]  fp32 residual input = x + x2 (x2 may be NULL; the model passes the feature and the residual prior
+ *          separately, arch:4449);  out [B,64,H,W] fp32 = fuse(cat[long, loc]) + x + x2  arch:2246-2249
  *   tables [9 + 9 + 64 + 4096] fp32: directW1_conv taps, directH1_conv taps, K1, R (see csrc/lra.cu); beta / bh their biases
  *   fuse_w [64,128] fp32, fuse_b [64];  workspace: cdfo_lra_workspace_bytes(B, H, W) bytes;  H, W multiples of 8.
  * No score tensor is materialised (the reference writes ~3.1 kB of fp32 scores per pixel and call). */
-int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *tables, float beta,
-                 float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B, int H, int W,
+int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                 float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B, int H, int W,
                  void *stream);
+/* ---- 1x1 convolutions of A8 on the tensor cores (csrc/pointwise.cu), NCHW fp32 in / out ----
+ *   y[b,co,p] = act(bias[co] + sum_k w[co,k] x[b,k,p]) + resid1[b,co,p] + resid2[b,co,p]        (act 0 none / 1 ReLU)
+ *   mode 0: x = in1 + in2 (in2 may be NULL), [B,K,H,W]; supported K -> Co: 64 -> 64 (conv_du_re.0, arch:2183), 64 -> 128 (input_conv
+ *           on fea + residual prior, arch:2206/:4449);  mode 1: x = cat(in1, in2), both pixel-major [B,H*W,64], 128 -> 64 (fuse, arch:2246). */
+int cdfo_pointwise_conv_fwd(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1,
+                            const float *resid2, float *out, int B, int K, int Co, int H, int W, int act, int mode, void *stream);
 size_t cdfo_lra_workspace_bytes(int B, int H, int W);
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
