@@ -151,20 +151,36 @@ __global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__
   for (int i = 0; i < 9; ++i) kw[i] = t.kw[i];
   for (int e = tid; e < 4096; e += kRowThreads) Rs[e] = t.r[e];
 
-  // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219)
+  // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219): the raw row is read from
+  // global once (coalesced along w) into vr[w][c]; then one thread per pixel slides the 9 taps over its 64 channels in place
   const float *vbase = qv + ((size_t)b * 128 + 64) * HW + (size_t)h * W;
   for (int e = tid; e < 64 * Wk; e += kRowThreads) {
     const int c = e / Wk, w = e - c * Wk;
-    float acc = 0.f;
-    if (w < W) {
-      acc = t.beta;
+    vr[w * kLd + c] = w < W ? __ldg(vbase + (size_t)c * HW + w) : 0.f;
+  }
+  __syncthreads();
+  for (int w = tid; w < W; w += kRowThreads) {
+    float *row = vr + w * kLd;
+    float win[72];                         // channels -4 .. 67 of this pixel (zero outside 0 .. 63)
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int cc = c + i - 4;
-        if (cc >= 0 && cc < 64) acc = fmaf(kw[i], __ldg(vbase + (size_t)cc * HW + w), acc);
-      }
+    for (int i = 0; i < 4; ++i) { win[i] = 0.f; win[68 + i] = 0.f; }
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 v = *reinterpret_cast<const float4 *>(row + 4 * c4);
+      win[4 + 4 * c4] = v.x; win[5 + 4 * c4] = v.y; win[6 + 4 * c4] = v.z; win[7 + 4 * c4] = v.w;
     }
-    vr[w * kLd + c] = acc;
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float acc = t.beta;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc = fmaf(kw[i], win[4 * c4 + j + i], acc);
+        o[j] = acc;
+      }
+      *reinterpret_cast<float4 *>(row + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
   if (tid == 0) mcount = 0;
   __syncthreads();
