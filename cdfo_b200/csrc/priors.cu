@@ -111,9 +111,47 @@ __global__ void unpack_c8_kernel(const uint4 *__restrict__ in, float *__restrict
   }
 }
 
+// ---------------------------------------------------------------- A9: prior embedding convs
+// conv_expand_ufs / conv_expand_rms (arch/SIDECVSR_our.py:4383-4384, :4446-4447): nn.Conv2d(1, Co, 3, 1, 1) on a one-channel
+// prior map.  One thread per pixel holds its 3x3 neighbourhood in registers and writes Co channels (coalesced along the
+// pixels of each channel plane): 4 * Co bytes written per pixel, HBM-bound.
+__global__ void __launch_bounds__(128) prior_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                         const float *__restrict__ bias, float *__restrict__ y, int Co, int H, int W) {
+  extern __shared__ float ws[];   // [Co][9] weights + [Co] bias
+  for (int e = threadIdx.x; e < Co * 9; e += blockDim.x) ws[e] = w[e];
+  for (int e = threadIdx.x; e < Co; e += blockDim.x) ws[Co * 9 + e] = bias ? bias[e] : 0.f;
+  __syncthreads();
+  const int HW = H * W, p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (p >= HW) return;
+  const int h = p / W, wq = p - h * W;
+  const float *xp = x + (size_t)b * HW;
+  float v[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int hh = h + i - 1, ww = wq + j - 1;
+      v[i * 3 + j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + hh * W + ww) : 0.f;
+    }
+  float *yp = y + (size_t)b * Co * HW + p;
+  for (int c = 0; c < Co; ++c) {
+    float acc = ws[Co * 9 + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc = fmaf(ws[c * 9 + k], v[k], acc);   // same tap order as a direct fp32 convolution
+    __stcs(yp + (size_t)c * HW, acc);
+  }
+}
+
 }  // namespace cdfo
 
 using namespace cdfo;
+
+extern "C" int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, void *stream) {
+  CDFO_REQUIRE(x && w && y, CDFO_ERR_NULL, "cdfo_prior_conv_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && Co > 0 && Co <= 1024 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_prior_conv_fwd: bad shape");
+  prior_conv_kernel<<<dim3(ceil_div(H * W, 128), B), 128, (size_t)Co * 10 * 4, (cudaStream_t)stream>>>(x, w, bias, y, Co, H, W);
+  return check_launch("cdfo_prior_conv_fwd");
+}
 
 extern "C" int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H, int W, void *stream) {
   CDFO_REQUIRE(mv && flows, CDFO_ERR_NULL, "cdfo_mv2mvs: NULL pointer");

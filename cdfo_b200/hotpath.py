@@ -199,6 +199,20 @@ def long_range_attention(mod, res, x, u, x2=None):
 
 
 # ------------------------------------------------------------------------------------------ model-level stages
+@torch.no_grad()
+def prior_conv(conv_mod, x):
+    """conv_expand_ufs / conv_expand_rms (arch:4446-4447): Conv2d(1, 64, 3, 1, 1) on a one-channel prior map, fp32."""
+    B, C, H, W = x.shape
+    if C != 1:
+        raise _lib.CdfoError("prior_conv: one-channel input expected")
+    x = _f32(x)
+    Co = conv_mod.weight.size(0)
+    y = torch.empty((B, Co, H, W), dtype=torch.float32, device=x.device)
+    _lib.call("cdfo_prior_conv_fwd", _lib.ptr(x), _lib.ptr(_f32(conv_mod.weight)), _lib.ptr(_f32(conv_mod.bias)), _lib.ptr(y), B, Co, H, W,
+              _lib.stream_ptr(x.device))
+    return y
+
+
 _SLOT = (0, 1, 2, 4, 5, 6)   # frame slot of neighbour n in the stacked tensor (arch:4463: frames in temporal order)
 
 
@@ -209,8 +223,8 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     Returns the fused feature as c8 bf16 [B, 8, H, W, 8].  The 448-channel stack is written once, in bf16, directly by the
     DCN epilogue (O2) and read by the tcgen05 convolution (the 1x1 is passed as a centre-tap 3x3)."""
     H, W = center.shape[2:]
-    ufs_prior = _c(model.conv_expand_ufs, ufs_nb, padding=1)
-    rms_prior = _c(model.conv_expand_rms, rms_nb, padding=1)
+    ufs_prior = prior_conv(model.conv_expand_ufs, ufs_nb)
+    rms_prior = prior_conv(model.conv_expand_rms, rms_nb)
     x_n = long_range_attention(model.RDAB, rms_prior, fea_nb, u_nb, x2=rms_prior)
     fr = model.conv_expand_fea_r
     fea_i = conv.conv3x3(conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)

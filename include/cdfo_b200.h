@@ -82,6 +82,10 @@ int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H, int W, voi
 /* ---- A2: in-place end-of-sequence fix-up on flows [B,7,2,H,W]; frame index i, max_idx as the caller passes. */
 int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void *stream);
 
+/* ---- A9: prior embedding convs conv_expand_ufs / conv_expand_rms = nn.Conv2d(1, Co, 3, 1, 1) (arch/SIDECVSR_our.py:4383-4384,
+ * :4446-4447).  x [B,1,H,W] fp32, w [Co,1,3,3], bias [Co] or NULL -> y [B,Co,H,W] fp32. */
+int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, void *stream);
+
 /* ---- layout adapters: NCHW fp32 <-> "c8" = [B, C/8, H, W, 8] bf16 (C % 8 == 0). ---- */
 int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H, int W, void *stream);
 int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, void *stream);

@@ -82,3 +82,17 @@ def test_pack_unpack_c8_roundtrip(cuda_dev):
     back = torch.empty_like(x)
     L.check(L.lib().cdfo_unpack_c8(L.ptr(c8), L.ptr(back), 2, 64, 9, 13, L.stream_ptr(cuda_dev)))
     assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+def test_prior_conv_vs_torch(cuda_dev):
+    """conv_expand_ufs / conv_expand_rms (arch/SIDECVSR_our.py:4446-4447): Conv2d(1, 64, 3, 1, 1), fp32, ragged size."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from cdfo_b200 import hotpath
+    g = torch.Generator().manual_seed(2)
+    conv = nn.Conv2d(1, 64, 3, 1, 1)
+    x = torch.randn(3, 1, 19, 37, generator=g)
+    with torch.no_grad():
+        ref = F.conv2d(x, conv.weight, conv.bias, padding=1)
+    got = hotpath.prior_conv(conv.to(cuda_dev), x.to(cuda_dev)).cpu()
+    assert (got - ref).abs().max().item() <= 1e-5

@@ -49,7 +49,7 @@ def main():
     res = {}
     with torch.no_grad():
         res["features_1frame"], _ = t(lambda: m._features(x1, x1))
-        res["prior_convs"], (up, rp) = t(lambda: (hotpath._c(m.conv_expand_ufs, ufs_nb, padding=1), hotpath._c(m.conv_expand_rms, rms_nb, padding=1)))
+        res["prior_convs"], (up, rp) = t(lambda: (hotpath.prior_conv(m.conv_expand_ufs, ufs_nb), hotpath.prior_conv(m.conv_expand_rms, rms_nb)))
         res["RDAB"], x_n = t(lambda: hotpath.long_range_attention(m.RDAB, rp, fea_nb + rp, u))
         fr = m.conv_expand_fea_r
         res["conv_expand_fea_r"], fea_i = t(lambda: cdfo_b200.conv.conv3x3(cdfo_b200.conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, 0, out_nchw=True))
