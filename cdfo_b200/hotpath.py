@@ -313,3 +313,26 @@ def recon_trunk(trunk, x8):
             r = cross_scale_block(blk, r)
         y = conv.conv3x3(r, grp.conv.weight, grp.conv.bias, conv.ACT_NONE, resid8=y)
     return y + x8
+
+
+# ------------------------------------------------------------------------------------------ feature extraction pieces (8f rank 2)
+@torch.no_grad()
+def layernorm_c(x, gamma, beta, eps=1e-5):
+    """LayerNorm over the channels of each pixel (WithBias, arch:1169-1198) on NCHW fp32 / bf16, fp32 arithmetic."""
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.call("cdfo_layernorm_c_fwd", _lib.ptr(x), _lib.ptr(_f32(gamma)), _lib.ptr(_f32(beta)), _lib.ptr(y), B, C, H, W,
+              ctypes.c_float(eps), _lib.dtype_code(x), _lib.stream_ptr(x.device))
+    return y
+
+
+@torch.no_grad()
+def dwconv3x3(x, weight):
+    """Depthwise 3x3 / stride 1 / padding 1 without bias (qkv_dwconv, arch:1545-1576) on NCHW fp32 / bf16."""
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.call("cdfo_dwconv3x3_fwd", _lib.ptr(x), _lib.ptr(_f32(weight).reshape(C, 9)), _lib.ptr(y), B, C, H, W, _lib.dtype_code(x),
+              _lib.stream_ptr(x.device))
+    return y

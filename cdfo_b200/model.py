@@ -54,6 +54,8 @@ class _ChannelLayerNorm(_Holder):
         self.body.bias = nn.Parameter(torch.zeros(dim))
 
     def forward(self, x):
+        if x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.size(1) == 64:
+            return hotpath.layernorm_c(x, self.body.weight, self.body.bias)
         mu = x.mean(1, keepdim=True)
         var = x.var(1, keepdim=True, unbiased=False)
         return (x - mu) * torch.rsqrt(var + 1e-5) * self.body.weight.view(1, -1, 1, 1) + self.body.bias.view(1, -1, 1, 1)
@@ -72,7 +74,12 @@ class _SelfMDTA(_Holder):
 
     def forward(self, x):
         b, c, h, w = x.shape
-        q, k, v = self.qkv_dwconv(self.qkv(x)).chunk(3, dim=1)
+        qkv = self.qkv(x)
+        if qkv.is_cuda and qkv.dtype in (torch.float32, torch.bfloat16):
+            qkv = hotpath.dwconv3x3(qkv, self.qkv_dwconv.weight)
+        else:
+            qkv = self.qkv_dwconv(qkv)
+        q, k, v = qkv.chunk(3, dim=1)
         sh = (b, self.num_heads, c // self.num_heads, h * w)
         q = F.normalize(q.reshape(sh).float(), dim=-1)
         k = F.normalize(k.reshape(sh).float(), dim=-1)

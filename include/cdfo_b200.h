@@ -211,6 +211,12 @@ int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float
 int cdfo_pointwise_conv_fwd(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1,
                             const float *resid2, float *out, int B, int K, int Co, int H, int W, int act, int mode, void *stream);
 size_t cdfo_lra_workspace_bytes(int B, int H, int W);
+/* ---- pieces of the feature extraction, NCHW, dtype CDFO_F32 or CDFO_BF16 storage, fp32 arithmetic ----
+ * LayerNorm over the 64 channels of each pixel, WithBias (arch/SIDECVSR_our.py:1169-1198): y = (x - mu) rsqrt(var + eps) gamma + beta. */
+int cdfo_layernorm_c_fwd(const void *x, const float *gamma, const float *beta, void *y, int B, int C, int H, int W, float eps,
+                         int dtype, void *stream);
+/* depthwise 3x3, stride 1, padding 1, no bias (qkv_dwconv, arch:1545-1576): w [C,1,3,3] fp32. */
+int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B, int C, int H, int W, int dtype, void *stream);
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
 

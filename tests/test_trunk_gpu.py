@@ -45,3 +45,23 @@ def test_trunk_vs_oracle(cuda_dev):
     err = (got - ref).abs().max().item()
     print("trunk max err %.3g (max|ref| %.3g)" % (err, ref.abs().max().item()))
     assert err <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_and_dwconv_vs_torch(cuda_dev, dtype):
+    """Channel LayerNorm (arch:1169-1198) and the depthwise 3x3 of the MDTA attention (arch:1545-1576)."""
+    from cdfo_b200 import hotpath
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 64, 19, 37, generator=g).to(dtype)
+    gamma, beta = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    xf = x.float()
+    mu, var = xf.mean(1, keepdim=True), xf.var(1, keepdim=True, unbiased=False)
+    ref = (xf - mu) * torch.rsqrt(var + 1e-5) * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    got = hotpath.layernorm_c(x.to(cuda_dev), gamma.to(cuda_dev), beta.to(cuda_dev)).float().cpu()
+    tol = 1e-5 if dtype == torch.float32 else 2 ** -7
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
+    x3 = torch.randn(2, 192, 19, 37, generator=g).to(dtype)
+    w = torch.randn(192, 1, 3, 3, generator=g)
+    ref = F.conv2d(x3.float(), w, None, 1, 1, 1, 192)
+    got = hotpath.dwconv3x3(x3.to(cuda_dev), w.to(cuda_dev)).float().cpu()
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
