@@ -59,6 +59,48 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x,
   stf(y + ((size_t)b * C + c) * HW + p, acc);
 }
 
+// Vectorised bf16 variant (W % 8 == 0): one thread = 8 consecutive pixels of a row (one 16-byte load per input row + the two
+// horizontal neighbours), 9x fewer load instructions than the scalar kernel (which is bound by LSU issue, not by HBM).
+__global__ void __launch_bounds__(256) dwconv3x3_bf16x8_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ w,
+                                                               __nv_bfloat16 *__restrict__ y, int C, int H, int W) {
+  const int W8 = W >> 3, n = H * W8;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+  if (q >= n) return;
+  const int h = q / W8, w0 = (q - h * W8) * 8;
+  const __nv_bfloat16 *xp = x + ((size_t)b * C + c) * H * W;
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int hh = h + i - 1;
+    if (hh < 0 || hh >= H) continue;
+    const __nv_bfloat16 *row = xp + (size_t)hh * W + w0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row));
+    float r[10];
+    r[0] = w0 > 0 ? ldf(row - 1) : 0.f;
+    r[9] = w0 + 8 < W ? ldf(row + 8) : 0.f;
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[1 + 2 * j] = __uint_as_float(u[j] << 16);
+      r[2 + 2 * j] = __uint_as_float(u[j] & 0xffff0000u);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(k[i * 3 + 2], r[j + 2], fmaf(k[i * 3 + 1], r[j + 1], fmaf(k[i * 3], r[j], acc[j])));
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    o[j] = *reinterpret_cast<uint32_t *>(&t);
+  }
+  *reinterpret_cast<uint4 *>(y + ((size_t)b * C + c) * H * W + (size_t)h * W + w0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace feat
 }  // namespace cdfo
 
@@ -85,6 +127,8 @@ extern "C" int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B,
   dim3 grid(ceil_div(H * W, 256), C, B);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CDFO_F32) feat::dwconv3x3_kernel<float><<<grid, 256, 0, s>>>((const float *)x, w, (float *)y, C, H, W);
+  else if (dtype == CDFO_BF16 && W % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0)
+    feat::dwconv3x3_bf16x8_kernel<<<dim3(ceil_div(H * (W / 8), 256), C, B), 256, 0, s>>>((const __nv_bfloat16 *)x, w, (__nv_bfloat16 *)y, C, H, W);
   else if (dtype == CDFO_BF16)
     feat::dwconv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)x, w, (__nv_bfloat16 *)y, C, H, W);
   else return fail(CDFO_ERR_UNSUPPORTED, "cdfo_dwconv3x3_fwd: dtype must be fp32 or bf16");

@@ -65,3 +65,8 @@ def test_layernorm_and_dwconv_vs_torch(cuda_dev, dtype):
     ref = F.conv2d(x3.float(), w, None, 1, 1, 1, 192)
     got = hotpath.dwconv3x3(x3.to(cuda_dev), w.to(cuda_dev)).float().cpu()
     assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
+    x4 = torch.randn(1, 24, 11, 40, generator=g).to(dtype)            # W % 8 == 0: vectorised bf16 path
+    w4 = torch.randn(24, 1, 3, 3, generator=g)
+    ref = F.conv2d(x4.float(), w4, None, 1, 1, 1, 24)
+    got = hotpath.dwconv3x3(x4.to(cuda_dev), w4.to(cuda_dev)).float().cpu()
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
