@@ -13,7 +13,8 @@
 //     padding supplied by TMA out-of-bounds fill.  The A operand of tap (i, j) is the SAME shared memory at a
 //     byte offset of (i*10 + j)*16: no im2col, no data movement between taps (SBO = 160 B, LBO = 2880 B).
 //   * a CTA is persistent, owns one N tile (NT output channels) whose weights stay resident in shared memory,
-//     and walks 16x8-pixel M tiles; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+//     and walks 16x8-pixel M tiles; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (two per TMEM lane
+//     quarter, alternating column chunks)
 //     (tcgen05.ld -> +bias -> activation -> +residual -> bf16 c8 or fp32 NCHW); TMEM accumulator double buffered.
 #include <cuda.h>
 
@@ -27,7 +28,8 @@ constexpr int kCvHaloH = kCvTileH + 2, kCvHaloW = kCvTileW + 2;
 constexpr int kCvPlane = kCvHaloH * kCvHaloW * 16;         // 2880 B: one 8-channel chunk of the halo
 constexpr int kCvStageBytes = 8 * kCvPlane;                // 23040 B: 64 channels
 constexpr int kCvSbo = kCvHaloW * 16;                      // 160 B between 8-pixel rows of the tile
-constexpr int kCvThreads = 192;
+constexpr int kCvThreads = 320;                            // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kCvEpiThreads = 256;
 
 struct Conv3x3Params {
   const uint8_t *wpk;   // [n_tiles][9 taps][Cin/8][NT][8] bf16
@@ -102,7 +104,7 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(BAR(8 + a), 1);
-      ptx::mbar_init(BAR(10 + a), 128);
+      ptx::mbar_init(BAR(10 + a), kCvEpiThreads);
     }
     ptx::mbar_init(BAR(12), 1);
     ptx::fence_mbar_init();
@@ -182,6 +184,7 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
   } else {
     // =========================== epilogue ===========================
     const int quarter = warp & 3;                 // TMEM lanes this warp may read
+    const int ehalf = (warp - 2) >> 2;            // the two warps of a quarter take alternate column chunks
     const int row = quarter * 32 + lane;          // tile pixel: ty = row / 8, tx = row % 8
     const int ty = row >> 3, tx = row & 7;
     const size_t HW = (size_t)p.H * p.W;
@@ -196,11 +199,13 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       ptx::tc_fence_after();
       if (p.epi == 3) {
         uint32_t rr[16];
-        tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16), rr);
-        ptx::tmem_ld_wait();
+        if (ehalf == 0) {
+          tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16), rr);
+          ptx::tmem_ld_wait();
+        }
         ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(10 + acc));
-        if (live) {
+        if (live && ehalf == 0) {
           // F.interpolate(scale_factor=4, bilinear, align_corners=False): src = max((dst + 0.5) / 4 - 0.5, 0)
           const int Hl = p.H >> 2, Wl = p.W >> 2;
           const float sy = fmaxf(((float)h + 0.5f) * 0.25f - 0.5f, 0.f), sx = fmaxf(((float)w + 0.5f) * 0.25f - 0.5f, 0.f);
@@ -218,17 +223,19 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       }
       if (p.epi != 0) {
         if constexpr (NT % 48 == 0) {
+          bool arrived = false;
 #pragma unroll 1
-          for (int c0 = 0; c0 < NT; c0 += 48) {
+          for (int c0 = ehalf * 48; c0 < NT; c0 += 96) {
             uint32_t r0[16], r1[16], r2[16];
             const uint32_t ta = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0;
             tmem_ld16(ta, r0);
             tmem_ld16(ta + 16, r1);
             tmem_ld16(ta + 32, r2);
             ptx::tmem_ld_wait();
-            if (c0 + 48 >= NT) {
+            if (c0 + 96 >= NT) {           // this warp's last read of the accumulator buffer
               ptx::tc_fence_before();
               ptx::mbar_arrive(BAR(10 + acc));
+              arrived = true;
             }
             if (!live) continue;
             float v[48];
@@ -291,19 +298,25 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
               }
             }
           }
+          if (!arrived) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(BAR(10 + acc));
+          }
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
+      bool arrived = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
+      for (int c0 = ehalf * 16; c0 < NT; c0 += 32) {
         uint32_t rr[16];
         tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0, rr);
         ptx::tmem_ld_wait();
-        if (c0 + 16 >= NT) {  // last read of this accumulator buffer
+        if (c0 + 32 >= NT) {  // this warp's last read of this accumulator buffer
           ptx::tc_fence_before();
           ptx::mbar_arrive(BAR(10 + acc));
+          arrived = true;
         }
         if (!live || n0 + c0 >= p.Cout) continue;
         float v[16];
@@ -346,6 +359,10 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
           y[HW] = make_uint4(cv_pack_bf2(v[8], v[9]), cv_pack_bf2(v[10], v[11]), cv_pack_bf2(v[12], v[13]),
                              cv_pack_bf2(v[14], v[15]));
         }
+      }
+      if (!arrived) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(BAR(10 + acc));
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
