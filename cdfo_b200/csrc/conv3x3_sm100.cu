@@ -72,16 +72,18 @@ __device__ __forceinline__ uint32_t cv_pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int NT, int kStages>
+template <int NT, int kStages, int KBLK>
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Params p) {
   constexpr int kAccCols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));  // per accumulator buffer
   constexpr int kTmemCols = 2 * kAccCols;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int KB = p.Cin / 64;                    // 64-channel blocks
+  const int KB = p.Cin / KBLK;                  // K blocks of KBLK channels (one pipeline stage each)
   const int w_bytes = 9 * p.Cin * NT * 2;
-  constexpr int kPiece = NT * 64 * 2;           // weights of one (tap, 64-channel block)
-  const int stage_stride = p.stream_w ? ((kCvStageBytes + 9 * kPiece + 1023) & ~1023) : kCvStageBytes;
+  constexpr int kChunks = KBLK / 8;             // 8-channel chunks per stage
+  constexpr int kABytes = kChunks * kCvPlane;   // activation halo of one stage
+  constexpr int kPiece = NT * KBLK * 2;         // weights of one (tap, K block)
+  const int stage_stride = p.stream_w ? ((kABytes + 9 * kPiece + 1023) & ~1023) : kABytes;
   uint8_t *wsm = smem;
   uint8_t *asmem = smem + (p.stream_w ? 0 : ((w_bytes + 1023) & ~1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(asmem + kStages * stage_stride);
@@ -113,7 +115,7 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       // resident weights of this N tile: 9 * KB pieces of NT x 64 bf16
       ptx::mbar_arrive_expect_tx(BAR(12), w_bytes);
       const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes;
-      for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * kPiece, src + (size_t)i * kPiece, kPiece, BAR(12));
+      for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * kPiece, src + (size_t)i * kPiece, kPiece, BAR(12));   // [tap][Cin/8][NT][8] as is
     }
   }
   if (warp == 1) {
@@ -136,12 +138,11 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
         if (lane == 0) {
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
           const uint32_t dst = ptx::smem_u32(asmem) + stage * stage_stride;
-          ptx::mbar_arrive_expect_tx(BAR(stage), kCvStageBytes + (p.stream_w ? 9 * kPiece : 0));
-          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * 8, b);
+          ptx::mbar_arrive_expect_tx(BAR(stage), kABytes + (p.stream_w ? 9 * kPiece : 0));
+          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * kChunks, b);
           if (p.stream_w) {
-            const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * kPiece;
-            for (int tap = 0; tap < 9; ++tap)
-              ptx::bulk_g2s(dst + kCvStageBytes + tap * kPiece, src + (size_t)tap * KB * kPiece, kPiece, BAR(stage));
+            // streamed weights are packed [n_tile][K block][tap][chunk][NT][8]: one bulk copy per stage
+            ptx::bulk_g2s(dst + kABytes, p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * 9 * kPiece, 9 * kPiece, BAR(stage));
           }
         }
         __syncwarp();
@@ -164,9 +165,9 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t a_tap = a0 + ((tap / 3) * kCvHaloW + (tap % 3)) * 16;
-            const uint32_t b_tap = p.stream_w ? a0 + kCvStageBytes + tap * kPiece : ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
+            const uint32_t b_tap = p.stream_w ? a0 + kABytes + tap * kPiece : ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < KBLK / 16; ++j) {
               const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kCvPlane, kCvPlane, kCvSbo);
               const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (NT * 16), NT * 16, 128);
               ptx::umma_f16(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
@@ -376,13 +377,20 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
 
 // weight [Cout][Cin][3][3] fp32 -> [n_tile][tap][Cin/8][NT][8] bf16 (rows beyond Cout are zero)
 __global__ void conv3x3_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int Cin,
-                                           int NT, int n_tiles) {
+                                           int NT, int n_tiles, int streamed) {
   const size_t total = (size_t)n_tiles * 9 * Cin * NT;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int j = e % 8;
     const int n = (e / 8) % NT;
-    const int kc = (e / 8 / NT) % (Cin / 8);
-    const int tap = (e / 8 / NT / (Cin / 8)) % 9;
+    int kc, tap;
+    if (streamed) {   // [n_tile][kb (64 ch)][tap][8 chunks][NT][8]
+      const int c8 = (e / 8 / NT) % 8;
+      tap = (e / 8 / NT / 8) % 9;
+      kc = (int)((e / 8 / NT / 8 / 9) % (Cin / 64)) * 8 + c8;
+    } else {          // [n_tile][tap][Cin/8][NT][8]
+      kc = (e / 8 / NT) % (Cin / 8);
+      tap = (e / 8 / NT / (Cin / 8)) % 9;
+    }
     const int nt = e / 8 / NT / (Cin / 8) / 9;
     const int co = nt * NT + n, ci = kc * 8 + j;
     out[e] = __float2bfloat16_rn(co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f);
@@ -421,13 +429,13 @@ static int conv3x3_ntile_resident(int Cout, int Cin) {
 bool conv3x3_streams(int Cout, int Cin) { return conv3x3_ntile_resident(Cout, Cin) < 64 && Cout % 64 == 0 && Cin >= 256; }
 int conv3x3_ntile(int Cout, int Cin) { return conv3x3_streams(Cout, Cin) ? 64 : conv3x3_ntile_resident(Cout, Cin); }
 
-template <int NT>
+template <int NT, int kStages, int KBLK>
 static int launch_conv3x3(const CUtensorMap &tm, const Conv3x3Params &p, int grid, cudaStream_t s) {
-  constexpr int kStages = 2;
-  auto kern = conv3x3_sm100_kernel<NT, kStages>;
+  auto kern = conv3x3_sm100_kernel<NT, kStages, KBLK>;
   const int w_bytes = 9 * p.Cin * NT * 2;
-  const size_t smem = (p.stream_w ? (size_t)kStages * ((kCvStageBytes + 9 * NT * 64 * 2 + 1023) & ~1023)
-                                  : (size_t)((w_bytes + 1023) & ~1023) + kStages * kCvStageBytes) + 18 * 8 + NT * 4 + 64;
+  constexpr int kABytes = (KBLK / 8) * kCvPlane;
+  const size_t smem = (p.stream_w ? (size_t)kStages * ((kABytes + 9 * NT * KBLK * 2 + 1023) & ~1023)
+                                  : (size_t)((w_bytes + 1023) & ~1023) + kStages * kABytes) + 18 * 8 + NT * 4 + 64;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -455,7 +463,8 @@ extern "C" int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cou
   const int nt = conv3x3_ntile(Cout, Cin);
   CDFO_REQUIRE(nt && Cin % 64 == 0, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100: unsupported channels %d -> %d", Cin, Cout);
   const int n_tiles = ceil_div(Cout, nt);
-  conv3x3_pack_weight_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16 *)wpk, Cout, Cin, nt, n_tiles);
+  conv3x3_pack_weight_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16 *)wpk, Cout, Cin, nt, n_tiles,
+                                                                             conv3x3_streams(Cout, Cin) ? 1 : 0);
   return check_launch("cdfo_conv3x3_sm100_pack_weight");
 }
 
@@ -524,11 +533,11 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   const int grid = groups * p.n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
   switch (nt) {
-    case 16: return launch_conv3x3<16>(tm, p, grid, s);
-    case 32: return launch_conv3x3<32>(tm, p, grid, s);
-    case 64: return launch_conv3x3<64>(tm, p, grid, s);
-    case 128: return launch_conv3x3<128>(tm, p, grid, s);
-    case 144: return launch_conv3x3<144>(tm, p, grid, s);
+    case 16: return launch_conv3x3<16, 2, 64>(tm, p, grid, s);
+    case 32: return launch_conv3x3<32, 2, 64>(tm, p, grid, s);
+    case 64: return launch_conv3x3<64, 2, 64>(tm, p, grid, s);
+    case 128: return launch_conv3x3<128, 2, 64>(tm, p, grid, s);
+    case 144: return launch_conv3x3<144, 2, 64>(tm, p, grid, s);
   }
   return fail(CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: N tile %d", nt);
 }

@@ -113,3 +113,30 @@ def test_full_model_ragged_size_vs_oracle(cuda_dev):
     err = (sr.cpu() - ref).abs().max().item()
     print("ragged O2 B=2 24x40: max abs err %.3g" % err)
     assert err <= TOL_ABS
+
+
+def test_full_model_config_c2_vs_oracle(cuda_dev):
+    """BASELINE.json configs[1] (JCT-VC Class-C-shaped clip: 7 x 208x120 LR -> 832x480 HR, LD priors), first frame and a cached
+    second frame, bf16 trunk / feature extraction, against the fp32 torch oracle on the host CPU (~10 s per frame)."""
+    from cdfo_b200 import synthetic
+    from oracle import priors_ref
+    H, W = 120, 208
+    sd = G.seeded_weights("O2")
+    m = _model("O2", cuda_dev, torch.bfloat16)
+    clip = synthetic.make_clip(21, H, W, 1)
+    mvs = torch.from_numpy(priors_ref.mv2mvs_model_layout(clip["mv_l0"][0].numpy()))
+    n0, n1 = synthetic.gumbel_uniforms(4, 2, 0, 1, H, W), synthetic.gumbel_uniforms(4, 2, 1, 1, H, W)
+    with torch.no_grad():
+        ref0, l1_ref = torch_ref.cvsr_v8_forward(sd, clip["x"], mvs, clip["pms"], clip["rms"], clip["ufs"], None, n0, "O2")
+        ref1, _ = torch_ref.cvsr_v8_forward(sd, clip["x"], mvs, clip["pms"], clip["rms"], clip["ufs"], l1_ref, n1, "O2")
+    c = _dev(clip, cuda_dev)
+    sr0, l1 = m(c["x"], None, mvs.to(cuda_dev), c["pms"], c["rms"], c["ufs"], None, noise=n0)
+    sr1, _ = m(c["x"], None, mvs.to(cuda_dev), c["pms"], c["rms"], c["ufs"], l1, noise=n1)
+    rng = np.random.default_rng(1)
+    for name, sr, ref in (("first", sr0, ref0), ("cached", sr1, ref1)):
+        out, r = sr.float().cpu().numpy(), ref.numpy()
+        err = np.abs(out - r).max()
+        target = np.clip(r + rng.normal(0, 0.02, r.shape), 0, 1)
+        dpsnr = abs(G.psnr(np.clip(out, 0, 1), target) - G.psnr(np.clip(r, 0, 1), target))
+        print("CVSR_V8 O2 c2 120x208 %s frame: max abs err %.3g, dPSNR %.4f dB" % (name, err, dpsnr))
+        assert err <= TOL_ABS and dpsnr <= TOL_PSNR
