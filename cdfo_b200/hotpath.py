@@ -147,7 +147,8 @@ _lra_tables = {}
 
 def _lra_tap_tables(mod):
     """kw[9], kh[9], K1[64], R[64,64] of csrc/lra.cu from directW1_conv / directH1_conv (cached per weight version)."""
-    key = (id(mod.directW1_conv.weight), mod.directW1_conv.weight._version, mod.directH1_conv.weight._version)
+    key = (id(mod.directW1_conv.weight), mod.directW1_conv.weight._version, mod.directH1_conv.weight._version,
+           mod.directW1_conv.bias._version, mod.directH1_conv.bias._version)
     hit = _lra_tables.get(id(mod))
     if hit is not None and hit[0] == key:
         return hit[1]
@@ -159,8 +160,11 @@ def _lra_tap_tables(mod):
     k1 = tapm.sum(dim=1)                                     # K1[c_star]
     r = tapm @ tapm.t()                                      # R[c1][c2]
     tab = torch.cat([kw, kh, k1, r.reshape(-1)]).float().contiguous()
-    _lra_tables[id(mod)] = (key, tab)
-    return tab
+    # the two scalar biases are read back ONCE per weight version (a .item() per call would be a host sync per step and
+    # would make the step impossible to capture in a CUDA graph)
+    out = (tab, float(mod.directW1_conv.bias), float(mod.directH1_conv.bias))
+    _lra_tables[id(mod)] = (key, out)
+    return out
 
 
 def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
@@ -191,8 +195,9 @@ def long_range_attention(mod, res, x, u, x2=None):
     out = torch.empty_like(x)
     nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(x2), _lib.ptr(_lra_tap_tables(mod)),
-              ctypes.c_float(float(mod.directW1_conv.bias)), ctypes.c_float(float(mod.directH1_conv.bias)),
+    tab, beta, bh = _lra_tap_tables(mod)
+    _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(x2), _lib.ptr(tab),
+              ctypes.c_float(beta), ctypes.c_float(bh),
               _lib.ptr(_f32(mod.fuse.weight).reshape(64, 128)), _lib.ptr(_f32(mod.fuse.bias)),
               _lib.ptr(out), _lib.ptr(ws), B, H, W, _lib.stream_ptr(x.device))
     return out

@@ -349,12 +349,14 @@ class CVSR_V8(nn.Module):
         if noise is None:
             noise = [torch.rand((B, 64, H, W), device=x.device, generator=self.noise_generator).clamp_min_(1e-12)
                      for _ in _NB]
-        nb = list(_NB)
-        # neighbour-major batch of 6*B: index n*B + b
-        fea_nb = fea[:, nb].transpose(0, 1).reshape(6 * B, -1, H, W)
-        ufs_nb = ufs[:, nb].transpose(0, 1).reshape(6 * B, 1, H, W)
-        rms_nb = rms[:, nb].transpose(0, 1).reshape(6 * B, 1, H, W)
-        mv_nb = mvs1[:, nb].transpose(0, 1).reshape(6 * B, 2, H, W).contiguous()
+        # neighbour-major batch of 6*B: index n*B + b (slices + cat: a list index would build a CPU index tensor, i.e. a
+        # host-to-device copy per call, which also cannot be captured in a CUDA graph)
+        def neighbours(t):
+            return torch.cat([t[:, :ctr], t[:, ctr + 1:]], 1).transpose(0, 1)
+        fea_nb = neighbours(fea).reshape(6 * B, -1, H, W)
+        ufs_nb = neighbours(ufs).reshape(6 * B, 1, H, W)
+        rms_nb = neighbours(rms).reshape(6 * B, 1, H, W)
+        mv_nb = neighbours(mvs1).reshape(6 * B, 2, H, W).contiguous()
         u_nb = torch.cat([u.to(x.device, torch.float32) for u in noise], 0)
         center = fea[:, ctr]
         fused8 = hotpath.align_and_fuse(self, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B)   # c8 bf16 [B,8,H,W,8]

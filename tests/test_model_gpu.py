@@ -140,3 +140,23 @@ def test_full_model_config_c2_vs_oracle(cuda_dev):
         dpsnr = abs(G.psnr(np.clip(out, 0, 1), target) - G.psnr(np.clip(r, 0, 1), target))
         print("CVSR_V8 O2 c2 120x208 %s frame: max abs err %.3g, dPSNR %.4f dB" % (name, err, dpsnr))
         assert err <= TOL_ABS and dpsnr <= TOL_PSNR
+
+
+def test_graphed_step_matches_eager(cuda_dev):
+    """cdfo_b200.graph.GraphedStep: the steady-state step captured in a CUDA graph replays to bit-identical outputs."""
+    from cdfo_b200 import synthetic
+    from cdfo_b200.graph import GraphedStep
+    from oracle import priors_ref
+    H, W, B = 32, 48, 2
+    m = _model("O2", cuda_dev, torch.bfloat16)
+    clip = synthetic.make_clip(5, H, W, B)
+    c = _dev(clip, cuda_dev)
+    mvs = torch.stack([torch.from_numpy(priors_ref.mv2mvs_model_layout(clip["mv_l0"][b].numpy())[0]) for b in range(B)]).to(cuda_dev)
+    noise = [u.to(cuda_dev) for u in synthetic.gumbel_uniforms(4, 9, 0, B, H, W)]
+    _, l1 = m(c["x"], None, mvs, c["pms"], c["rms"], c["ufs"], None, noise=noise)
+    sr_e, l1_e = m(c["x"], None, mvs, c["pms"], c["rms"], c["ufs"], l1, noise=noise)
+    gs = GraphedStep(m, c["x"], mvs, c["pms"], c["rms"], c["ufs"], l1, noise)
+    for _ in range(2):
+        sr_g, l1_g = gs(c["x"], mvs, c["pms"], c["rms"], c["ufs"], l1, noise)
+        torch.cuda.synchronize()
+        assert torch.equal(sr_g, sr_e) and torch.equal(l1_g, l1_e)
