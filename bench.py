@@ -297,7 +297,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=2, help="independent sequences resident per GPU (batched per step)")
+    ap.add_argument("--seqs", type=int, default=4, help="independent sequences resident per GPU (batched per step)")
     ap.add_argument("--pool", type=int, default=3, help="distinct input windows rotated through")
     ap.add_argument("--variant", default="O2", choices=["O1", "O2"])
     ap.add_argument("--lr-h", type=int, default=LR_H)
