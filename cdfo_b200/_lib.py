@@ -33,6 +33,7 @@ def lib():
         _lib = ctypes.CDLL(SO_PATH)
         _lib.cdfo_last_error.restype = ctypes.c_char_p
         _lib.cdfo_conv3x3_sm100_weight_bytes.restype = ctypes.c_size_t
+        _lib.cdfo_conv_sm100_weight_bytes.restype = ctypes.c_size_t
         _lib.cdfo_lra_workspace_bytes.restype = ctypes.c_size_t
         _lib.cdfo_q4t_bytes.restype = ctypes.c_size_t
         _lib.cdfo_mdta_workspace_bytes.restype = ctypes.c_size_t

@@ -30,18 +30,20 @@ def from_c8(x8: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def pack_weight(weight: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 3, 3] -> packed bf16 B operand (cached per parameter / version)."""
+    """[Cout, Cin, k, k] (k = 1 or 3) -> packed bf16 B operand (cached per parameter / version)."""
     key = id(weight)
     hit = _wcache.get(key)
     if hit is not None and hit[0]() is weight and hit[1] == weight._version:
         return hit[2]
-    Cout, Cin = weight.shape[:2]
-    nbytes = _lib.lib().cdfo_conv3x3_sm100_weight_bytes(Cout, Cin)
+    Cout, Cin, ks = weight.shape[:3]
+    if ks not in (1, 3) or weight.shape[3] != ks:
+        raise _lib.CdfoError("conv_sm100: kernel size 1 or 3 expected, got %s" % (tuple(weight.shape[2:]),))
+    nbytes = _lib.lib().cdfo_conv_sm100_weight_bytes(Cout, Cin, ks)
     if nbytes == 0 or Cin % 64 or Cout % 16:
-        raise _lib.CdfoError("conv3x3_sm100: unsupported channels %d -> %d" % (Cin, Cout))
+        raise _lib.CdfoError("conv_sm100: unsupported channels %d -> %d" % (Cin, Cout))
     w = weight.detach().contiguous().float()
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-    _lib.call("cdfo_conv3x3_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, _lib.stream_ptr(w.device))
+    _lib.call("cdfo_conv_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, int(ks), _lib.stream_ptr(w.device))
     _wcache[key] = (weakref.ref(weight), weight._version, out)
     return out
 
@@ -79,11 +81,12 @@ def ps_order(t):
 
 @torch.no_grad()
 def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False):
-    """x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw, or
+    """Convolution with a [Cout, Cin, k, k] weight, k = 1 or 3, stride 1, "same" padding, on the tcgen05 kernel.
+    x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw, or
     [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) when pixel_shuffle and the weight rows are in ps_order)."""
     B, C8, H, W, _ = x8.shape
-    Cout, Cin = weight.shape[:2]
-    if C8 * 8 != Cin or tuple(weight.shape[2:]) != (3, 3):
+    Cout, Cin, ks = weight.shape[:3]
+    if C8 * 8 != Cin or ks not in (1, 3) or weight.shape[3] != ks:
         raise _lib.CdfoError("conv3x3: weight %s does not match input with %d channels" % (tuple(weight.shape), C8 * 8))
     if x8.dtype != torch.bfloat16 or not x8.is_contiguous():
         raise _lib.CdfoError("conv3x3: input must be a contiguous bf16 c8 tensor")
@@ -97,8 +100,8 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
     if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16):
         raise _lib.CdfoError("conv3x3: residual must be a bf16 c8 tensor of the output shape")
-    _lib.call("cdfo_conv3x3_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y),
-              B, Cin, Cout, H, W, int(act), 2 if pixel_shuffle else (0 if out_nchw else 1), _lib.stream_ptr(x8.device))
+    _lib.call("cdfo_conv_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y),
+              B, Cin, Cout, H, W, int(ks), int(act), 2 if pixel_shuffle else (0 if out_nchw else 1), _lib.stream_ptr(x8.device))
     return y
 
 

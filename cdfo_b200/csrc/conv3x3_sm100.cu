@@ -24,10 +24,13 @@
 namespace cdfo {
 
 constexpr int kCvTileH = 16, kCvTileW = 8;                 // 128 output pixels
-constexpr int kCvHaloH = kCvTileH + 2, kCvHaloW = kCvTileW + 2;
-constexpr int kCvPlane = kCvHaloH * kCvHaloW * 16;         // 2880 B: one 8-channel chunk of the halo
-constexpr int kCvStageBytes = 8 * kCvPlane;                // 23040 B: 64 channels
-constexpr int kCvSbo = kCvHaloW * 16;                      // 160 B between 8-pixel rows of the tile
+// geometry of a KS x KS convolution (KS = 3: 18 x 10 halo, 2880 B per 8-channel chunk, 160 B between 8-pixel rows; KS = 1: the tile itself)
+template <int KS> struct CvGeom {
+  static constexpr int kHaloH = kCvTileH + KS - 1, kHaloW = kCvTileW + KS - 1;
+  static constexpr int kPlane = kHaloH * kHaloW * 16;
+  static constexpr int kSbo = kHaloW * 16;
+  static constexpr int kTaps = KS * KS;
+};
 constexpr int kCvThreads = 320;                            // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kCvEpiThreads = 256;
 
@@ -72,18 +75,20 @@ __device__ __forceinline__ uint32_t cv_pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int NT, int kStages, int KBLK>
+template <int NT, int kStages, int KBLK, int KS>
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Params p) {
   constexpr int kAccCols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));  // per accumulator buffer
   constexpr int kTmemCols = 2 * kAccCols;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int KB = p.Cin / KBLK;                  // K blocks of KBLK channels (one pipeline stage each)
-  const int w_bytes = 9 * p.Cin * NT * 2;
+  using G = CvGeom<KS>;
+  constexpr int kTaps = G::kTaps;
+  const int w_bytes = kTaps * p.Cin * NT * 2;
   constexpr int kChunks = KBLK / 8;             // 8-channel chunks per stage
-  constexpr int kABytes = kChunks * kCvPlane;   // activation halo of one stage
+  constexpr int kABytes = kChunks * G::kPlane;  // activation halo of one stage
   constexpr int kPiece = NT * KBLK * 2;         // weights of one (tap, K block)
-  const int stage_stride = p.stream_w ? ((kABytes + 9 * kPiece + 1023) & ~1023) : kABytes;
+  const int stage_stride = p.stream_w ? ((kABytes + kTaps * kPiece + 1023) & ~1023) : kABytes;
   uint8_t *wsm = smem;
   uint8_t *asmem = smem + (p.stream_w ? 0 : ((w_bytes + 1023) & ~1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(asmem + kStages * stage_stride);
@@ -112,10 +117,10 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmap);
     if (!p.stream_w) {
-      // resident weights of this N tile: 9 * KB pieces of NT x 64 bf16
+      // resident weights of this N tile: taps * KB pieces of NT x 64 bf16
       ptx::mbar_arrive_expect_tx(BAR(12), w_bytes);
       const uint8_t *src = p.wpk + (size_t)n_tile * w_bytes;
-      for (int i = 0; i < 9 * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * kPiece, src + (size_t)i * kPiece, kPiece, BAR(12));   // [tap][Cin/8][NT][8] as is
+      for (int i = 0; i < kTaps * KB; ++i) ptx::bulk_g2s(ptx::smem_u32(wsm) + i * kPiece, src + (size_t)i * kPiece, kPiece, BAR(12));   // [tap][Cin/8][NT][8] as is
     }
   }
   if (warp == 1) {
@@ -138,11 +143,11 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
         if (lane == 0) {
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
           const uint32_t dst = ptx::smem_u32(asmem) + stage * stage_stride;
-          ptx::mbar_arrive_expect_tx(BAR(stage), kABytes + (p.stream_w ? 9 * kPiece : 0));
-          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * kChunks, b);
+          ptx::mbar_arrive_expect_tx(BAR(stage), kABytes + (p.stream_w ? kTaps * kPiece : 0));
+          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - KS / 2, h0 - KS / 2, kb * kChunks, b);
           if (p.stream_w) {
             // streamed weights are packed [n_tile][K block][tap][chunk][NT][8]: one bulk copy per stage
-            ptx::bulk_g2s(dst + kABytes, p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * 9 * kPiece, 9 * kPiece, BAR(stage));
+            ptx::bulk_g2s(dst + kABytes, p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * kTaps * kPiece, kTaps * kPiece, BAR(stage));
           }
         }
         __syncwarp();
@@ -163,12 +168,12 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
         if (lane == 0) {
           const uint32_t a0 = ptx::smem_u32(asmem) + stage * stage_stride;
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_tap = a0 + ((tap / 3) * kCvHaloW + (tap % 3)) * 16;
+          for (int tap = 0; tap < kTaps; ++tap) {
+            const uint32_t a_tap = a0 + ((tap / KS) * G::kHaloW + (tap % KS)) * 16;
             const uint32_t b_tap = p.stream_w ? a0 + kABytes + tap * kPiece : ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
 #pragma unroll
             for (int j = 0; j < KBLK / 16; ++j) {
-              const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kCvPlane, kCvPlane, kCvSbo);
+              const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * G::kPlane, G::kPlane, G::kSbo);
               const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (NT * 16), NT * 16, 128);
               ptx::umma_f16(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
             }
@@ -377,23 +382,23 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
 
 // weight [Cout][Cin][3][3] fp32 -> [n_tile][tap][Cin/8][NT][8] bf16 (rows beyond Cout are zero)
 __global__ void conv3x3_pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout, int Cin,
-                                           int NT, int n_tiles, int streamed) {
-  const size_t total = (size_t)n_tiles * 9 * Cin * NT;
+                                           int NT, int n_tiles, int streamed, int taps) {
+  const size_t total = (size_t)n_tiles * taps * Cin * NT;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int j = e % 8;
     const int n = (e / 8) % NT;
     int kc, tap;
     if (streamed) {   // [n_tile][kb (64 ch)][tap][8 chunks][NT][8]
       const int c8 = (e / 8 / NT) % 8;
-      tap = (e / 8 / NT / 8) % 9;
-      kc = (int)((e / 8 / NT / 8 / 9) % (Cin / 64)) * 8 + c8;
+      tap = (e / 8 / NT / 8) % taps;
+      kc = (int)((e / 8 / NT / 8 / taps) % (Cin / 64)) * 8 + c8;
     } else {          // [n_tile][tap][Cin/8][NT][8]
       kc = (e / 8 / NT) % (Cin / 8);
-      tap = (e / 8 / NT / (Cin / 8)) % 9;
+      tap = (e / 8 / NT / (Cin / 8)) % taps;
     }
-    const int nt = e / 8 / NT / (Cin / 8) / 9;
+    const int nt = e / 8 / NT / (Cin / 8) / taps;
     const int co = nt * NT + n, ci = kc * 8 + j;
-    out[e] = __float2bfloat16_rn(co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f);
+    out[e] = __float2bfloat16_rn(co < Cout ? w[((size_t)co * Cin + ci) * taps + tap] : 0.f);
   }
 }
 
@@ -415,26 +420,29 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // N-tile size used for a given Cout / Cin: the largest tile that divides Cout and whose weights (9 * Cin * NT bf16)
 // stay resident in shared memory next to the A stages.
-static int conv3x3_ntile_resident(int Cout, int Cin) {
-  const int budget = 168 * 1024;
+static int conv3x3_ntile_resident(int Cout, int Cin, int taps = 9) {
+  const int budget = (taps == 9 ? 168 : 128) * 1024;     // 1x1: four 16 KB stages instead of two 23 KB ones
   const int cands[5] = {144, 128, 64, 32, 16};
-  for (int c = 0; c < 5; ++c) {
+  for (int c = taps == 9 ? 0 : 1; c < 5; ++c) {
     const int nt = cands[c];
-    if (9 * Cin * nt * 2 <= budget && Cout % nt == 0) return nt;
+    if (taps * Cin * nt * 2 <= budget && Cout % nt == 0) return nt;
   }
   return 0;
 }
 // Wide inputs (Cin >= 256: the trunk's 256 -> 64, tsa_fusion's 448 -> 64) would leave only a 16/32-channel resident N tile,
 // where every A tile is re-read per N tile and the MMA is bound by the shared-memory reads of A; stream the weights instead.
-bool conv3x3_streams(int Cout, int Cin) { return conv3x3_ntile_resident(Cout, Cin) < 64 && Cout % 64 == 0 && Cin >= 256; }
-int conv3x3_ntile(int Cout, int Cin) { return conv3x3_streams(Cout, Cin) ? 64 : conv3x3_ntile_resident(Cout, Cin); }
+bool conv3x3_streams(int Cout, int Cin, int taps = 9) {
+  return taps == 9 && conv3x3_ntile_resident(Cout, Cin) < 64 && Cout % 64 == 0 && Cin >= 256;
+}
+int conv3x3_ntile(int Cout, int Cin, int taps = 9) { return conv3x3_streams(Cout, Cin, taps) ? 64 : conv3x3_ntile_resident(Cout, Cin, taps); }
 
-template <int NT, int kStages, int KBLK>
+template <int NT, int kStages, int KBLK, int KS>
 static int launch_conv3x3(const CUtensorMap &tm, const Conv3x3Params &p, int grid, cudaStream_t s) {
-  auto kern = conv3x3_sm100_kernel<NT, kStages, KBLK>;
-  const int w_bytes = 9 * p.Cin * NT * 2;
-  constexpr int kABytes = (KBLK / 8) * kCvPlane;
-  const size_t smem = (p.stream_w ? (size_t)kStages * ((kABytes + 9 * NT * KBLK * 2 + 1023) & ~1023)
+  auto kern = conv3x3_sm100_kernel<NT, kStages, KBLK, KS>;
+  constexpr int kTaps = KS * KS;
+  const int w_bytes = kTaps * p.Cin * NT * 2;
+  constexpr int kABytes = (KBLK / 8) * CvGeom<KS>::kPlane;
+  const size_t smem = (p.stream_w ? (size_t)kStages * ((kABytes + kTaps * NT * KBLK * 2 + 1023) & ~1023)
                                   : (size_t)((w_bytes + 1023) & ~1023) + kStages * kABytes) + 18 * 8 + NT * 4 + 64;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -452,28 +460,40 @@ using namespace cdfo;
 
 extern "C" int cdfo_conv3x3_sm100_ntile(int Cout, int Cin) { return conv3x3_ntile(Cout, Cin); }
 
-extern "C" size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin) {
-  const int nt = conv3x3_ntile(Cout, Cin);
+extern "C" size_t cdfo_conv_sm100_weight_bytes(int Cout, int Cin, int ksize) {
+  if (ksize != 1 && ksize != 3) return 0;
+  const int nt = conv3x3_ntile(Cout, Cin, ksize * ksize);
   if (!nt) return 0;
-  return (size_t)ceil_div(Cout, nt) * 9 * Cin * nt * 2;
+  return (size_t)ceil_div(Cout, nt) * ksize * ksize * Cin * nt * 2;
 }
+extern "C" size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin) { return cdfo_conv_sm100_weight_bytes(Cout, Cin, 3); }
 
-extern "C" int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream) {
-  CDFO_REQUIRE(w && wpk, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_pack_weight: NULL pointer");
-  const int nt = conv3x3_ntile(Cout, Cin);
-  CDFO_REQUIRE(nt && Cin % 64 == 0, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100: unsupported channels %d -> %d", Cin, Cout);
+extern "C" int cdfo_conv_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, int ksize, void *stream) {
+  CDFO_REQUIRE(w && wpk, CDFO_ERR_NULL, "cdfo_conv_sm100_pack_weight: NULL pointer");
+  CDFO_REQUIRE(ksize == 1 || ksize == 3, CDFO_ERR_UNSUPPORTED, "cdfo_conv_sm100: kernel size 1 or 3 (got %d)", ksize);
+  const int taps = ksize * ksize, nt = conv3x3_ntile(Cout, Cin, taps);
+  CDFO_REQUIRE(nt && Cin % 64 == 0, CDFO_ERR_UNSUPPORTED, "cdfo_conv_sm100: unsupported channels %d -> %d", Cin, Cout);
   const int n_tiles = ceil_div(Cout, nt);
   conv3x3_pack_weight_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16 *)wpk, Cout, Cin, nt, n_tiles,
-                                                                             conv3x3_streams(Cout, Cin) ? 1 : 0);
-  return check_launch("cdfo_conv3x3_sm100_pack_weight");
+                                                                             conv3x3_streams(Cout, Cin, taps) ? 1 : 0, taps);
+  return check_launch("cdfo_conv_sm100_pack_weight");
+}
+extern "C" int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream) {
+  return cdfo_conv_sm100_pack_weight(w, wpk, Cout, Cin, 3, stream);
 }
 
 static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
-                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream);
+                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream, int ksize = 3);
 
 extern "C" int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                                       int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream) {
   return conv3x3_run(x_c8, wpk, bias, resid_c8, y, B, Cin, Cout, H, W, act, out_mode, 0, 0.f, nullptr, stream);
+}
+
+extern "C" int cdfo_conv_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B,
+                                   int Cin, int Cout, int H, int W, int ksize, int act, int out_mode, void *stream) {
+  CDFO_REQUIRE(ksize == 1 || ksize == 3, CDFO_ERR_UNSUPPORTED, "cdfo_conv_sm100_fwd: kernel size 1 or 3 (got %d)", ksize);
+  return conv3x3_run(x_c8, wpk, bias, resid_c8, y, B, Cin, Cout, H, W, act, out_mode, 0, 0.f, nullptr, stream, ksize);
 }
 
 extern "C" int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, const void *first,
@@ -494,7 +514,7 @@ extern "C" int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, 
 }
 
 static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
-                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream) {
+                       int Cout, int H, int W, int act, int out_mode, int epi, float mag, const void *aux, void *stream, int ksize) {
   CDFO_REQUIRE(x_c8 && wpk && y, CDFO_ERR_NULL, "cdfo_conv3x3_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_sm100_fwd: bad shape");
   CDFO_REQUIRE(Cin % 64 == 0 && Cout % 16 == 0, CDFO_ERR_UNSUPPORTED,
@@ -505,14 +525,15 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   CDFO_REQUIRE(epi != 3 || (H % 4 == 0 && W % 4 == 0 && aux), CDFO_ERR_SHAPE, "cdfo_conv_last_skip_sm100_fwd: H, W must be multiples of 4");
   CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & (epi ? 7 : 15)) == 0, CDFO_ERR_SHAPE,
                "cdfo_conv3x3_sm100_fwd: pointers must be 16-byte aligned");
-  const int nt = conv3x3_ntile(Cout, Cin);
+  const int taps = ksize * ksize;
+  const int nt = conv3x3_ntile(Cout, Cin, taps);
   CDFO_REQUIRE(nt, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: no N tile fits shared memory for %d -> %d", Cin, Cout);
   EncodeTiledFn enc = encode_tiled_fn();
   CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv3x3_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
   const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
-  const cuuint32_t box[5] = {8, kCvHaloW, kCvHaloH, 8, 1};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(kCvTileW + ksize - 1), (cuuint32_t)(kCvTileH + ksize - 1), 8, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(x_c8), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -523,7 +544,7 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.act = act; p.out_mode = out_mode;
   p.epi = epi; p.mag = mag; p.aux = (const uint2 *)aux;
   p.n_tiles = ceil_div(Cout, nt);
-  p.stream_w = conv3x3_streams(Cout, Cin) ? 1 : 0;
+  p.stream_w = conv3x3_streams(Cout, Cin, taps) ? 1 : 0;
   p.tiles_x = ceil_div(W, kCvTileW); p.tiles_y = ceil_div(H, kCvTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;
   CDFO_REQUIRE(mt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: too many tiles");
@@ -532,12 +553,21 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   if (groups > p.m_tiles) groups = p.m_tiles;
   const int grid = groups * p.n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
+  if (ksize == 1) {   // 1x1: the A operand is the tile itself, four 16 KB stages
+    switch (nt) {
+      case 16: return launch_conv3x3<16, 4, 64, 1>(tm, p, grid, s);
+      case 32: return launch_conv3x3<32, 4, 64, 1>(tm, p, grid, s);
+      case 64: return launch_conv3x3<64, 4, 64, 1>(tm, p, grid, s);
+      case 128: return launch_conv3x3<128, 4, 64, 1>(tm, p, grid, s);
+    }
+    return fail(CDFO_ERR_UNSUPPORTED, "cdfo_conv_sm100_fwd: N tile %d", nt);
+  }
   switch (nt) {
-    case 16: return launch_conv3x3<16, 2, 64>(tm, p, grid, s);
-    case 32: return launch_conv3x3<32, 2, 64>(tm, p, grid, s);
-    case 64: return launch_conv3x3<64, 2, 64>(tm, p, grid, s);
-    case 128: return launch_conv3x3<128, 2, 64>(tm, p, grid, s);
-    case 144: return launch_conv3x3<144, 2, 64>(tm, p, grid, s);
+    case 16: return launch_conv3x3<16, 2, 64, 3>(tm, p, grid, s);
+    case 32: return launch_conv3x3<32, 2, 64, 3>(tm, p, grid, s);
+    case 64: return launch_conv3x3<64, 2, 64, 3>(tm, p, grid, s);
+    case 128: return launch_conv3x3<128, 2, 64, 3>(tm, p, grid, s);
+    case 144: return launch_conv3x3<144, 2, 64, 3>(tm, p, grid, s);
   }
   return fail(CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_sm100_fwd: N tile %d", nt);
 }

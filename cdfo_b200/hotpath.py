@@ -242,8 +242,7 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
         a8 = conv.to_c8(al(center, fea_i, ufs_prior, mv_nb)).view(6, B, 8, H, W, 8)
         for n, f in enumerate(_SLOT):
             stack[:, 8 * f:8 * f + 8] = a8[n]
-    w = conv.derived(model.tsa_fusion.weight, "3x3", conv.centre_tap)
-    return conv.conv3x3(stack, w, model.tsa_fusion.bias, conv.ACT_LRELU)
+    return conv.conv3x3(stack, model.tsa_fusion.weight, model.tsa_fusion.bias, conv.ACT_LRELU)   # 1x1, 448 -> 64
 
 
 @torch.no_grad()
@@ -253,7 +252,7 @@ def tail(model, t, x_center):
     conv_last + bias + bilinear x4 skip.  t: [B,64,H,W] fp32 or c8 bf16 [B,8,H,W,8]."""
     t8 = t if t.dim() == 5 else conv.to_c8(t)
     for up in (model.upconv1, model.upconv2):
-        w = conv.derived(up.weight, "ps3x3", lambda v: conv.ps_order(conv.centre_tap(v)))
+        w = conv.derived(up.weight, "ps", lambda v: conv.ps_order(v.float()))
         b = conv.derived(up.bias, "ps", conv.ps_order)
         t8 = conv.conv3x3(t8, w, b, conv.ACT_LRELU, pixel_shuffle=True)
     return conv.conv_last_skip(t8, model.conv_last.weight, model.conv_last.bias, x_center)
@@ -269,7 +268,7 @@ def _compose_1x1_after_3x3(w1, b1, w3, b3):
 
 
 def _block_weights(blk):
-    """Per cross-scale block: body convs, 1x1 convs as centre taps, and the 1x1 convs that FOLLOW a body composed into it."""
+    """Per cross-scale block: the 1x1 convs that FOLLOW a body, composed into the body's second 3x3."""
     b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
     dn, up = blk.down._modules["0"], blk.up._modules["0"]
     key = (id(blk), b0.weight._version, b2.weight._version, dn.weight._version, up.weight._version,
@@ -279,8 +278,7 @@ def _block_weights(blk):
         return hit[1]
     wu2, bu2 = _compose_1x1_after_3x3(up.weight.detach(), up.bias.detach(), b2.weight.detach(), b2.bias.detach())
     wd2, bd2 = _compose_1x1_after_3x3(dn.weight.detach(), dn.bias.detach(), b2.weight.detach(), b2.bias.detach())
-    out = {"dn3": conv.centre_tap(dn.weight.detach()), "up3": conv.centre_tap(up.weight.detach()),
-           "up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
+    out = {"up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
     _trunk_cache[id(blk)] = (key, out)
     return out
 
@@ -301,9 +299,9 @@ def cross_scale_block(blk, x8):
     dn, up = blk.down._modules["0"], blk.up._modules["0"]
     wts = _block_weights(blk)
     y = conv.conv3x3(conv.conv3x3(x8, b0.weight, b0.bias, conv.ACT_LRELU), b2.weight, b2.bias, conv.ACT_NONE, resid8=x8)
-    xd = conv.conv3x3(conv.resample(x8, 0), wts["dn3"], dn.bias, conv.ACT_NONE)
+    xd = conv.conv3x3(conv.resample(x8, 0), dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
     cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
-    xu = conv.resample(conv.conv3x3(x8, wts["up3"], up.bias, conv.ACT_NONE), 1)
+    xu = conv.resample(conv.conv3x3(x8, up.weight, up.bias, conv.ACT_NONE), 1)               # 1x1
     b3 = conv.conv3x3(conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU), wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
     return conv.resample(b3, 2, b=cu, base=y)
 

@@ -145,8 +145,7 @@ size_t cdfo_q4t_bytes(int B, int C, int H, int W);
  *   added after the activation; y: out_mode 0 = [B, Cout, H, W] fp32, 1 = [B, Cout/8, H, W, 8] bf16,
  *   2 = [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) of the result when the caller packed the weights / bias with output
  *   channels ordered n' = (2i+j)*(Cout/4) + c (PixelShuffle: channel 4c+2i+j -> (c, 2h+i, 2w+j)): upconv + PixelShuffle +
- *   LeakyReLU of the tail (arch/SIDECVSR_our.py:4473-4476) in one launch.  A 1x1 convolution is passed as a 3x3 weight
- *   whose only non-zero tap is the centre. */
+ *   LeakyReLU of the tail (arch/SIDECVSR_our.py:4473-4476) in one launch (cdfo_conv_sm100_fwd with ksize = 1). */
 int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                            int B, int Cin, int Cout, int H, int W, int act, int out_mode, void *stream);
 /* ---- offset / mask head of MVDualAttAlignment (arch/SIDECVSR_our.py:3274, :3339-3350) fused into the conv epilogue ----
@@ -164,6 +163,13 @@ int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float
 int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const float *lr, float *y, int B,
                                   int Cin, int H, int W, void *stream);
 int cdfo_conv3x3_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream);
+/* The same kernel for kernel size 1 or 3 (stride 1, "same" padding): 1x1 convolutions of the path -- tsa_fusion (448 -> 64,
+ * arch/SIDECVSR_our.py:4466), upconv1 / upconv2 (:4473-4475), the trunk's down / up convs (:388-399).  For ksize = 1 the A operand
+ * is the pixel tile itself (no halo) and the pipeline runs four 16 KB stages.  weight [Cout, Cin, ksize, ksize] fp32. */
+int cdfo_conv_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B, int Cin,
+                        int Cout, int H, int W, int ksize, int act, int out_mode, void *stream);
+int cdfo_conv_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, int ksize, void *stream);
+size_t cdfo_conv_sm100_weight_bytes(int Cout, int Cin, int ksize);
 size_t cdfo_conv3x3_sm100_weight_bytes(int Cout, int Cin);
 int cdfo_conv3x3_sm100_ntile(int Cout, int Cin);
 /* ---- A4 / A5: warp + fusion_out + dual MDTA + project_out (csrc/mdta.cu) ----

@@ -57,7 +57,7 @@ def test_pixel_shuffle_epilogue_and_conv_last_skip(cuda_dev):
     b1 = torch.randn(256, generator=g) * 0.1
     ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(t, w1, b1), 2), 0.1)
     d = lambda v: v.to(cuda_dev)
-    w3 = conv.ps_order(conv.centre_tap(d(w1)))
+    w3 = conv.ps_order(d(w1))                                        # 1x1 weight, PixelShuffle row order
     y8 = conv.conv3x3(conv.to_c8(d(t)), w3, conv.ps_order(d(b1)), conv.ACT_LRELU, pixel_shuffle=True)
     assert tuple(y8.shape) == (B, 8, 2 * H, 2 * W, 8)
     got = conv.from_c8(y8).cpu()
@@ -73,3 +73,20 @@ def test_pixel_shuffle_epilogue_and_conv_last_skip(cuda_dev):
     err = (got2 - ref2).abs().max().item()
     print("conv_last+skip max err %.3g" % err)
     assert err <= 2e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 64, 64, 33, 21), (1, 448, 64, 40, 24), (1, 64, 256, 20, 24), (1, 128, 48, 18, 10)])
+def test_conv1x1_sm100(cuda_dev, B, Cin, Cout, H, W):
+    """Kernel size 1 on the tcgen05 convolution kernel (tsa_fusion, upconv, the trunk's down / up convs)."""
+    import torch.nn.functional as F
+    from cdfo_b200 import conv
+    g = torch.Generator().manual_seed(B + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, w, b), 0.1)
+    d = lambda v: v.to(cuda_dev)
+    y = conv.conv3x3(conv.to_c8(d(x)), d(w), d(b), conv.ACT_LRELU, out_nchw=True).cpu()
+    err = (y - ref).abs().max().item()
+    print("conv1x1 %s: max err %.3g (max|ref| %.3g)" % ((B, Cin, Cout, H, W), err, ref.abs().max().item()))
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item())
