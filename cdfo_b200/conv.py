@@ -53,8 +53,8 @@ _derived = {}
 
 @torch.no_grad()
 def derived(param, kind, fn):
-    """fn(param) cached per (parameter, version, kind): weights re-laid-out for a kernel (1x1 embedded as the centre tap
-    of a 3x3, PixelShuffle channel order, padded output channels ...).  The result then has its own pack_weight entry."""
+    """fn(param) cached per (parameter, version, kind): weights re-laid-out for a kernel (PixelShuffle channel
+    order, padded output channels, composed 1x1 o 3x3 ...).  The result then has its own pack_weight entry."""
     key = (id(param), kind)
     hit = _derived.get(key)
     if hit is not None and hit[0]() is param and hit[1] == param._version:

@@ -226,7 +226,7 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     """Body of the reference's neighbour loop (arch:4445-4456) for all six neighbours at once (batch index n*B + b,
     `center` [B,64,H,W] shared by the six), then stack + tsa_fusion 1x1 + lrelu (arch:4463-4466).
     Returns the fused feature as c8 bf16 [B, 8, H, W, 8].  The 448-channel stack is written once, in bf16, directly by the
-    DCN epilogue (O2) and read by the tcgen05 convolution (the 1x1 is passed as a centre-tap 3x3)."""
+    DCN epilogue (O2) and read by the tcgen05 convolution kernel (kernel size 1)."""
     H, W = center.shape[2:]
     ufs_prior = prior_conv(model.conv_expand_ufs, ufs_nb)
     rms_prior = prior_conv(model.conv_expand_rms, rms_nb)
