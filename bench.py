@@ -35,7 +35,7 @@ UNIT = "frames/s"
 LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
 ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
 # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture (profiles/r01_dcn_tex_ncu.md), per LR pixel
-NCU_TRAFFIC_BYTES_PER_PX = (1.004401e9 + 67.159e6) / (6 * 272 * 480)
+NCU_TRAFFIC_BYTES_PER_PX = (1.004433e9 + 72.121e6) / (6 * 272 * 480)
 
 
 def peaks():
