@@ -9,6 +9,6 @@ from . import deform_conv_cuda  # noqa: F401
 from .dcn import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack,  # noqa: F401
                   deform_conv, deform_conv2d, modulated_deform_conv)
 from .attentionlayer import DSTA  # noqa: F401
-from .priors import flow_warp, modify_mv_for_end_frames, mv2mvs  # noqa: F401
+from .priors import flow_warp, modify_mv_for_end_frames, mv2mvs, mv2mvs_ra  # noqa: F401
 
 __version__ = "0.1.0"

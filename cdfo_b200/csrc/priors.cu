@@ -36,6 +36,33 @@ __global__ void mv2mvs_kernel(const MV *__restrict__ mv, float *__restrict__ flo
   }
 }
 
+// RA twin (opt/data_RA_bi.py:419-424,496-533 + the / 32 of train_RA_37.py:383-386): frame 2 = l0 / -refdist, frame 4 = l1 / refdist
+// (no sign flip), NaN -> 0, refdist == -99 marks a missing list: frame 2 <- -frame 4 (raw), then frame 4 <- -frame 2 (already
+// complemented), frames 1, 0 = 2x, 3x frame 2; 5, 6 = 2x, 3x frame 4; (/ 4) / 32.  Every step is one IEEE fp32 operation.
+template <typename MV>
+__global__ void mv2mvs_ra_kernel(const MV *__restrict__ l0, const MV *__restrict__ l1, float *__restrict__ flows, int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float d0 = (float)l0[p * 3 + 2], d1 = (float)l1[p * 3 + 2];
+  const float n0 = __fmul_rn(d0, -1.0f);
+  // channel swap first: x = stored channel 1, y = stored channel 0
+  float x2 = __fdiv_rn((float)l0[p * 3 + 1], n0), y2 = __fdiv_rn((float)l0[p * 3 + 0], n0);
+  float x4 = __fdiv_rn((float)l1[p * 3 + 1], d1), y4 = __fdiv_rn((float)l1[p * 3 + 0], d1);
+  if (isnan(x2)) x2 = 0.f;
+  if (isnan(y2)) y2 = 0.f;
+  if (isnan(x4)) x4 = 0.f;
+  if (isnan(y4)) y4 = 0.f;
+  if (d0 == -99.f) { x2 = __fmul_rn(x4, -1.f); y2 = __fmul_rn(y4, -1.f); }
+  if (d1 == -99.f) { x4 = __fmul_rn(x2, -1.f); y4 = __fmul_rn(y2, -1.f); }
+  const float vx[7] = {__fmul_rn(x2, 3.f), __fmul_rn(x2, 2.f), x2, 0.f, x4, __fmul_rn(x4, 2.f), __fmul_rn(x4, 3.f)};
+  const float vy[7] = {__fmul_rn(y2, 3.f), __fmul_rn(y2, 2.f), y2, 0.f, y4, __fmul_rn(y4, 2.f), __fmul_rn(y4, 3.f)};
+#pragma unroll
+  for (int f = 0; f < 7; ++f) {
+    flows[((size_t)f * 2 + 0) * HW + p] = __fdiv_rn(__fdiv_rn(vx[f], 4.0f), 32.0f);
+    flows[((size_t)f * 2 + 1) * HW + p] = __fdiv_rn(__fdiv_rn(vy[f], 4.0f), 32.0f);
+  }
+}
+
 // ---------------------------------------------------------------- A2
 // dst slot <- src slot (src >= 0) or 0 (src < 0) for every sample; slot = 2*H*W floats.
 __global__ void mv_slot_kernel(float *__restrict__ flows, int B, int slot_elems, int dst, int src) {
@@ -161,6 +188,16 @@ extern "C" int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H,
   if (mv_is_int32) mv2mvs_kernel<int32_t><<<ceil_div(HW, 256), 256, 0, s>>>((const int32_t *)mv, flows, HW);
   else mv2mvs_kernel<int8_t><<<ceil_div(HW, 256), 256, 0, s>>>((const int8_t *)mv, flows, HW);
   return check_launch("cdfo_mv2mvs");
+}
+
+extern "C" int cdfo_mv2mvs_ra(const void *mv_l0, const void *mv_l1, int mv_is_int32, float *flows, int H, int W, void *stream) {
+  CDFO_REQUIRE(mv_l0 && mv_l1 && flows, CDFO_ERR_NULL, "cdfo_mv2mvs_ra: NULL pointer");
+  CDFO_REQUIRE(H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_mv2mvs_ra: bad size %d x %d", H, W);
+  const int HW = H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mv_is_int32) mv2mvs_ra_kernel<int32_t><<<ceil_div(HW, 256), 256, 0, s>>>((const int32_t *)mv_l0, (const int32_t *)mv_l1, flows, HW);
+  else mv2mvs_ra_kernel<int8_t><<<ceil_div(HW, 256), 256, 0, s>>>((const int8_t *)mv_l0, (const int8_t *)mv_l1, flows, HW);
+  return check_launch("cdfo_mv2mvs_ra");
 }
 
 extern "C" int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void *stream) {

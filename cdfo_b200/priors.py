@@ -29,6 +29,24 @@ def mv2mvs(mv: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
+def mv2mvs_ra(mv_l0: torch.Tensor, mv_l1: torch.Tensor) -> torch.Tensor:
+    """RA configuration: an (l0, l1) pair of CUDA int8 / int32 MV fields [H, W, 3] (ref-distance -99 = list missing) ->
+    fp32 flows [1, 7, 2, H, W]: frames 0-2 from l0, 4-6 from l1, each list complemented from the other where it is missing
+    (opt/data_RA_bi.py:419-424, :496-533, and the / 32 of train_RA_37.py:383-386)."""
+    _lib.require_cuda(mv_l0, mv_l1)
+    if mv_l0.shape != mv_l1.shape or mv_l0.dim() != 3 or mv_l0.size(2) != 3:
+        raise ValueError("mv_l0 / mv_l1 must both be [H, W, 3]")
+    if mv_l0.dtype != mv_l1.dtype or mv_l0.dtype not in (torch.int8, torch.int32):
+        raise TypeError("mv_l0 / mv_l1 must both be int8 or int32")
+    mv_l0, mv_l1 = mv_l0.contiguous(), mv_l1.contiguous()
+    H, W = mv_l0.shape[:2]
+    out = torch.empty((1, 7, 2, H, W), dtype=torch.float32, device=mv_l0.device)
+    _lib.call("cdfo_mv2mvs_ra", _lib.ptr(mv_l0), _lib.ptr(mv_l1), int(mv_l0.dtype == torch.int32), _lib.ptr(out), H, W,
+              _lib.stream_ptr(mv_l0.device))
+    return out
+
+
+@torch.no_grad()
 def modify_mv_for_end_frames(i: int, mvs: torch.Tensor, max_idx: int) -> torch.Tensor:
     """In place on mvs [B, 7, 2, H, W] fp32 (contiguous CUDA); returns mvs."""
     _lib.require_cuda(mvs)

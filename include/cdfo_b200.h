@@ -13,7 +13,7 @@
  *                           torchvision.ops.deform_conv2d at arch/SIDECVSR_our.py:3352
  *   cdfo_dcn_sample_index   floor() indices of deform_conv_cuda_kernel.cu:614-615 + :470-471 (parity probe)
  *   cdfo_flow_warp_fwd      arch/SIDECVSR_our.py:3068-3099  flow_warp (bilinear, zeros, align_corners=True)
- *   cdfo_mv2mvs             test_LD_37.py:83-105  mv2mvs  (+ permute at :160-161)
+ *   cdfo_mv2mvs             test_LD_37.py:83-105  mv2mvs  (+ permute at :160-161);  cdfo_mv2mvs_ra: opt/data_RA_bi.py:496-533
  *   cdfo_mv_end_fix         test_LD_37.py:209-234 modify_mv_for_end_frames
  *   cdfo_pack_c8 / unpack   layout adapters NCHW fp32 <-> channel-chunked bf16 used by the sm_100a kernels
  *   cdfo_dcn_sm100_fwd      same contraction as cdfo_dcn_fwd at the model's hot shape (C=Co=64, 3x3, s=p=d=1,
@@ -79,6 +79,9 @@ int cdfo_flow_warp_fwd(const float *x, const float *flow, float *y, int B, int C
 
 /* ---- A1: mv [H,W,3] (mv_a, mv_b, refdist) int8 or int32 -> flows fp32 [7,2,H,W] (already permuted). ---- */
 int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H, int W, void *stream);
+/* RA twin (opt/data_RA_bi.py:419-424,496-533 and the / 32 of train_RA_37.py:383-386): an (l0, l1) pair of MV fields [H,W,3] with
+ * refdist == -99 marking a missing list -> flows fp32 [7,2,H,W]: frames 0-2 from l0, 4-6 from l1 (no sign flip), complemented. */
+int cdfo_mv2mvs_ra(const void *mv_l0, const void *mv_l1, int mv_is_int32, float *flows, int H, int W, void *stream);
 /* ---- A2: in-place end-of-sequence fix-up on flows [B,7,2,H,W]; frame index i, max_idx as the caller passes. */
 int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void *stream);
 

@@ -96,3 +96,26 @@ def test_prior_conv_vs_torch(cuda_dev):
         ref = F.conv2d(x, conv.weight, conv.bias, padding=1)
     got = hotpath.prior_conv(conv.to(cuda_dev), x.to(cuda_dev)).cpu()
     assert (got - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.int32])
+def test_mv2mvs_ra_bit_exact(cuda_dev, dtype):
+    """RA MV decoding on the device: bit-exact against the golden vector of the reference's Augment and against the
+    oracle on a larger random field with sentinels."""
+    import cdfo_b200
+    import golden_util as G
+    from oracle import priors_ref
+    g = G.load("priors_ra_golden.npz")
+    l0, l1 = g["l0"][0].astype(dtype), g["l1"][0].astype(dtype)
+    got = cdfo_b200.mv2mvs_ra(torch.from_numpy(l0).to(cuda_dev), torch.from_numpy(l1).to(cuda_dev)).cpu().numpy()
+    ref = np.ascontiguousarray(g["flows"][None].transpose(0, 1, 4, 2, 3))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    rng = np.random.default_rng(3)
+    H, W = 40, 56
+    a = rng.integers(-128, 128, (H, W, 3)).astype(dtype)
+    b = rng.integers(-128, 128, (H, W, 3)).astype(dtype)
+    a[..., 2] = rng.choice([-1, -2, -4, -99, 0], (H, W))
+    b[..., 2] = rng.choice([1, 2, 4, -99, 0], (H, W))
+    got = cdfo_b200.mv2mvs_ra(torch.from_numpy(a).to(cuda_dev), torch.from_numpy(b).to(cuda_dev)).cpu().numpy()
+    ref = np.ascontiguousarray(priors_ref.mv2mvs_ra(a, b)[None].transpose(0, 1, 4, 2, 3))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
