@@ -10,5 +10,6 @@ from .dcn import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDefo
                   deform_conv, deform_conv2d, modulated_deform_conv)
 from .attentionlayer import DSTA  # noqa: F401
 from .priors import flow_warp, modify_mv_for_end_frames, mv2mvs, mv2mvs_ra  # noqa: F401
+from .metrics import planes_to_unit, psnr_ssim, sr_to_u8  # noqa: F401
 
 __version__ = "0.1.0"

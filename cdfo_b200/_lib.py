@@ -37,11 +37,12 @@ def lib():
         _lib.cdfo_lra_workspace_bytes.restype = ctypes.c_size_t
         _lib.cdfo_q4t_bytes.restype = ctypes.c_size_t
         _lib.cdfo_mdta_workspace_bytes.restype = ctypes.c_size_t
+        _lib.cdfo_psnr_ssim_workspace_bytes.restype = ctypes.c_size_t
     return _lib
 
 
 # number of CUDA kernels each C-ABI entry launches (for bench.py's gpu_launches claim)
-_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_mdta_fwd": 3}
+_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_mdta_fwd": 3, "cdfo_psnr_ssim_u8": 3}
 launch_count = 0
 
 

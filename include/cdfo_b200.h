@@ -25,6 +25,8 @@
  *   cdfo_mdta_*             arch/SIDECVSR_our.py:3303-3337 / :3455-3492 (warp + fusion + dual MDTA)
  *   cdfo_lra_*              arch/SIDECVSR_our.py:2179-2249 LLongRangAttention.forward
  *   cdfo_tail_fwd           arch/SIDECVSR_our.py:4473-4480 (upconv/PixelShuffle/lrelu x2, conv_last, bilinear x4 skip)
+ *   cdfo_planes_to_unit_f32 / cdfo_sr_to_u8   test_LD_37.py:19-29,172-180 (frame I/O of eval_seq)
+ *   cdfo_psnr_ssim_u8       metric/psnr_ssim.py:278-399,446-484 (calculate_psnr / calculate_ssim, Y channel, border 4)
  */
 #ifndef CDFO_B200_H_
 #define CDFO_B200_H_
@@ -226,6 +228,22 @@ int cdfo_layernorm_c_fwd(const void *x, const float *gamma, const float *beta, v
                          int dtype, void *stream);
 /* depthwise 3x3, stride 1, padding 1, no bias (qkv_dwconv, arch:1545-1576): w [C,1,3,3] fp32. */
 int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B, int C, int H, int W, int dtype, void *stream);
+/* ---- frame I/O of the evaluation loop ----
+ * Integer planes [n_planes, H_in, W] (src_kind 0 uint8, 1 int8, 2 int16, 3 int32) -> fp32 k / 255 [n_planes, H_out, W], rows
+ * H_in..H_out-1 zero: generate_input / generate_PM_input / generate_RM_input (test_LD_37.py:19-29,33-46,64-74; 270 -> 272 rows). */
+int cdfo_planes_to_unit_f32(const void *src, int src_kind, float *dst, int n_planes, int H_in, int W, int H_out, void *stream);
+/* SR fp32 [n_planes, H_in, W] -> uint8 [n_planes, H_out, W], H_out <= H_in (drops the padded rows): slice, clamp(0, 1) * 255.0,
+ * astype(uint8) = truncation, what cv2.imwrite receives at test_LD_37.py:172-180. */
+int cdfo_sr_to_u8(const float *sr, uint8_t *out, int n_planes, int H_in, int W, int H_out, void *stream);
+/* ---- on-GPU PSNR / SSIM: metric/psnr_ssim.py:278-317 calculate_psnr, :320-399 _ssim / calculate_ssim as
+ * cal_psnr_ssim (:446-484) calls them -- single-channel uint8 frames, crop_border pixels dropped on every edge, the float32
+ * / 255 * 255 round trip of to_y_channel, 11x11 Gaussian (sigma 1.5) in fp64 on the valid region.
+ *   res, gt   [B, H, W] uint8;  frame_out [B, 2] fp64 = (psnr dB (inf when identical), ssim) or NULL
+ *   accum     [B, 3] fp64 or NULL: += (psnr, ssim, 1) per image -- the per-sequence sums cal_psnr_ssim averages over frames
+ *   workspace cdfo_psnr_ssim_workspace_bytes(B, H, W, border) bytes.  Summation order is fixed (reproducible). */
+size_t cdfo_psnr_ssim_workspace_bytes(int B, int H, int W, int border);
+int cdfo_psnr_ssim_u8(const uint8_t *res, const uint8_t *gt, int B, int H, int W, int border, double *frame_out, double *accum,
+                      void *workspace, void *stream);
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
 
