@@ -26,7 +26,9 @@
 //     data stage is the bottleneck -- one thread issues tcgen05.mma with A in TMEM (M128 N64 K16, fp16 -> fp32), 4 warps
 //     drain the accumulator (+ bias) to NCHW fp32 or c8 bf16.  Producers are software-pipelined two taps deep
 //     (fields of tap t+2 and the texture fetches of tap t+1 are in flight while tap t is packed).
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -66,7 +68,15 @@ struct Params {
   int tiles_x, tiles_per_img, num_tiles;
 };
 
-constexpr size_t smem_bytes() { return kWBytes + 256 + 16 * 8 + 16; }
+// Mode 2 (dg = 16, dense fields): the fields of a (tile, tap) = 8 group-pair planes x 4 rows x 512 bytes arrive as ONE tiled TMA
+// box in a 6-stage shared-memory ring, issued by a dedicated warp; producers read them with two conflict-free LDS.128.  An
+// L1-missing LDG.128 costs the L1TEX data stage ~11 wavefronts per 512-byte warp request (fill + read-out), an LDS.128 costs 4,
+// and that stage is what bounds this kernel (profiles/r01_dcn_tex_ncu.md).
+constexpr int kFStages = 6;
+constexpr int kFStageBytes = 8 * kTileH * kTileW * 16;      // 16 KB
+constexpr int kFRingOff = (kWBytes + 256 + 32 * 8 + 16 + 1023) & ~1023;
+constexpr int kBarFFull = 16, kBarFEmpty = 24;
+constexpr size_t smem_bytes(int mode) { return mode == 2 ? (size_t)kFRingOff + kFStages * kFStageBytes : (size_t)kWBytes + 256 + 32 * 8 + 16; }
 
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -102,14 +112,17 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <bool kDG16>
-__global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm100_kernel(const __grid_constant__ Params p) {
+// kMode 0: dg < 16 (per-group LDG of the fields); 1: dg = 16, two coalesced LDG.128 per tap; 2: dg = 16, fields staged by TMA
+template <int kMode>
+__global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1)
+dcn_tex_sm100_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap ftm) {
+  constexpr bool kDG16 = kMode != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *wsm = smem;
   float *bias_s = reinterpret_cast<float *>(smem + kWBytes);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + 256);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-  // barrier map: [0,4) A stage full, [4,8) A stage empty, 8 accumulator full, 12 weights
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+  // barrier map: [0,4) A stage full, [4,8) A stage empty, 8 accumulator full, 12 weights, [16,22) fields full, [24,30) fields empty
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -125,6 +138,11 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
       }
       ptx::mbar_init(BAR(8), 1);
       ptx::mbar_init(BAR(12), 1);
+      if (kMode == 2)
+        for (int s = 0; s < kFStages; ++s) {
+          ptx::mbar_init(BAR(kBarFFull + s), 1);
+          ptx::mbar_init(BAR(kBarFEmpty + s), kProdWarps);
+        }
       ptx::fence_mbar_init();
       ptx::mbar_arrive_expect_tx(BAR(12), kWBytes);
       for (int t = 0; t < 9; ++t)
@@ -144,6 +162,21 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
     const uint32_t idesc = make_idesc_f16(kTileM, 64);
     if (warp == 0) ptx::mbar_wait(BAR(12), 0);
     int stage = 0, phase = 0, acc_phase = 0;
+    // mode 2: lane 0 of warp 1 streams the fields of every (tile, tap) of this CTA into the shared-memory ring while the warp
+    // waits for the accumulator (non-blocking probes on both sides, so the pump can never be starved by its own wait)
+    int ftile = blockIdx.x, ftap = 0, fs = 0, fph = 0;
+    const uint32_t ring = ptx::smem_u32(smem + kFRingOff);
+    auto pump_fields = [&]() {
+      while (ftile < p.num_tiles && ptx::mbar_test_wait(BAR(kBarFEmpty + fs), fph ^ 1)) {
+        const TileCoord fc = tile_coord(p, ftile);
+        ptx::mbar_arrive_expect_tx(BAR(kBarFFull + fs), kFStageBytes);
+        // box = (32 px x 2 groups x 2 words, 4 rows, 8 pair planes); rows / columns outside the frame arrive as zeros
+        ptx::tma_load_3d(ring + fs * kFStageBytes, &ftm, BAR(kBarFFull + fs), fc.w0 * 4, fc.h0, (fc.b * 9 + ftap) * 8);
+        if (++fs == kFStages) { fs = 0; fph ^= 1; }
+        if (++ftap == 9) { ftap = 0; ftile += gridDim.x; }
+      }
+    };
+    if (kMode == 2 && warp == 1 && lane == 0) ptx::prefetch_tmap(&ftm);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       if (warp == 0) {
         for (int tap = 0; tap < 9; ++tap) {
@@ -168,7 +201,24 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
       const int h = tc.h0 + warp, w = tc.w0 + lane;
       const bool live = h < p.H && w < p.W;
       const int pix = h * p.W + w;
-      ptx::mbar_wait(BAR(8), acc_phase);
+      if (kMode == 2 && warp == 1) {
+        bool done = false;
+        uint32_t spins = 0;
+        while (!done) {
+          uint32_t d = 0;
+          if (lane == 0) {
+            pump_fields();
+            d = ptx::mbar_test_wait(BAR(8), acc_phase) ? 1u : 0u;
+          }
+          done = __shfl_sync(0xffffffffu, d, 0) != 0;      // warp-uniform exit: lanes must not leave this loop one by one
+          if (!done) {
+            __nanosleep(64);
+            if (++spins > (1u << 26)) __trap();
+          }
+        }
+      } else {
+        ptx::mbar_wait(BAR(8), acc_phase);
+      }
       acc_phase ^= 1;
       ptx::tc_fence_after();
       uint32_t r[32];
@@ -252,9 +302,20 @@ __global__ void __launch_bounds__((kEpiWarps + kProdWarps) * 32, 1) dcn_tex_sm10
       Pix fpix = pix_state(blockIdx.x), ipix = fpix;
       int ftile = blockIdx.x;
       uint2 f[4];
+      int fstage = 0, fphase = 0;
+      const uint8_t *fring = smem + kFRingOff + ((quad0 >> 1) * kTileH + ty) * (kTileW * 16) + tx * 16;
       auto fetch_fields = [&](int tap) {
         const uint2 *src = fpix.f + (size_t)tap * tap_stride;
-        if (kDG16) {
+        if (kMode == 2) {
+          // this thread's two group pairs of the tap the TMA warp staged: a warp reads 512 contiguous bytes per load
+          ptx::mbar_wait(BAR(kBarFFull + fstage), fphase);
+          const uint4 *q = reinterpret_cast<const uint4 *>(fring + fstage * kFStageBytes);
+          const uint4 a = q[0], c = q[kTileH * kTileW];        // next pair plane: + 4 rows x 512 bytes
+          f[0] = make_uint2(a.x, a.y); f[1] = make_uint2(a.z, a.w); f[2] = make_uint2(c.x, c.y); f[3] = make_uint2(c.z, c.w);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(BAR(kBarFEmpty + fstage));   // LSU order: the loads above read before this arrive lands
+          if (++fstage == kFStages) { fstage = 0; fphase ^= 1; }
+        } else if (kDG16) {
           // lanes = consecutive pixels, 16 bytes (two groups) each: 512 contiguous bytes per warp request
           const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(src)), c = ld_stream_u4(reinterpret_cast<const uint4 *>(src + pair_stride));
           f[0] = make_uint2(a.x, a.y); f[1] = make_uint2(a.z, a.w); f[2] = make_uint2(c.x, c.y); f[3] = make_uint2(c.z, c.w);
@@ -353,6 +414,21 @@ __global__ void pack_q4t_kernel(const float *__restrict__ x, uint2 *__restrict__
   out[((size_t)b * (C / 4) + q) * Hp * Wpt + pp] = v;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+static bool g_no_tma_fields = false;   // cdfo_dcn_tex_sm100_set_fields_path: A/B switch for tools/bench_dcn.py
+
 // ---- texture objects over caller-owned linear memory, cached by (device, pointer, shape) ----
 struct TexEntry { int dev; const void *ptr; int rows, Wpt; cudaTextureObject_t tex; unsigned long long stamp; };
 static std::mutex g_mu;
@@ -404,6 +480,11 @@ static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaTe
 }  // namespace cdfo
 
 using namespace cdfo;
+
+extern "C" int cdfo_dcn_tex_sm100_set_fields_path(int use_tma) {
+  dtex::g_no_tma_fields = use_tma == 0;
+  return CDFO_OK;
+}
 
 extern "C" int cdfo_q4t_pitch(int W) { return (W + 3 + 3) & ~3; }
 
@@ -485,16 +566,38 @@ static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, c
   p.num_tiles = (int)nt;
   int grid = num_ctas > 0 ? num_ctas : kNumSMs;
   if (grid > p.num_tiles) grid = p.num_tiles;
+  // mode 2 (fields through TMA) needs the dense [B][9][8][H][W][2] layout; tiny frames keep the LDG path
+  const bool dense = p.f_bstride == (long long)dg * 9 * H * W;
+  int mode = dg != 16 ? 0 : (dense && W >= dtex::kTileW && H >= dtex::kTileH && !dtex::g_no_tma_fields ? 2 : 1);
+  CUtensorMap ftm;
+  memset(&ftm, 0, sizeof(ftm));
+  if (mode == 2) {
+    dtex::EncodeTiledFn enc = dtex::encode_tiled_fn();
+    if (!enc) {
+      mode = 1;
+    } else {
+      const cuuint64_t gdim[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)B * 72};
+      const cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+      const cuuint32_t box[3] = {(cuuint32_t)dtex::kTileW * 4, (cuuint32_t)dtex::kTileH, 8};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult cr = enc(&ftm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(fields), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cdfo_dcn_tex_sm100_fwd: cuTensorMapEncodeTiled(fields) failed with CUresult %d", (int)cr);
+    }
+  }
   static bool attr_done = false;
-  const size_t smem = dtex::smem_bytes();
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtex::smem_bytes(0));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtex::smem_bytes(1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dtex::dcn_tex_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtex::smem_bytes(2));
     if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(dcn_tex_sm100): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   const int threads = (dtex::kEpiWarps + dtex::kProdWarps) * 32;
-  if (dg == 16) dtex::dcn_tex_sm100_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
-  else dtex::dcn_tex_sm100_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 2) dtex::dcn_tex_sm100_kernel<2><<<grid, threads, dtex::smem_bytes(2), st>>>(p, ftm);
+  else if (mode == 1) dtex::dcn_tex_sm100_kernel<1><<<grid, threads, dtex::smem_bytes(1), st>>>(p, ftm);
+  else dtex::dcn_tex_sm100_kernel<0><<<grid, threads, dtex::smem_bytes(0), st>>>(p, ftm);
   return check_launch("cdfo_dcn_tex_sm100_fwd");
 }

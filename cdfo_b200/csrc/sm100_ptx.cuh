@@ -32,12 +32,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the warp for a HW time slice; this never does).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug must fault loudly (trap -> launch error) instead of hanging the device.
-// try_wait itself blocks for a HW time slice, so the bound is many seconds of real time.
+// try_wait itself blocks for a HW time slice (~4 us), so the bound is ~15 s of real time.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 
@@ -53,6 +65,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 }
 
 // Tiled TMA loads (tensor map created on the host with cuTensorMapEncodeTiled).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void *tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void *tmap, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(

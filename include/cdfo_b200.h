@@ -131,6 +131,9 @@ int cdfo_pack_q4p(const float *x_nchw, void *x_q4p, int B, int C, int H, int W, 
 int cdfo_dcn_tex_sm100_fwd(const void *x_q4t, const void *fields, const float *mv, const void *wpk, const float *bias,
                            void *y, int B, int H, int W, int dg, int out_mode, int num_ctas, int x_batch,
                            long long fields_bstride, void *stream);
+/* How cdfo_dcn_tex_sm100_fwd reads dense dg = 16 fields: 1 (default) = tiled TMA boxes into a shared-memory ring, 0 = per-thread
+ * LDG.128 (the path strided fields and dg < 16 always take).  Same results; a measurement switch (tools/bench_dcn.py). */
+int cdfo_dcn_tex_sm100_set_fields_path(int use_tma);
 /* Same kernel writing straight into the stacked input of tsa_fusion (arch/SIDECVSR_our.py:4463-4466): the batch is
  * group-major (sample s = group * n_seq + sequence; the model's groups are the six neighbour frames), and sample s lands in
  * the 8-channel chunks [group_chunk[group], +8) of y_stack [n_seq, stack_chunks, H, W, 8] bf16 (frame slot * 8). */

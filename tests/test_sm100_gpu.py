@@ -117,7 +117,7 @@ def _ref_off_mask(fields):
     return S.unpack_fields(fields)
 
 
-@pytest.mark.parametrize("B,H,W,dg", [(1, 16, 24, 16), (2, 33, 47, 16), (1, 64, 64, 16), (1, 20, 20, 4), (3, 8, 8, 1)])
+@pytest.mark.parametrize("B,H,W,dg", [(1, 16, 24, 16), (2, 33, 47, 16), (1, 64, 64, 16), (1, 20, 20, 4), (3, 8, 8, 1), (2, 6, 70, 16)])
 def test_dcn_tex_vs_oracle(cuda_dev, B, H, W, dg):
     """Texture-unit gather: x and W pre-rounded to fp16, offsets/mask to fp16 on both sides; what remains is the
     texture filter's 8-bit weights (<= 2^-9 of the local texel differences per sample), the fp16 rounding of the
@@ -190,3 +190,28 @@ def test_dcn_tex_full_size_properties(cuda_dev):
     gen = cdfo_b200.dcn._generic_modulated(x1, off, msk, wt, None, 1, 1, 1, 1, dg)
     yr = S.dcn_tex(xq, rnd, w16)
     assert (yr - gen).abs().max().item() <= 6e-3 * gen.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 37, 70), (7, 64, 96), (1, 4, 32)])
+def test_dcn_tex_tma_fields_equals_ldg_fields(cuda_dev, B, H, W):
+    """dg = 16, dense fields: the TMA-staged shared-memory ring and the per-thread LDG.128 path feed the same arithmetic ->
+    bit-identical outputs, ragged tiles (rows / columns past the frame are zero-filled by TMA, never stored) included."""
+    import cdfo_b200
+    from cdfo_b200 import dcn_sm100 as S
+    dg = 16
+    x, offset, mask, wt, b = _case(B, H, W, dg, seed=B * H + W, off_scale=3.0)
+    g = torch.Generator().manual_seed(W)
+    flow = torch.randint(-192, 192, (B, 2, H, W), generator=g).float() / 128.0
+    d = lambda t: t.to(cuda_dev)
+    xq, fields, w16 = S.pack_q4t(d(x)), d(_fields(offset, mask, dg)), S.pack_weight_f16(d(wt))
+    lib = cdfo_b200._lib.lib()
+    try:
+        lib.cdfo_dcn_tex_sm100_set_fields_path(1)
+        y_tma = S.dcn_tex(xq, fields, w16, d(b), mv=d(flow))
+        y8_tma = S.dcn_tex(xq, fields, w16, d(b), mv=d(flow), out_c8=True)
+        lib.cdfo_dcn_tex_sm100_set_fields_path(0)
+        y_ldg = S.dcn_tex(xq, fields, w16, d(b), mv=d(flow))
+        y8_ldg = S.dcn_tex(xq, fields, w16, d(b), mv=d(flow), out_c8=True)
+    finally:
+        lib.cdfo_dcn_tex_sm100_set_fields_path(1)
+    assert torch.equal(y_tma, y_ldg) and torch.equal(y8_tma, y8_ldg)

@@ -67,6 +67,12 @@ def main():
     t = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, out_c8=True, num_ctas=a.ctas), a.iters)
     res["tex_fields_c8out_us"] = t
     res["tex_GBs_algo_1120"] = 1120.0 * P * B / t / 1e3
+    if not a.only_tex:
+        y_tma = S.dcn_tex(xt, fields, w16, bias)
+        cdfo_b200._lib.lib().cdfo_dcn_tex_sm100_set_fields_path(0)      # A/B: fields through per-thread LDG.128 instead of TMA
+        res["tex_fields_ldg_c8out_us"] = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, out_c8=True, num_ctas=a.ctas), a.iters)
+        res["tex_tma_vs_ldg_fields_maxdiff"] = float((y_tma - S.dcn_tex(xt, fields, w16, bias)).abs().max())
+        cdfo_b200._lib.lib().cdfo_dcn_tex_sm100_set_fields_path(1)
     t = timeit(lambda: S.dcn_tex(xt, fields, w16, bias, num_ctas=a.ctas), a.iters)
     res["tex_fields_f32out_us"] = t
     res["pack_q4t_us"] = timeit(lambda: S.pack_q4t(x), a.iters)
