@@ -162,20 +162,24 @@ def run_ours(args):
     # a pool of distinct windows per rank (sequence ids are global: rank r owns sequences r*S .. r*S+S-1)
     pool = []
     for wdx in range(args.pool):
-        clip = synthetic.make_clip(1000 * (rank * S) + wdx, H, W, S)
+        clip = synthetic.make_clip(1000 * (rank * S) + wdx, H, W, S, config=args.priors)
         host = {k: clip[k].pin_memory() for k in ("x", "pms", "rms", "ufs")}
         host["mv"] = clip["mv_l0"].pin_memory()
+        if args.priors == "RA":
+            host["mv1"] = clip["mv_l1"].pin_memory()
         pool.append(host)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     noise = [torch.rand((S, 64, H, W), device=dev, generator=g).clamp_min_(1e-12) for _ in range(6)]
 
-    def decode_mv(mv_dev):
+    def decode_mv(mv_dev, mv1_dev=None):
+        if mv1_dev is not None:      # config c5: bidirectional decoding of the (l0, l1) pair (opt/data_RA_bi.py:496-533)
+            return torch.cat([cdfo_b200.mv2mvs_ra(mv_dev[s], mv1_dev[s]) for s in range(S)], 0)
         return torch.cat([cdfo_b200.mv2mvs(mv_dev[s]) for s in range(S)], 0)
 
     resident = []
     for host in pool:
         d = {k: host[k].to(dev) for k in ("x", "pms", "rms", "ufs")}
-        d["mvs"] = decode_mv(host["mv"].to(dev))
+        d["mvs"] = decode_mv(host["mv"].to(dev), host["mv1"].to(dev) if "mv1" in host else None)
         resident.append(d)
     _, l1 = model(resident[0]["x"], None, resident[0]["mvs"], resident[0]["pms"], resident[0]["rms"], resident[0]["ufs"],
                   None, noise=noise)
@@ -189,14 +193,14 @@ def run_ours(args):
     # exactly like the reference's sliding window would allow); SR leaves as uint8 like cv2.imwrite gets it.
     win = {k: resident[0][k].clone() for k in ("x", "pms", "rms", "ufs")}
     sr_host = torch.empty((S, 1, 4 * H - 8, 4 * W), dtype=torch.uint8).pin_memory()
-    h2d = sum(pool[0][k][:, -1:].numel() * 4 for k in ("x", "pms", "rms", "ufs")) + pool[0]["mv"].numel()
+    h2d = sum(pool[0][k][:, -1:].numel() * 4 for k in ("x", "pms", "rms", "ufs")) + pool[0]["mv"].numel() * (2 if args.priors == "RA" else 1)
     d2h = sr_host.numel()
 
     def step_e2e(i, l1):
         host = pool[i % len(pool)]
         for k in ("x", "pms", "rms", "ufs"):
             win[k] = torch.cat([win[k][:, 1:], host[k][:, -1:].to(dev, non_blocking=True)], 1)
-        mvs = decode_mv(host["mv"].to(dev, non_blocking=True))
+        mvs = decode_mv(host["mv"].to(dev, non_blocking=True), host["mv1"].to(dev, non_blocking=True) if "mv1" in host else None)
         sr, l1 = model(win["x"], None, mvs, win["pms"], win["rms"], win["ufs"], l1, noise=noise)
         out8 = (sr[:, :, :-8].clamp(0, 1) * 255.0).to(torch.uint8)     # crop 1088 -> 1080 rows (test_LD_37.py:172-173)
         sr_host.copy_(out8, non_blocking=True)
@@ -278,8 +282,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, LD priors, "
-                                   "steady state (cached L1_fea), %d sequences per GPU per step" % (args.variant, S),
+            "config": {"workload": "CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, %s priors, "
+                                   "steady state (cached L1_fea), %d sequences per GPU per step" % (args.variant, args.priors, S),
                        "lr": [H, W], "seqs_per_gpu": S, "parallelism": "sequence-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (per step > 1 GB of offsets/masks/activations; %d rotating windows)" % len(pool),
                        "stages": "alignment / attention / fusion / trunk / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16"},
@@ -300,6 +304,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=4, help="independent sequences resident per GPU (batched per step)")
     ap.add_argument("--pool", type=int, default=3, help="distinct input windows rotated through")
     ap.add_argument("--variant", default="O2", choices=["O1", "O2"])
+    ap.add_argument("--priors", default="LD", choices=["LD", "RA"], help="LD (configs c3/c4) or RA = bidirectional (l0, l1) MV pairs (config c5)")
     ap.add_argument("--lr-h", type=int, default=LR_H)
     ap.add_argument("--lr-w", type=int, default=LR_W)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -142,6 +142,39 @@ def test_full_model_config_c2_vs_oracle(cuda_dev):
         assert err <= TOL_ABS and dpsnr <= TOL_PSNR
 
 
+def test_full_model_config_c5_ra_priors_vs_oracle(cuda_dev):
+    """BASELINE.json configs[4] in miniature: the same network fed RA priors -- (a) the bidirectional decoding of an (l0, l1) MV
+    pair with -99 sentinels (opt/data_RA_bi.py:496-533, what train_RA_37 feeds the model) and (b) the RA eval loop's choice, the
+    LD-style mv2mvs applied to l1 alone (mvs1 is the only flow the forward consumes, arch:4445).  Flows must be bit-exact
+    against the oracle's decoding; the SR frame within the north-star tolerance of the fp32 oracle forward."""
+    import cdfo_b200
+    from cdfo_b200 import synthetic
+    from oracle import priors_ref
+    H, W = 40, 64
+    clip = synthetic.make_clip(31, H, W, 1, config="RA")
+    l0, l1 = clip["mv_l0"][0], clip["mv_l1"][0]
+    assert int((l1[..., 2] == -99).sum()) > 0
+    sd = G.seeded_weights("O2")
+    m = _model("O2", cuda_dev)
+    c = _dev({k: clip[k] for k in ("x", "pms", "rms", "ufs")}, cuda_dev)
+    with np.errstate(all="ignore"):
+        flows_ra = priors_ref.mv2mvs_ra(l0.numpy(), l1.numpy())                                  # [7, H, W, 2]
+        flows_l1 = priors_ref.mv2mvs(l1.numpy())
+    cases = {"bidirectional": (np.ascontiguousarray(flows_ra.transpose(0, 3, 1, 2))[None], cdfo_b200.mv2mvs_ra(l0.to(cuda_dev), l1.to(cuda_dev))),
+             "eval-l1": (np.ascontiguousarray(np.asarray(flows_l1).transpose(0, 3, 1, 2))[None], cdfo_b200.mv2mvs(l1.to(cuda_dev)))}
+    for k, (ref_flows, dev_flows) in cases.items():
+        assert np.array_equal(dev_flows.cpu().numpy().view(np.uint32), ref_flows.view(np.uint32)), k     # bit-exact, inf included
+        if not np.isfinite(ref_flows).all():      # x / 0 stays +-inf in the reference (test_LD_37.py:93 only filters NaN)
+            continue
+        noise = synthetic.gumbel_uniforms(4, 5, 0, 1, H, W)
+        with torch.no_grad():
+            ref, _ = torch_ref.cvsr_v8_forward(sd, clip["x"], torch.from_numpy(ref_flows), clip["pms"], clip["rms"], clip["ufs"], None, noise, "O2")
+        sr, _ = m(c["x"], None, dev_flows, c["pms"], c["rms"], c["ufs"], None, noise=noise)
+        err = (sr.cpu() - ref).abs().max().item()
+        print("CVSR_V8 O2 RA priors (%s) 40x64: max abs err %.3g" % (k, err))
+        assert err <= TOL_ABS
+
+
 def test_graphed_step_matches_eager(cuda_dev):
     """cdfo_b200.graph.GraphedStep: the steady-state step captured in a CUDA graph replays to bit-identical outputs."""
     from cdfo_b200 import synthetic
