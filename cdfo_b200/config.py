@@ -1,4 +1,5 @@
 """Process-wide switches of the host side."""
+import os
 
 # Route deformable convolutions of the model's hot shape (64->64, 3x3, s=p=d=1, groups=1) to the tcgen05
 # implicit-GEMM kernel (bf16 operands, fp32 accumulate).  False: every call takes the fp32 catch-all kernel.
@@ -8,3 +9,7 @@ tensor_core = True
 #   "tex"   bilinear footprint fetched by the texture units (cdfo_dcn_tex_sm100_fwd; 8-bit filter weights, fp16 operands)
 #   "exact" fp32 coordinate / weight arithmetic of the reference with LDG gathers (cdfo_dcn_sm100_fwd; bf16 operands)
 dcn_gather = "tex"
+
+# 3x3 convolutions with >= 128 input and 64 output channels (the trunk's 256 -> 64): True = the two-SM kernel (CTA pair,
+# tcgen05.mma cta_group::2, weights resident, cdfo_conv3x3_pair_sm100_fwd); False = the single-SM kernel that streams the weights.
+conv_pair = os.environ.get("CDFO_CONV_PAIR", "1") != "0"

@@ -3,7 +3,7 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, config
 
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 _wcache = {}
@@ -45,6 +45,27 @@ def pack_weight(weight: torch.Tensor) -> torch.Tensor:
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
     _lib.call("cdfo_conv_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, int(ks), _lib.stream_ptr(w.device))
     _wcache[key] = (weakref.ref(weight), weight._version, out)
+    return out
+
+
+_wcache_pair = {}
+
+
+@torch.no_grad()
+def pack_weight_pair(weight: torch.Tensor) -> torch.Tensor:
+    """[64, Cin, 3, 3] -> the CTA-pair kernel's B operand [2 halves][9][Cin/8][32][8] bf16 (cached per parameter / version)."""
+    key = id(weight)
+    hit = _wcache_pair.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    Cin = weight.size(1)
+    nbytes = _lib.lib().cdfo_conv3x3_pair_sm100_weight_bytes(Cin)
+    if nbytes == 0:
+        raise _lib.CdfoError("conv3x3 (CTA pair): unsupported channels %d -> %d" % (Cin, weight.size(0)))
+    w = weight.detach().contiguous().float()
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.call("cdfo_conv3x3_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cin, _lib.stream_ptr(w.device))
+    _wcache_pair[key] = (weakref.ref(weight), weight._version, out)
     return out
 
 
@@ -90,16 +111,22 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
         raise _lib.CdfoError("conv3x3: weight %s does not match input with %d channels" % (tuple(weight.shape), C8 * 8))
     if x8.dtype != torch.bfloat16 or not x8.is_contiguous():
         raise _lib.CdfoError("conv3x3: input must be a contiguous bf16 c8 tensor")
-    wpk = pack_weight(weight)
     b = None if bias is None else bias.detach().contiguous().float()
+    if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
+        raise _lib.CdfoError("conv3x3: residual must be a contiguous bf16 c8 tensor of the output shape")
+    if (config.conv_pair and ks == 3 and not pixel_shuffle and not out_nchw
+            and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)):
+        y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
+        _lib.call("cdfo_conv3x3_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(resid8),
+                  _lib.ptr(y), B, Cin, H, W, int(act), _lib.stream_ptr(x8.device))
+        return y
+    wpk = pack_weight(weight)
     if pixel_shuffle:
         y = torch.empty((B, Cout // 32, 2 * H, 2 * W, 8), dtype=torch.bfloat16, device=x8.device)
     elif out_nchw:
         y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x8.device)
     else:
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
-    if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16):
-        raise _lib.CdfoError("conv3x3: residual must be a bf16 c8 tensor of the output shape")
     _lib.call("cdfo_conv_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y),
               B, Cin, Cout, H, W, int(ks), int(act), 2 if pixel_shuffle else (0 if out_nchw else 1), _lib.stream_ptr(x8.device))
     return y

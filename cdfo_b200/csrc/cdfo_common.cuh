@@ -53,6 +53,9 @@ __device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
 int pointwise_conv(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1, const float *resid2,
                    float *out, int B, int K, int Co, int HW, int act, int mode, cudaStream_t s);
 
+// csrc/conv3x3_sm100.cu: weight [Cout][Cin][k][k] fp32 -> [n_tile][tap][Cin/8][NT][8] bf16 (streamed: [n_tile][K block][tap][8][NT][8])
+int conv3x3_pack_weight_raw(const float *w, void *out, int Cout, int Cin, int NT, int n_tiles, int streamed, int taps, cudaStream_t s);
+
 }  // namespace cdfo
 
 #define CDFO_REQUIRE(cond, code, ...)                 \

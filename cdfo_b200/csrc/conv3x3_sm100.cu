@@ -402,6 +402,11 @@ __global__ void conv3x3_pack_weight_kernel(const float *__restrict__ w, __nv_bfl
   }
 }
 
+int conv3x3_pack_weight_raw(const float *w, void *out, int Cout, int Cin, int NT, int n_tiles, int streamed, int taps, cudaStream_t s) {
+  conv3x3_pack_weight_kernel<<<kNumSMs * 2, 256, 0, s>>>(w, (__nv_bfloat16 *)out, Cout, Cin, NT, n_tiles, streamed, taps);
+  return check_launch("conv3x3_pack_weight");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

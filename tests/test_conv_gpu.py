@@ -45,6 +45,55 @@ def test_conv3x3_sm100(cuda_dev, case):
     assert (conv.from_c8(y8).cpu() - ref).abs().max().item() <= 1.2e-2 * max(1.0, ref.abs().max().item())  # bf16 output rounding
 
 
+PAIR_CASES = [
+    # B, Cin, H, W, act, resid
+    (1, 256, 16, 8, 0, False),      # one tile: the pair's second CTA runs on an out-of-range (zero) box
+    (1, 256, 16, 16, 2, True),      # exactly one tile per CTA of one pair
+    (2, 256, 33, 21, 1, True),      # ragged tiles, odd tile count
+    (1, 128, 24, 40, 0, False),     # two K blocks (conv_expand_fea_r's shape)
+    (1, 192, 20, 24, 2, False),     # three K blocks = the stage count
+    (3, 256, 136, 240, 0, True),    # the trunk's half-resolution call: ~10 tiles per CTA (ring and accumulator wrap-around)
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv3x3_pair_sm100(cuda_dev, case):
+    """Two-SM kernel (tcgen05.mma cta_group::2, weights resident in a CTA pair) against torch conv2d, and against the single-SM
+    kernel (same bf16 operands, fp32 accumulation in a different order)."""
+    import cdfo_b200
+    from cdfo_b200 import conv
+    B, Cin, H, W, act, use_res = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(64, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    w[40:] *= 3.0                                   # the two halves of the output channels live in different CTAs: make them differ
+    b = torch.randn(64, generator=g) * 0.1
+    r = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float() if use_res else None
+    d = lambda t: None if t is None else t.to(cuda_dev)
+    xd, wd, bd = d(x), d(w), d(b)
+    ref = F.conv2d(xd, wd, bd, 1, 1)
+    ref = F.relu(ref) if act == 1 else (F.leaky_relu(ref, 0.1) if act == 2 else ref)
+    if use_res:
+        ref = ref + d(r)
+    x8 = conv.to_c8(xd)
+    r8 = conv.to_c8(d(r)) if use_res else None
+    assert cdfo_b200._lib.lib().cdfo_conv3x3_pair_sm100_supported(64, Cin) == 1
+    try:
+        cdfo_b200.config.conv_pair = True
+        y_pair = conv.from_c8(conv.conv3x3(x8, wd, bd, act, r8))
+        y_again = conv.from_c8(conv.conv3x3(x8, wd, bd, act, r8))
+        cdfo_b200.config.conv_pair = False
+        y_single = conv.from_c8(conv.conv3x3(x8, wd, bd, act, r8))
+    finally:
+        cdfo_b200.config.conv_pair = True
+    scale = max(1.0, ref.abs().max().item())
+    err = (y_pair - ref).abs().max().item()
+    print("conv3x3 pair %s: max err %.3g vs torch, %.3g vs single-SM (max|ref| %.3g)" % (case, err, (y_pair - y_single).abs().max().item(), scale))
+    assert torch.equal(y_pair, y_again)
+    assert err <= 1.2e-2 * scale                    # bf16 output rounding
+    assert (y_pair - y_single).abs().max().item() <= 8e-3 * scale
+
+
 def test_pixel_shuffle_epilogue_and_conv_last_skip(cuda_dev):
     """upconv (1x1 as a centre-tap 3x3) + PixelShuffle(2) + lrelu in the conv epilogue, and conv_last + bilinear x4 skip,
     against the plain torch composition of arch/SIDECVSR_our.py:4473-4480 on bf16-rounded operands."""

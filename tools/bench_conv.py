@@ -34,12 +34,19 @@ def main():
         b = torch.randn(Cout, device=dev)
         x8 = conv.to_c8(x)
         t_ours = timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU))
+        t_single = None
+        if Cout == 64 and Cin >= 128:      # A/B: the single-SM kernel with streamed weights
+            import cdfo_b200
+            cdfo_b200.config.conv_pair = False
+            t_single = timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU))
+            cdfo_b200.config.conv_pair = True
         xcl = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wcl = wt.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         bb = b.to(torch.bfloat16)
         t_cudnn = timeit(lambda: F.leaky_relu(F.conv2d(xcl, wcl, bb, 1, 1), 0.1))
         flops = 2.0 * B * h * w * Cin * Cout * 9
         out.append({"shape": [B, Cin, Cout, h, w], "ours_us": round(t_ours, 1), "ours_TFLOPs": round(flops / t_ours / 1e6, 1),
+                    "single_sm_TFLOPs": None if t_single is None else round(flops / t_single / 1e6, 1),
                     "cudnn_bf16_us": round(t_cudnn, 1), "cudnn_TFLOPs": round(flops / t_cudnn / 1e6, 1)})
     for o in out:
         print(json.dumps(o))
