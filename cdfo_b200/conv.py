@@ -53,18 +53,18 @@ _wcache_pair = {}
 
 @torch.no_grad()
 def pack_weight_pair(weight: torch.Tensor) -> torch.Tensor:
-    """[64, Cin, 3, 3] -> the CTA-pair kernel's B operand [2 halves][9][Cin/8][32][8] bf16 (cached per parameter / version)."""
+    """[Cout, Cin, 3, 3] -> the CTA-pair kernel's B operand [2 halves][9][Cin/8][Cout/2][8] bf16 (cached per parameter / version)."""
     key = id(weight)
     hit = _wcache_pair.get(key)
     if hit is not None and hit[0]() is weight and hit[1] == weight._version:
         return hit[2]
-    Cin = weight.size(1)
-    nbytes = _lib.lib().cdfo_conv3x3_pair_sm100_weight_bytes(Cin)
+    Cout, Cin = weight.shape[:2]
+    nbytes = _lib.lib().cdfo_conv3x3_pair_sm100_weight_bytes(Cout, Cin)
     if nbytes == 0:
-        raise _lib.CdfoError("conv3x3 (CTA pair): unsupported channels %d -> %d" % (Cin, weight.size(0)))
+        raise _lib.CdfoError("conv3x3 (CTA pair): unsupported channels %d -> %d" % (Cin, Cout))
     w = weight.detach().contiguous().float()
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-    _lib.call("cdfo_conv3x3_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cin, _lib.stream_ptr(w.device))
+    _lib.call("cdfo_conv3x3_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, _lib.stream_ptr(w.device))
     _wcache_pair[key] = (weakref.ref(weight), weight._version, out)
     return out
 
@@ -118,7 +118,7 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
             and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)):
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
         _lib.call("cdfo_conv3x3_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(resid8),
-                  _lib.ptr(y), B, Cin, H, W, int(act), _lib.stream_ptr(x8.device))
+                  _lib.ptr(y), B, Cin, Cout, H, W, int(act), _lib.stream_ptr(x8.device))
         return y
     wpk = pack_weight(weight)
     if pixel_shuffle:

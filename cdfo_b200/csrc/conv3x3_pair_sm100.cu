@@ -1,5 +1,6 @@
-// 3x3 / stride 1 / padding 1 convolution, wide input -> 64 output channels (the trunk's 256 -> 64, arch/SIDECVSR_our.py:378-406),
-// as a TWO-SM tcgen05 implicit GEMM: a cluster of 2 CTAs (one TPC) issues tcgen05.mma.cta_group::2 with M = 256, N = 64.
+// 3x3 / stride 1 / padding 1 convolutions of the reconstruction trunk (256 -> 64 and 64 -> 256, arch/SIDECVSR_our.py:378-406) and other
+// Cin -> 64 layers as a TWO-SM tcgen05 implicit GEMM: a cluster of 2 CTAs (one TPC) issues tcgen05.mma.cta_group::2 with M = 256 and
+// N = 64 or 256; each CTA holds the weights of HALF the output channels (template NH = 32 or 128) resident in shared memory.
 //
 // Why a CTA pair: at N = 64 the single-SM kernel (conv3x3_sm100.cu) cannot keep 9 x 256 x 64 weights (295 KB) in shared memory, so it
 // streams them from L2 with every pixel tile: 387 KB per 128 pixels and SM, i.e. 84 B/clk at tensor peak against an L2 that sustains
@@ -26,18 +27,15 @@ constexpr int kPlane = kHaloH * kHaloW * 16;      // bytes of one 8-channel chun
 constexpr int kSbo = kHaloW * 16;
 constexpr int kChunks = 8;                        // 64 channels per pipeline stage
 constexpr int kABytes = kChunks * kPlane;         // 23 040
-constexpr int kNH = 32;                           // output channels whose weights one CTA holds
-constexpr int kPiece = kNH * 64 * 2;              // weights of one (tap, K block) and CTA
 constexpr int kStages = 3;
 constexpr int kThreads = 320, kEpiWarps = 8;
-constexpr int kAccCols = 64, kTmemCols = 128;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA of the pair
 
 struct Params {
-  const uint8_t *wpk;   // [2 halves][9 taps][Cin/8][32][8] bf16
-  const float *bias;    // [64] or nullptr
-  const uint4 *resid;   // c8 bf16 [B][8][H][W][8] or nullptr (added after the activation)
-  uint4 *y;             // c8 bf16 [B][8][H][W][8]
+  const uint8_t *wpk;   // [2 halves][9 taps][Cin/8][NH][8] bf16
+  const float *bias;    // [2 NH] or nullptr
+  const uint4 *resid;   // c8 bf16 [B][2 NH / 8][H][W][8] or nullptr (added after the activation)
+  uint4 *y;             // c8 bf16 [B][2 NH / 8][H][W][8]
   int B, Cin, H, W, act;
   int tiles_x, tiles_y, m_tiles;
 };
@@ -103,8 +101,13 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// NH = output channels whose weights one CTA holds (N = 2 NH over the pair)
+template <int NH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  constexpr int kNH = NH, kN = 2 * NH;
+  constexpr int kPiece = kNH * 64 * 2;              // weights of one (tap, K block) and CTA
+  constexpr int kAccCols = kN, kTmemCols = 2 * kN;  // accumulator double-buffered: 128 or 512 columns
   extern __shared__ __align__(1024) uint8_t smem[];
   const int KB = p.Cin / 64;
   const int w_bytes = 9 * p.Cin * kNH * 2;                // this CTA's half of the weights
@@ -122,7 +125,7 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
-  for (int i = tid; i < 64; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = tid; i < kN; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(BAR(s), 1);
@@ -183,7 +186,7 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
     if (leader) {
-      const uint32_t idesc = ptx::make_idesc_bf16(256, 64);
+      const uint32_t idesc = ptx::make_idesc_bf16(256, kN);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int it = 0;; ++it) {
         if ((it * num_pairs + pair) * 2 >= p.m_tiles) break;
@@ -242,45 +245,44 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       const size_t pix = (size_t)h * p.W + w;
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
-      uint32_t r0[16], r1[16];
-      const uint32_t ta = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + ehalf * 16;
-      tmem_ld16(ta, r0);
-      tmem_ld16(ta + 32, r1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {                                     // this warp has drained its part of the buffer: tell the leader's issuer
-        if (leader) ptx::mbar_arrive(BAR(10 + acc));
-        else mbar_arrive_cluster(BAR(10 + acc), 0);
-      }
-      if (live) {
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          const int c0 = ehalf * 16 + part * 32;
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = __uint_as_float(part ? r1[i] : r0[i]) + bias_s[c0 + i];
-            if (p.act == 1) t = fmaxf(t, 0.f);
-            else if (p.act == 2) t = t > 0.f ? t : 0.1f * t;
-            v[i] = t;
+      // the two warps of a TMEM lane quarter take alternate 16-column chunks; 16 channels = two c8 chunks of 16 bytes per pixel
+#pragma unroll 1
+      for (int c0 = ehalf * 16; c0 < kN; c0 += 32) {
+        uint32_t rr[16];
+        tmem_ld16(tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0, rr);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= kN) {                               // this warp has drained its part of the buffer: tell the leader's issuer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(BAR(10 + acc));
+            else mbar_arrive_cluster(BAR(10 + acc), 0);
           }
-          if (p.resid) {
+        }
+        if (!live) continue;
+        float v[16];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint4 q = __ldg(p.resid + ((size_t)b * 8 + c0 / 8 + half) * HW + pix);
-              const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+        for (int i = 0; i < 16; ++i) {
+          float t = __uint_as_float(rr[i]) + bias_s[c0 + i];
+          if (p.act == 1) t = fmaxf(t, 0.f);
+          else if (p.act == 2) t = t > 0.f ? t : 0.1f * t;
+          v[i] = t;
+        }
+        if (p.resid) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                v[half * 8 + 2 * i] += __uint_as_float(qq[i] << 16);
-                v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
-              }
+          for (int half = 0; half < 2; ++half) {
+            const uint4 q = __ldg(p.resid + ((size_t)b * (kN / 8) + c0 / 8 + half) * HW + pix);
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[half * 8 + 2 * i] += __uint_as_float(qq[i] << 16);
+              v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
             }
           }
-          uint4 *y = p.y + ((size_t)b * 8 + c0 / 8) * HW + pix;
-          y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
-          y[HW] = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
         }
+        uint4 *y = p.y + ((size_t)b * (kN / 8) + c0 / 8) * HW + pix;
+        y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
+        y[HW] = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -308,34 +310,65 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-static size_t smem_bytes(int Cin) { return (size_t)((9 * Cin * kNH * 2 + 1023) & ~1023) + kStages * kABytes + 18 * 8 + 64 * 4 + 64; }
+static int half_channels(int Cout, int Cin) {
+  if (Cout == 64 && Cin % 64 == 0 && Cin >= 64 && Cin <= 256) return 32;
+  if (Cout == 256 && Cin == 64) return 128;
+  return 0;
+}
+static size_t smem_bytes(int Cin, int NH) { return (size_t)((9 * Cin * NH * 2 + 1023) & ~1023) + kStages * kABytes + 18 * 8 + 2 * NH * 4 + 64; }
+
+template <int NH>
+static int launch(const CUtensorMap &tm, const Params &p, cudaStream_t stream) {
+  const size_t smem = smem_bytes(p.Cin, NH);
+  static size_t attr_smem = 0;
+  static int max_pairs = 0;
+  auto kern = conv3x3_pair_sm100_kernel<NH>;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(conv3x3_pair_sm100<%d>, %zu): %s", NH, smem, cudaGetErrorString(e));
+    attr_smem = smem;
+    // how many CTA pairs are co-resident (one CTA per SM; a GPC with an odd SM count leaves one SM out)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs & ~1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    max_pairs = (e == cudaSuccess && n > 0) ? n : kNumSMs / 2;
+    if (max_pairs > kNumSMs / 2) max_pairs = kNumSMs / 2;
+    (void)cudaGetLastError();
+  }
+  int pairs = (p.m_tiles + 1) / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  kern<<<pairs * 2, kThreads, smem, stream>>>(tm, p);
+  return check_launch("cdfo_conv3x3_pair_sm100_fwd");
+}
 
 }  // namespace cpair
-
-
 }  // namespace cdfo
 
 using namespace cdfo;
 
 extern "C" int cdfo_conv3x3_pair_sm100_supported(int Cout, int Cin) {
-  return Cout == 64 && Cin % 64 == 0 && Cin >= 128 && cpair::smem_bytes(Cin) <= 227 * 1024 ? 1 : 0;
+  const int nh = cpair::half_channels(Cout, Cin);
+  return nh && cpair::smem_bytes(Cin, nh) <= 227 * 1024 ? 1 : 0;
 }
 
-extern "C" size_t cdfo_conv3x3_pair_sm100_weight_bytes(int Cin) {
-  return cdfo_conv3x3_pair_sm100_supported(64, Cin) ? (size_t)2 * 9 * Cin * cpair::kNH * 2 : 0;
+extern "C" size_t cdfo_conv3x3_pair_sm100_weight_bytes(int Cout, int Cin) {
+  return cdfo_conv3x3_pair_sm100_supported(Cout, Cin) ? (size_t)9 * Cin * Cout * 2 : 0;
 }
 
-extern "C" int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, int Cin, void *stream) {
+extern "C" int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream) {
   CDFO_REQUIRE(w && wpk, CDFO_ERR_NULL, "cdfo_conv3x3_pair_sm100_pack_weight: NULL pointer");
-  CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(64, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100: unsupported input channels %d", Cin);
-  return conv3x3_pack_weight_raw(w, wpk, 64, Cin, cpair::kNH, 2, 0, 9, (cudaStream_t)stream);
+  CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(Cout, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100: unsupported channels %d -> %d", Cin, Cout);
+  return conv3x3_pack_weight_raw(w, wpk, Cout, Cin, cpair::half_channels(Cout, Cin), 2, 0, 9, (cudaStream_t)stream);
 }
 
 extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B,
-                                           int Cin, int H, int W, int act, void *stream) {
+                                           int Cin, int Cout, int H, int W, int act, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv3x3_pair_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_pair_sm100_fwd: bad shape");
-  CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(64, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: unsupported input channels %d", Cin);
+  CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(Cout, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: unsupported channels %d -> %d", Cin, Cout);
   CDFO_REQUIRE(act >= 0 && act <= 2, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: act %d", act);
   CDFO_REQUIRE(((uintptr_t)x_c8 & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y_c8 & 15) == 0 && ((uintptr_t)resid_c8 & 15) == 0,
                CDFO_ERR_SHAPE, "cdfo_conv3x3_pair_sm100_fwd: pointers must be 16-byte aligned");
@@ -356,26 +389,6 @@ extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, co
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;
   CDFO_REQUIRE(mt < (1ll << 30), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: too many tiles");
   p.m_tiles = (int)mt;
-  const size_t smem = cpair::smem_bytes(Cin);
-  static size_t attr_smem = 0;
-  static int max_pairs = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(cpair::conv3x3_pair_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cudaFuncSetAttribute(conv3x3_pair_sm100, %zu): %s", smem, cudaGetErrorString(e));
-    attr_smem = smem;
-    // how many CTA pairs are co-resident (one CTA per SM; a GPC with an odd SM count leaves one SM out)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs & ~1);
-    cfg.blockDim = dim3(cpair::kThreads);
-    cfg.dynamicSmemBytes = smem;
-    int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, cpair::conv3x3_pair_sm100_kernel, &cfg);
-    max_pairs = (e == cudaSuccess && n > 0) ? n : kNumSMs / 2;
-    if (max_pairs > kNumSMs / 2) max_pairs = kNumSMs / 2;
-    (void)cudaGetLastError();
-  }
-  int pairs = (p.m_tiles + 1) / 2;
-  if (pairs > max_pairs) pairs = max_pairs;
-  cpair::conv3x3_pair_sm100_kernel<<<pairs * 2, cpair::kThreads, smem, (cudaStream_t)stream>>>(tm, p);
-  return check_launch("cdfo_conv3x3_pair_sm100_fwd");
+  if (cpair::half_channels(Cout, Cin) == 32) return cpair::launch<32>(tm, p, (cudaStream_t)stream);
+  return cpair::launch<128>(tm, p, (cudaStream_t)stream);
 }

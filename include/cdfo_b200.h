@@ -231,15 +231,16 @@ int cdfo_layernorm_c_fwd(const void *x, const float *gamma, const float *beta, v
                          int dtype, void *stream);
 /* depthwise 3x3, stride 1, padding 1, no bias (qkv_dwconv, arch:1545-1576): w [C,1,3,3] fp32. */
 int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B, int C, int H, int W, int dtype, void *stream);
-/* ---- 3x3 convolution Cin -> 64 for wide inputs (the trunk's 256 -> 64, arch/SIDECVSR_our.py:378-406) on a CTA PAIR: tcgen05.mma
- * cta_group::2, M = 256 pixels over two SMs, each CTA holding the weights of 32 output channels resident in shared memory
- * (csrc/conv3x3_pair_sm100.cu).  x_c8 [B,Cin/8,H,W,8] bf16 -> y_c8 [B,8,H,W,8] bf16 = act(conv + bias) + resid_c8 (act 0 none /
- * 1 ReLU / 2 LeakyReLU 0.1; bias, resid_c8 may be NULL).  Supported: Cin in {128, 192, 256}. */
+/* ---- 3x3 convolutions on a CTA PAIR (csrc/conv3x3_pair_sm100.cu): tcgen05.mma cta_group::2, M = 256 pixels over the two SMs of a
+ * TPC, each CTA holding the weights of HALF the output channels resident in shared memory.  Supported: Cout = 64 with Cin in
+ * {64, 128, 192, 256} (the trunk's 256 -> 64, conv_expand_fea_r, the 64 -> 64 layers) and 64 -> 256 (the trunk's body.0,
+ * arch/SIDECVSR_our.py:378-406).  x_c8 [B,Cin/8,H,W,8] bf16 -> y_c8 [B,Cout/8,H,W,8] bf16 = act(conv + bias) + resid_c8
+ * (act 0 none / 1 ReLU / 2 LeakyReLU 0.1; bias, resid_c8 may be NULL).  Results are bit-identical to cdfo_conv_sm100_fwd. */
 int cdfo_conv3x3_pair_sm100_supported(int Cout, int Cin);
-size_t cdfo_conv3x3_pair_sm100_weight_bytes(int Cin);
-int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, int Cin, void *stream);
+size_t cdfo_conv3x3_pair_sm100_weight_bytes(int Cout, int Cin);
+int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, int Cout, int Cin, void *stream);
 int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B, int Cin,
-                                int H, int W, int act, void *stream);
+                                int Cout, int H, int W, int act, void *stream);
 /* ---- frame I/O of the evaluation loop ----
  * Integer planes [n_planes, H_in, W] (src_kind 0 uint8, 1 int8, 2 int16, 3 int32) -> fp32 k / 255 [n_planes, H_out, W], rows
  * H_in..H_out-1 zero: generate_input / generate_PM_input / generate_RM_input (test_LD_37.py:19-29,33-46,64-74; 270 -> 272 rows). */

@@ -46,13 +46,18 @@ def test_conv3x3_sm100(cuda_dev, case):
 
 
 PAIR_CASES = [
-    # B, Cin, H, W, act, resid
-    (1, 256, 16, 8, 0, False),      # one tile: the pair's second CTA runs on an out-of-range (zero) box
-    (1, 256, 16, 16, 2, True),      # exactly one tile per CTA of one pair
-    (2, 256, 33, 21, 1, True),      # ragged tiles, odd tile count
-    (1, 128, 24, 40, 0, False),     # two K blocks (conv_expand_fea_r's shape)
-    (1, 192, 20, 24, 2, False),     # three K blocks = the stage count
-    (3, 256, 136, 240, 0, True),    # the trunk's half-resolution call: ~10 tiles per CTA (ring and accumulator wrap-around)
+    # B, Cin, Cout, H, W, act, resid
+    (1, 256, 64, 16, 8, 0, False),      # one tile: the pair's second CTA recomputes tile 0 and stores nothing
+    (1, 256, 64, 16, 16, 2, True),      # exactly one tile per CTA of one pair
+    (2, 256, 64, 33, 21, 1, True),      # ragged tiles, odd tile count
+    (1, 128, 64, 24, 40, 0, False),     # two K blocks (conv_expand_fea_r's shape)
+    (1, 192, 64, 20, 24, 2, False),     # three K blocks = the stage count
+    (3, 256, 64, 136, 240, 0, True),    # the trunk's half-resolution call: ~10 tiles per CTA (ring and accumulator wrap-around)
+    (1, 64, 256, 16, 8, 2, False),      # N = 256: each CTA holds 128 output channels, the accumulators fill all 512 TMEM columns
+    (2, 64, 256, 40, 56, 2, False),     # trunk body.0 shape, several tiles per CTA
+    (3, 64, 256, 136, 240, 0, False),
+    (2, 64, 64, 33, 21, 1, True),       # 64 -> 64 layers (one K block per tile)
+    (6, 64, 64, 64, 64, 2, True),
 ]
 
 
@@ -62,13 +67,13 @@ def test_conv3x3_pair_sm100(cuda_dev, case):
     kernel (same bf16 operands, fp32 accumulation in a different order)."""
     import cdfo_b200
     from cdfo_b200 import conv
-    B, Cin, H, W, act, use_res = case
+    B, Cin, Cout, H, W, act, use_res = case
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16).float()
-    w = (torch.randn(64, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
-    w[40:] *= 3.0                                   # the two halves of the output channels live in different CTAs: make them differ
-    b = torch.randn(64, generator=g) * 0.1
-    r = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float() if use_res else None
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    w[Cout // 2 + 8:] *= 3.0                        # the two halves of the output channels live in different CTAs: make them differ
+    b = torch.randn(Cout, generator=g) * 0.1
+    r = torch.randn(B, Cout, H, W, generator=g).to(torch.bfloat16).float() if use_res else None
     d = lambda t: None if t is None else t.to(cuda_dev)
     xd, wd, bd = d(x), d(w), d(b)
     ref = F.conv2d(xd, wd, bd, 1, 1)
@@ -77,7 +82,7 @@ def test_conv3x3_pair_sm100(cuda_dev, case):
         ref = ref + d(r)
     x8 = conv.to_c8(xd)
     r8 = conv.to_c8(d(r)) if use_res else None
-    assert cdfo_b200._lib.lib().cdfo_conv3x3_pair_sm100_supported(64, Cin) == 1
+    assert cdfo_b200._lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin) == 1
     try:
         cdfo_b200.config.conv_pair = True
         y_pair = conv.from_c8(conv.conv3x3(x8, wd, bd, act, r8))

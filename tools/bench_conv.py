@@ -8,6 +8,9 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cdfo_b200 import conv  # noqa: E402
+import cdfo_b200  # noqa: E402
+
+cdfo_b200_lib = cdfo_b200._lib.lib()
 
 
 def timeit(fn, iters=10, warmup=3):
@@ -35,8 +38,7 @@ def main():
         x8 = conv.to_c8(x)
         t_ours = timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU))
         t_single = None
-        if Cout == 64 and Cin >= 128:      # A/B: the single-SM kernel with streamed weights
-            import cdfo_b200
+        if cdfo_b200_lib.cdfo_conv3x3_pair_sm100_supported(Cout, Cin):      # A/B: the single-SM kernel
             cdfo_b200.config.conv_pair = False
             t_single = timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU))
             cdfo_b200.config.conv_pair = True
