@@ -34,8 +34,8 @@ METRIC = "HR frames/sec, 1080p x4 LD-QP37"
 UNIT = "frames/s"
 LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
 ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
-# dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture (profiles/r01_dcn_tex_ncu.md), per LR pixel
-NCU_TRAFFIC_BYTES_PER_PX = (1.004433e9 + 72.121e6) / (6 * 272 * 480)
+# dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture (profiles/r01_dcn_tex_tma_fields_ncu.md), per LR pixel
+NCU_TRAFFIC_BYTES_PER_PX = (1.005385e9 + 95.661e6) / (6 * 272 * 480)
 
 
 def peaks():
@@ -267,9 +267,10 @@ def run_ours(args):
             "peak_source": peak_src, "avg_launch_us": avg * 1e6, "launches_timed": len(durs),
             "algorithmic_bytes_per_launch": per_px * px,
             "note": "algorithmic bytes = SURVEY 8d's 1120 B per LR pixel and neighbour call (x 128 + offset 576 + mask 288 + y 128) x "
-                    "%d px per launch; this build moves 1536 B/px (fp16 x 128, packed fp16x4 fields 1152, fp32 y 256); traffic = "
-                    "dram bytes per px of the ncu --set full capture in profiles/ scaled to this launch; the binding resource is "
-                    "the L1TEX data stage, see DESIGN.md" % px,
+                    "%d px per launch; this build moves 1408 B/px (fp16 x 128, packed fp16x4 fields 1152 staged by TMA, bf16 y 128 "
+                    "written straight into tsa_fusion's stacked input); traffic = dram bytes per px of the ncu --set full capture "
+                    "(profiles/r01_dcn_tex_tma_fields_ncu.md) scaled to this launch; the binding resource is the L1TEX data stage "
+                    "(texture wavefronts alone put the floor at frac 0.68), see DESIGN.md 3.1" % px,
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -286,7 +287,7 @@ def run_ours(args):
                                    "steady state (cached L1_fea), %d sequences per GPU per step" % (args.variant, args.priors, S),
                        "lr": [H, W], "seqs_per_gpu": S, "parallelism": "sequence-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (per step > 1 GB of offsets/masks/activations; %d rotating windows)" % len(pool),
-                       "stages": "alignment / attention / fusion / trunk / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16"},
+                       "stages": "alignment / attention / fusion / trunk (CTA-pair tcgen05 convs) / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16 + own LayerNorm / depthwise kernels"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
