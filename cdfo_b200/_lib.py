@@ -39,6 +39,7 @@ def lib():
         _lib.cdfo_mdta_workspace_bytes.restype = ctypes.c_size_t
         _lib.cdfo_psnr_ssim_workspace_bytes.restype = ctypes.c_size_t
         _lib.cdfo_conv3x3_pair_sm100_weight_bytes.restype = ctypes.c_size_t
+        _lib.cdfo_conv4x4s2_pair_sm100_weight_bytes.restype = ctypes.c_size_t
     return _lib
 
 

@@ -13,3 +13,7 @@ dcn_gather = "tex"
 # 3x3 convolutions with >= 128 input and 64 output channels (the trunk's 256 -> 64): True = the two-SM kernel (CTA pair,
 # tcgen05.mma cta_group::2, weights resident, cdfo_conv3x3_pair_sm100_fwd); False = the single-SM kernel that streams the weights.
 conv_pair = os.environ.get("CDFO_CONV_PAIR", "1") != "0"
+
+# Block_'s down(body(up(x))) branch: True = its last 3x3 convolution and the bilinear x0.5 that follows run as one 4x4 / stride-2
+# convolution at the output resolution (cdfo_conv4x4s2_pair_sm100_fwd, 2.25x fewer FLOPs); False = conv at 2x + resample kernel.
+conv_fold_half = os.environ.get("CDFO_CONV_FOLD_HALF", "1") != "0"

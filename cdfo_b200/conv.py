@@ -69,6 +69,37 @@ def pack_weight_pair(weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_wcache_4x4 = {}
+
+
+@torch.no_grad()
+def conv3x3_then_half(x8, weight, bias=None, resid8=None):
+    """bilinear_x0.5(conv3x3(x8, weight) + bias) + resid8 as ONE 4x4 / stride-2 convolution on a CTA pair (cdfo_conv4x4s2_pair_sm100_fwd).
+    x8 [B, Cin/8, 2H, 2W, 8] bf16, weight [64, Cin, 3, 3] -> [B, 8, H, W, 8] bf16; resid8 at the output size."""
+    B, C8, Hi, Wi, _ = x8.shape
+    Cout, Cin = weight.shape[:2]
+    if C8 * 8 != Cin or tuple(weight.shape[2:]) != (3, 3) or not _lib.lib().cdfo_conv4x4s2_pair_sm100_supported(Cout, Cin) or Hi % 2 or Wi % 2:
+        raise _lib.CdfoError("conv3x3_then_half: unsupported shape %s on %s" % (tuple(weight.shape), tuple(x8.shape)))
+    if x8.dtype != torch.bfloat16 or not x8.is_contiguous():
+        raise _lib.CdfoError("conv3x3_then_half: input must be a contiguous bf16 c8 tensor")
+    key = id(weight)
+    hit = _wcache_4x4.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        wpk = hit[2]
+    else:
+        w = weight.detach().contiguous().float()
+        wpk = torch.empty(_lib.lib().cdfo_conv4x4s2_pair_sm100_weight_bytes(Cin) // 2, dtype=torch.bfloat16, device=w.device)
+        _lib.call("cdfo_conv4x4s2_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(wpk), Cin, _lib.stream_ptr(w.device))
+        _wcache_4x4[key] = (weakref.ref(weight), weight._version, wpk)
+    y = torch.empty((B, Cout // 8, Hi // 2, Wi // 2, 8), dtype=torch.bfloat16, device=x8.device)
+    if resid8 is not None and (tuple(resid8.shape) != tuple(y.shape) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
+        raise _lib.CdfoError("conv3x3_then_half: residual must be a contiguous bf16 c8 tensor of the output shape")
+    b = None if bias is None else bias.detach().contiguous().float()
+    _lib.call("cdfo_conv4x4s2_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y), B, Cin, Hi, Wi,
+              _lib.stream_ptr(x8.device))
+    return y
+
+
 _derived = {}
 
 
@@ -151,7 +182,16 @@ def conv_last_skip(x8, weight, bias, lr):
 
 @torch.no_grad()
 def resample(a, mode, b=None, base=None):
-    """c8 bf16 bilinear resampling (align_corners=False): mode 0 = x0.5 of a, 1 = x2 of a, 2 = base + x0.5(a) + x2(b)."""
+    """c8 bf16 bilinear resampling (align_corners=False): mode 0 = x0.5 of a, 1 = x2 of a, 2 = base + x0.5(a) + x2(b),
+    3 = base + x2(b) (a is ignored)."""
+    if mode == 3:
+        B, C8, Ho, Wo, _ = base.shape
+        if tuple(b.shape) != (B, C8, Ho // 2, Wo // 2, 8) or Ho % 2 or Wo % 2 or not base.is_contiguous() or not b.is_contiguous() \
+                or base.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+            raise _lib.CdfoError("resample: base / b shapes do not match")
+        y = torch.empty_like(base)
+        _lib.call("cdfo_resample_c8", _lib.ptr(None), _lib.ptr(b), _lib.ptr(base), _lib.ptr(y), B, C8 * 8, Ho, Wo, 3, _lib.stream_ptr(base.device))
+        return y
     B, C8, Ha, Wa, _ = a.shape
     Ho, Wo = (Ha // 2, Wa // 2) if mode in (0, 2) else (2 * Ha, 2 * Wa)
     if a.dtype != torch.bfloat16 or not a.is_contiguous() or (mode != 1 and (Ha % 2 or Wa % 2)):

@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include "cdfo_common.cuh"
+#include "sm100_pair.cuh"
 #include "sm100_ptx.cuh"
 
 namespace cdfo {
@@ -29,7 +30,6 @@ constexpr int kChunks = 8;                        // 64 channels per pipeline st
 constexpr int kABytes = kChunks * kPlane;         // 23 040
 constexpr int kStages = 3;
 constexpr int kThreads = 320, kEpiWarps = 8;
-constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA of the pair
 
 struct Params {
   const uint8_t *wpk;   // [2 halves][9 taps][Cin/8][NH][8] bf16
@@ -40,66 +40,7 @@ struct Params {
   int tiles_x, tiles_y, m_tiles;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// every thread of both CTAs; the warps are reconverged first and the non-.aligned forms are used, because the role branches
-// above (one elected lane per producer / issuer warp) may leave a warp diverged when it gets here
-__device__ __forceinline__ void cluster_sync_all() {
-  __syncwarp();
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem, 256 x N over the pair] (+)= A[smem of each CTA: its 128 rows] * B[smem: N/2 rows per CTA]^T; issued by ONE thread of the leader
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
-      : "memory");
-}
-// arrive (count 1) on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  const uint16_t mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-// this CTA's halo box -> its own shared memory; the transaction bytes are credited to the LEADER's barrier
-__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst_smem, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
-          "r"(dst_smem),
-      "l"(tmap), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t *>(&v);
-}
+using namespace pairptx;
 
 // NH = output channels whose weights one CTA holds (N = 2 NH over the pair)
 template <int NH>

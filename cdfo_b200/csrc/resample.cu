@@ -57,7 +57,7 @@ __device__ __forceinline__ void up2_acc(F8 &acc, const uint4 *plane, int h, int 
 }
 
 // mode 0: y[Ho,Wo] = avg2(a[2Ho,2Wo]);  mode 1: y[Ho,Wo] = up2(a[Ho/2,Wo/2]);
-// mode 2: y[Ho,Wo] = base[Ho,Wo] + avg2(a[2Ho,2Wo]) + up2(b[Ho/2,Wo/2])        (planes = B * C/8)
+// mode 2: y[Ho,Wo] = base[Ho,Wo] + avg2(a[2Ho,2Wo]) + up2(b[Ho/2,Wo/2]);  mode 3: y = base + up2(b)   (planes = B * C/8)
 __global__ void resample_c8_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, const uint4 *__restrict__ base,
                                    uint4 *__restrict__ y, int Ho, int Wo, int mode) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,9 +71,12 @@ __global__ void resample_c8_kernel(const uint4 *__restrict__ a, const uint4 *__r
     avg2_acc(acc, a + (size_t)plane * 4 * Ho * Wo, h, w, 2 * Wo);
   } else if (mode == 1) {
     up2_acc(acc, a + (size_t)plane * (Ho / 2) * (Wo / 2), h, w, Ho / 2, Wo / 2);
-  } else {
+  } else if (mode == 2) {
     axpy(acc, 1.f, __ldg(base + (size_t)plane * Ho * Wo + pix));
     avg2_acc(acc, a + (size_t)plane * 4 * Ho * Wo, h, w, 2 * Wo);
+    up2_acc(acc, b + (size_t)plane * (Ho / 2) * (Wo / 2), h, w, Ho / 2, Wo / 2);
+  } else {
+    axpy(acc, 1.f, __ldg(base + (size_t)plane * Ho * Wo + pix));
     up2_acc(acc, b + (size_t)plane * (Ho / 2) * (Wo / 2), h, w, Ho / 2, Wo / 2);
   }
   y[(size_t)plane * Ho * Wo + pix] = pack(acc);
@@ -85,12 +88,12 @@ __global__ void resample_c8_kernel(const uint4 *__restrict__ a, const uint4 *__r
 using namespace cdfo;
 
 // mode 0: a [B,C/8,2Ho,2Wo,8] -> y [B,C/8,Ho,Wo,8] (bilinear x0.5); mode 1: a [B,C/8,Ho/2,Wo/2,8] -> y (bilinear x2);
-// mode 2: y = base [Ho,Wo] + x0.5(a [2Ho,2Wo]) + x2(b [Ho/2,Wo/2]).  Ho, Wo even.
+// mode 2: y = base [Ho,Wo] + x0.5(a [2Ho,2Wo]) + x2(b [Ho/2,Wo/2]);  mode 3: y = base + x2(b) (a unused).  Ho, Wo even.
 extern "C" int cdfo_resample_c8(const void *a, const void *b, const void *base, void *y, int B, int C, int Ho, int Wo, int mode,
                                 void *stream) {
-  CDFO_REQUIRE(a && y && (mode != 2 || (b && base)), CDFO_ERR_NULL, "cdfo_resample_c8: NULL pointer");
+  CDFO_REQUIRE(y && (mode == 3 || a) && (mode < 2 || (b && base)), CDFO_ERR_NULL, "cdfo_resample_c8: NULL pointer");
   CDFO_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && Ho > 0 && Wo > 0 && (long long)B * (C / 8) <= 65535, CDFO_ERR_SHAPE, "cdfo_resample_c8: bad shape");
-  CDFO_REQUIRE(mode >= 0 && mode <= 2, CDFO_ERR_UNSUPPORTED, "cdfo_resample_c8: mode %d", mode);
+  CDFO_REQUIRE(mode >= 0 && mode <= 3, CDFO_ERR_UNSUPPORTED, "cdfo_resample_c8: mode %d", mode);
   CDFO_REQUIRE(mode == 0 || (Ho % 2 == 0 && Wo % 2 == 0), CDFO_ERR_SHAPE, "cdfo_resample_c8: x2 output size must be even");
   dim3 grid(ceil_div(Ho * Wo, 256), B * (C / 8));
   rs::resample_c8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (const uint4 *)base, (uint4 *)y, Ho, Wo, mode);

@@ -99,6 +99,43 @@ def test_conv3x3_pair_sm100(cuda_dev, case):
     assert (y_pair - y_single).abs().max().item() <= 8e-3 * scale
 
 
+@pytest.mark.parametrize("case", [(1, 256, 32, 16, False), (2, 256, 66, 42, True), (1, 64, 34, 18, True), (3, 256, 136, 240, True),
+                                  (1, 256, 544, 960, False)])
+def test_conv3x3_then_half_as_4x4_stride2(cuda_dev, case):
+    """bilinear x0.5 (align_corners=False: 2x2 mean) of a 3x3 convolution as one 4x4 / stride-2 convolution on a CTA pair, against
+    the torch composition F.interpolate(F.conv2d(...), scale_factor=0.5) on bf16-rounded operands (arch:324-333, :401-406)."""
+    from cdfo_b200 import conv
+    B, Cin, Hi, Wi, use_res = case
+    g = torch.Generator().manual_seed(sum(case))
+    d = lambda t: None if t is None else t.to(cuda_dev)
+    x = d(torch.randn(B, Cin, Hi, Wi, generator=g).to(torch.bfloat16).float())
+    w = d((torch.randn(64, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float())
+    w[40:] *= 3.0
+    b = d(torch.randn(64, generator=g) * 0.1)
+    r = d(torch.randn(B, 64, Hi // 2, Wi // 2, generator=g).to(torch.bfloat16).float()) if use_res else None
+    ref = F.interpolate(F.conv2d(x, w, b, 1, 1), scale_factor=0.5, mode="bilinear", align_corners=False)
+    if use_res:
+        ref = ref + r
+    x8 = conv.to_c8(x)
+    y = conv.from_c8(conv.conv3x3_then_half(x8, w, b, conv.to_c8(r) if use_res else None))
+    y2 = conv.from_c8(conv.conv3x3_then_half(x8, w, b, conv.to_c8(r) if use_res else None))
+    scale = max(1.0, ref.abs().max().item())
+    err = (y - ref).abs().max().item()
+    print("conv4x4s2 %s: max err %.3g (max|ref| %.3g)" % (case, err, scale))
+    assert torch.equal(y, y2)
+    assert err <= 1.2e-2 * scale          # bf16 rounding of the output and of the folded weights (sums of up to four bf16 values / 4)
+
+
+def test_resample_mode3(cuda_dev):
+    from cdfo_b200 import conv
+    g = torch.Generator().manual_seed(2)
+    base = torch.randn(2, 64, 24, 40, generator=g).to(torch.bfloat16).float().to(cuda_dev)
+    low = torch.randn(2, 64, 12, 20, generator=g).to(torch.bfloat16).float().to(cuda_dev)
+    ref = base + F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)
+    y = conv.from_c8(conv.resample(None, 3, b=conv.to_c8(low), base=conv.to_c8(base)))
+    assert (y - ref).abs().max().item() <= 1.2e-2 * ref.abs().max().item()
+
+
 def test_pixel_shuffle_epilogue_and_conv_last_skip(cuda_dev):
     """upconv (1x1 as a centre-tap 3x3) + PixelShuffle(2) + lrelu in the conv epilogue, and conv_last + bilinear x4 skip,
     against the plain torch composition of arch/SIDECVSR_our.py:4473-4480 on bf16-rounded operands."""
