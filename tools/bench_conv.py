@@ -50,6 +50,18 @@ def main():
         out.append({"shape": [B, Cin, Cout, h, w], "ours_us": round(t_ours, 1), "ours_TFLOPs": round(flops / t_ours / 1e6, 1),
                     "single_sm_TFLOPs": None if t_single is None else round(flops / t_single / 1e6, 1),
                     "cudnn_bf16_us": round(t_cudnn, 1), "cudnn_TFLOPs": round(flops / t_cudnn / 1e6, 1)})
+    # the folded "3x3 at 2x + bilinear x0.5" (4x4 stride 2 on a CTA pair) against its two-kernel form
+    for B in (2, 4):
+        x = torch.randn(B, 256, 2 * H, 2 * W, device=dev)
+        wt = torch.randn(64, 256, 3, 3, device=dev) * 0.05
+        b = torch.randn(64, device=dev)
+        x8 = conv.to_c8(x)
+        base = conv.to_c8(torch.randn(B, 64, H, W, device=dev))
+        t_fold = timeit(lambda: conv.conv3x3_then_half(x8, wt, b, base))
+        t_two = timeit(lambda: conv.resample(conv.conv3x3(x8, wt, b, conv.ACT_NONE), 0))
+        flops = 2.0 * B * H * W * 256 * 64 * 16
+        out.append({"shape": [B, 256, 64, 2 * H, 2 * W], "folded_4x4s2_us": round(t_fold, 1), "folded_TFLOPs": round(flops / t_fold / 1e6, 1),
+                    "conv3x3_plus_resample_us": round(t_two, 1)})
     for o in out:
         print(json.dumps(o))
 
