@@ -3,7 +3,7 @@ import collections
 import csv
 import sys
 
-OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::")
+OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::", "cpair::", "c4::")
 
 
 def main(src, dst, title, note):
