@@ -17,3 +17,9 @@ conv_pair = os.environ.get("CDFO_CONV_PAIR", "1") != "0"
 # Block_'s down(body(up(x))) branch: True = its last 3x3 convolution and the bilinear x0.5 that follows run as one 4x4 / stride-2
 # convolution at the output resolution (cdfo_conv4x4s2_pair_sm100_fwd, 2.25x fewer FLOPs); False = conv at 2x + resample kernel.
 conv_fold_half = os.environ.get("CDFO_CONV_FOLD_HALF", "1") != "0"
+
+# With conv_fold_half: True = the 2x-resolution intermediate of that branch is written by the 64 -> 256 convolution as its four parity
+# planes ([B, C/8, 2, 2, H, W, 8]), so every stride-2 phase window of the folded convolution is a dense TMA box; False = plain c8,
+# loaded with elementStrides = 2.  Measured (tools/bench_conv.py): no gain for the folded convolution once its streamed weights arrive
+# as 512-byte TMA rows (212 us either way at 2 x 544x960), and the producer's scattered stores cost 5 % -- kept as an option, off.
+conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "0") != "0"

@@ -75,8 +75,16 @@ _wcache_4x4 = {}
 @torch.no_grad()
 def conv3x3_then_half(x8, weight, bias=None, resid8=None):
     """bilinear_x0.5(conv3x3(x8, weight) + bias) + resid8 as ONE 4x4 / stride-2 convolution on a CTA pair (cdfo_conv4x4s2_pair_sm100_fwd).
-    x8 [B, Cin/8, 2H, 2W, 8] bf16, weight [64, Cin, 3, 3] -> [B, 8, H, W, 8] bf16; resid8 at the output size."""
-    B, C8, Hi, Wi, _ = x8.shape
+    x8 [B, Cin/8, 2H, 2W, 8] bf16 -- or its parity planes [B, Cin/8, 2, 2, H, W, 8] as conv3x3(..., parity_planes=True) writes them
+    (dense TMA boxes instead of stride-2 loads) -- weight [64, Cin, 3, 3] -> [B, 8, H, W, 8] bf16; resid8 at the output size."""
+    planes = x8.dim() == 7
+    if planes:
+        B, C8, _, _, Ho, Wo, _ = x8.shape
+        Hi, Wi = 2 * Ho, 2 * Wo
+        if tuple(x8.shape[2:4]) != (2, 2):
+            raise _lib.CdfoError("conv3x3_then_half: parity planes must be [B, Cin/8, 2, 2, H, W, 8]")
+    else:
+        B, C8, Hi, Wi, _ = x8.shape
     Cout, Cin = weight.shape[:2]
     if C8 * 8 != Cin or tuple(weight.shape[2:]) != (3, 3) or not _lib.lib().cdfo_conv4x4s2_pair_sm100_supported(Cout, Cin) or Hi % 2 or Wi % 2:
         raise _lib.CdfoError("conv3x3_then_half: unsupported shape %s on %s" % (tuple(weight.shape), tuple(x8.shape)))
@@ -95,8 +103,8 @@ def conv3x3_then_half(x8, weight, bias=None, resid8=None):
     if resid8 is not None and (tuple(resid8.shape) != tuple(y.shape) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
         raise _lib.CdfoError("conv3x3_then_half: residual must be a contiguous bf16 c8 tensor of the output shape")
     b = None if bias is None else bias.detach().contiguous().float()
-    _lib.call("cdfo_conv4x4s2_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y), B, Cin, Hi, Wi,
-              _lib.stream_ptr(x8.device))
+    _lib.call("cdfo_conv4x4s2_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y), B, Cin, Hi, Wi,
+              1 if planes else 0, _lib.stream_ptr(x8.device))
     return y
 
 
@@ -132,10 +140,11 @@ def ps_order(t):
 
 
 @torch.no_grad()
-def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False):
+def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False, parity_planes=False):
     """Convolution with a [Cout, Cin, k, k] weight, k = 1 or 3, stride 1, "same" padding, on the tcgen05 kernel.
     x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw, or
-    [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) when pixel_shuffle and the weight rows are in ps_order)."""
+    [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) when pixel_shuffle and the weight rows are in ps_order, or the four parity
+    planes [B, Cout/8, 2, 2, H/2, W/2, 8] when parity_planes: CTA-pair shapes only, the input layout of conv3x3_then_half)."""
     B, C8, H, W, _ = x8.shape
     Cout, Cin, ks = weight.shape[:3]
     if C8 * 8 != Cin or ks not in (1, 3) or weight.shape[3] != ks:
@@ -145,8 +154,15 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
     b = None if bias is None else bias.detach().contiguous().float()
     if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
         raise _lib.CdfoError("conv3x3: residual must be a contiguous bf16 c8 tensor of the output shape")
-    if (config.conv_pair and ks == 3 and not pixel_shuffle and not out_nchw
-            and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)):
+    pair_ok = ks == 3 and not pixel_shuffle and not out_nchw and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)
+    if parity_planes:
+        if not pair_ok or resid8 is not None or H % 2 or W % 2:
+            raise _lib.CdfoError("conv3x3: parity_planes needs a CTA-pair shape (3x3, %d -> %d), an even size and no residual" % (Cin, Cout))
+        y = torch.empty((B, Cout // 8, 2, 2, H // 2, W // 2, 8), dtype=torch.bfloat16, device=x8.device)
+        _lib.call("cdfo_conv3x3_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(None),
+                  _lib.ptr(y), B, Cin, Cout, H, W, int(act), 1, _lib.stream_ptr(x8.device))
+        return y
+    if config.conv_pair and pair_ok:
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
         _lib.call("cdfo_conv3x3_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(resid8),
                   _lib.ptr(y), B, Cin, Cout, H, W, int(act), _lib.stream_ptr(x8.device))

@@ -15,6 +15,7 @@
 // full barrier), warp 1 of the leader = MMA issuer (commits are multicast to both CTAs' barriers), warps 2..9 = epilogue of the
 // CTA's own 128 pixels (bias -> act -> +residual -> c8 bf16), accumulator double-buffered in TMEM (2 x 64 columns per CTA).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cdfo_common.cuh"
 #include "sm100_pair.cuh"
@@ -38,6 +39,9 @@ struct Params {
   uint4 *y;             // c8 bf16 [B][2 NH / 8][H][W][8]
   int B, Cin, H, W, act;
   int tiles_x, tiles_y, m_tiles;
+  int tma_wide;         // 1: the tensor map merges the pixel and channel axes (a halo row = 80 contiguous elements = one 160-byte request)
+  int y_planes;         // 1: y is stored as its four parity planes [B][2 NH / 8][row parity][column parity][H/2][W/2][8] (H, W even) --
+                        // the layout from which the 4x4 / stride-2 convolution (conv4x4s2_pair_sm100.cu) loads dense TMA boxes
 };
 
 using namespace pairptx;
@@ -113,7 +117,8 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
           if (leader) ptx::mbar_arrive_expect_tx(BAR(stage), 2 * kABytes);
-          tma_load_5d_pair(ptx::smem_u32(asmem) + stage * kABytes, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * kChunks, b);
+          if (p.tma_wide) tma_load_5d_pair(ptx::smem_u32(asmem) + stage * kABytes, &tmap, BAR(stage), (w0 - 1) * 8, h0 - 1, kb * kChunks, b, 0);
+          else tma_load_5d_pair(ptx::smem_u32(asmem) + stage * kABytes, &tmap, BAR(stage), 0, w0 - 1, h0 - 1, kb * kChunks, b);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,6 +189,8 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       const int h = (r / p.tiles_x) * kTileH + ty, w = (r % p.tiles_x) * kTileW + tx;
       const bool live = valid && h < p.H && w < p.W;
       const size_t pix = (size_t)h * p.W + w;
+      // parity planes: pixel (h, w) -> plane (h & 1, w & 1), position (h / 2, w / 2); a chunk still spans H * W pixels
+      const size_t opix = p.y_planes ? (size_t)((h & 1) * 2 + (w & 1)) * (HW >> 2) + (size_t)(h >> 1) * (p.W >> 1) + (w >> 1) : pix;
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
       // the two warps of a TMEM lane quarter take alternate 16-column chunks; 16 channels = two c8 chunks of 16 bytes per pixel
@@ -221,7 +228,7 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             }
           }
         }
-        uint4 *y = p.y + ((size_t)b * (kN / 8) + c0 / 8) * HW + pix;
+        uint4 *y = p.y + ((size_t)b * (kN / 8) + c0 / 8) * HW + opix;
         y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
         y[HW] = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
       }
@@ -305,9 +312,19 @@ extern "C" int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, in
   return conv3x3_pack_weight_raw(w, wpk, Cout, Cin, cpair::half_channels(Cout, Cin), 2, 0, 9, (cudaStream_t)stream);
 }
 
+extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
+                                                  int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream);
+
 extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B,
                                            int Cin, int Cout, int H, int W, int act, void *stream) {
+  return cdfo_conv3x3_pair_sm100_planes_fwd(x_c8, wpk, bias, resid_c8, y_c8, B, Cin, Cout, H, W, act, 0, stream);
+}
+
+extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
+                                                  int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv3x3_pair_sm100_fwd: NULL pointer");
+  CDFO_REQUIRE(y_planes == 0 || (y_planes == 1 && H % 2 == 0 && W % 2 == 0), CDFO_ERR_SHAPE,
+               "cdfo_conv3x3_pair_sm100_planes_fwd: the parity-plane output needs an even size (got %d x %d)", H, W);
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_pair_sm100_fwd: bad shape");
   CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(Cout, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: unsupported channels %d -> %d", Cin, Cout);
   CDFO_REQUIRE(act >= 0 && act <= 2, CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: act %d", act);
@@ -316,16 +333,24 @@ extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, co
   cpair::EncodeTiledFn enc = cpair::encode_tiled_fn();
   CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv3x3_pair_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tm;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)cpair::kHaloW, (cuuint32_t)cpair::kHaloH, 8, 1};
+  static const bool wide128 = getenv("CDFO_TMA_WIDE") == nullptr || getenv("CDFO_TMA_WIDE")[0] != '0';
+  static const bool wide32 = getenv("CDFO_TMA_WIDE32") == nullptr || getenv("CDFO_TMA_WIDE32")[0] != '0';
+  const bool wide = cpair::half_channels(Cout, Cin) == 128 ? wide128 : wide32;
+  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)cpair::kHaloW, (cuuint32_t)cpair::kHaloH, 8, 1};
+  if (wide) {   // same bytes, same landing order, one request per halo row instead of one per pixel chunk
+    gdim[0] = (cuuint64_t)W * 8; gdim[1] = H; gdim[2] = Cin / 8; gdim[3] = B; gdim[4] = 1;
+    gstr[0] = (cuuint64_t)W * 16; gstr[1] = (cuuint64_t)H * W * 16; gstr[2] = (cuuint64_t)(Cin / 8) * H * W * 16; gstr[3] = gstr[2] * B;
+    box[0] = 8 * cpair::kHaloW; box[1] = cpair::kHaloH; box[2] = 8; box[3] = 1; box[4] = 1;
+  }
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(x_c8), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
   cpair::Params p;
   p.wpk = (const uint8_t *)wpk; p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = (uint4 *)y_c8;
-  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.act = act;
+  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.act = act; p.y_planes = y_planes; p.tma_wide = wide ? 1 : 0;
   p.tiles_x = ceil_div(W, cpair::kTileW); p.tiles_y = ceil_div(H, cpair::kTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;
   CDFO_REQUIRE(mt < (1ll << 30), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: too many tiles");

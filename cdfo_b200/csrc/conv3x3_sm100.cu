@@ -17,6 +17,7 @@
 //     quarter, alternating column chunks)
 //     (tcgen05.ld -> +bias -> activation -> +residual -> bf16 c8 or fp32 NCHW); TMEM accumulator double buffered.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cdfo_common.cuh"
 #include "sm100_ptx.cuh"
@@ -40,6 +41,7 @@ struct Conv3x3Params {
   const uint4 *resid;   // c8 bf16 [B][Cout/8][H][W][8] or nullptr: added after the activation
   void *y;
   int B, Cin, Cout, H, W;
+  int tma_wide;  // 1: the tensor map merges the pixel and channel axes (one request per halo row instead of one per 16-byte pixel chunk)
   int act;       // 0 none, 1 relu, 2 leaky relu 0.1
   int out_mode;  // 0: NCHW fp32, 1: c8 bf16, 2: c8 bf16 through PixelShuffle(2): output channels arrive ordered
                  //    n' = (2i+j)*(Cout/4) + c and leave at [B][Cout/32][2H][2W][8], pixel (2h+i, 2w+j)
@@ -144,7 +146,8 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
           const uint32_t dst = ptx::smem_u32(asmem) + stage * stage_stride;
           ptx::mbar_arrive_expect_tx(BAR(stage), kABytes + (p.stream_w ? kTaps * kPiece : 0));
-          ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - KS / 2, h0 - KS / 2, kb * kChunks, b);
+          if (p.tma_wide) ptx::tma_load_5d(dst, &tmap, BAR(stage), (w0 - KS / 2) * 8, h0 - KS / 2, kb * kChunks, b, 0);
+          else ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - KS / 2, h0 - KS / 2, kb * kChunks, b);
           if (p.stream_w) {
             // streamed weights are packed [n_tile][K block][tap][chunk][NT][8]: one bulk copy per stage
             ptx::bulk_g2s(dst + kABytes, p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * kTaps * kPiece, kTaps * kPiece, BAR(stage));
@@ -536,9 +539,15 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   EncodeTiledFn enc = encode_tiled_fn();
   CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv3x3_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tm;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)(kCvTileW + ksize - 1), (cuuint32_t)(kCvTileH + ksize - 1), 8, 1};
+  static const bool wide = getenv("CDFO_TMA_WIDE1") == nullptr || getenv("CDFO_TMA_WIDE1")[0] != '0';
+  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)(kCvTileW + ksize - 1), (cuuint32_t)(kCvTileH + ksize - 1), 8, 1};
+  if (wide) {   // same bytes, same landing order; TMA issues one request per halo row (up to 160 bytes) instead of one per 16-byte chunk
+    gdim[0] = (cuuint64_t)W * 8; gdim[1] = H; gdim[2] = Cin / 8; gdim[3] = B; gdim[4] = 1;
+    gstr[0] = (cuuint64_t)W * 16; gstr[1] = (cuuint64_t)H * W * 16; gstr[2] = (cuuint64_t)(Cin / 8) * H * W * 16; gstr[3] = gstr[2] * B;
+    box[0] = 8 * (kCvTileW + ksize - 1); box[1] = kCvTileH + ksize - 1; box[2] = 8; box[3] = 1; box[4] = 1;
+  }
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(x_c8), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -547,7 +556,7 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   Conv3x3Params p;
   p.wpk = (const uint8_t *)wpk; p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = y;
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.act = act; p.out_mode = out_mode;
-  p.epi = epi; p.mag = mag; p.aux = (const uint2 *)aux;
+  p.epi = epi; p.mag = mag; p.aux = (const uint2 *)aux; p.tma_wide = wide ? 1 : 0;
   p.n_tiles = ceil_div(Cout, nt);
   p.stream_w = conv3x3_streams(Cout, Cin, taps) ? 1 : 0;
   p.tiles_x = ceil_div(W, kCvTileW); p.tiles_y = ceil_div(H, kCvTileH);

@@ -48,6 +48,9 @@ struct Params {
   uint4 *y;             // c8 bf16 [B][8][H][W][8]
   int B, Cin, H, W;     // H, W = OUTPUT size (input is 2H x 2W)
   int tiles_x, tiles_y, m_tiles;
+  int x_planes;         // 1: x is stored as parity planes [B][Cin/8][2][2][H][W][8] (what cdfo_conv3x3_pair_sm100_planes_fwd writes):
+                        // every phase window is a DENSE box.  0: plain c8, loaded with elementStrides = 2 -- each 16-byte pixel chunk
+                        // is then a separate L2 request that drags a 32-byte sector, the kernel's bottleneck in that mode.
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -112,9 +115,14 @@ conv4x4s2_pair_sm100_kernel(const __grid_constant__ CUtensorMap xmap, const __gr
           if (leader) ptx::mbar_arrive_expect_tx(BAR(stage), 2 * kTxBytes);
           const uint32_t dst = stage0 + stage * kStageBytes;
 #pragma unroll
-          for (int ph = 0; ph < 4; ++ph)     // phase (a, b) = (ph >> 1, ph & 1): input rows 2 h0 - a + 2 r, columns 2 w0 - b + 2 c
-            tma_load_5d_pair(dst + ph * kPhaseStride, &xmap, BAR(stage), 0, 2 * w0 - (ph & 1), 2 * h0 - (ph >> 1), kb * kChunks, b);
-          tma_load_3d_pair(dst + kAStage, &wmap, BAR(stage), 0, 0, ((int)rank * KB + kb) * 8);
+          for (int ph = 0; ph < 4; ++ph) {   // phase (a, b) = (ph >> 1, ph & 1): input rows 2 h0 - a + 2 r, columns 2 w0 - b + 2 c
+            if (p.x_planes)                  // = rows h0 - a + r of the plane of parity a (odd rows start one plane row earlier);
+                                             // innermost dimension = a whole window row (9 pixels x 8 channels = 144 contiguous bytes)
+              tma_load_5d_pair(dst + ph * kPhaseStride, &xmap, BAR(stage), (w0 - (ph & 1)) * 8, h0 - (ph >> 1), ph, b * (p.Cin / 8) + kb * kChunks, 0);
+            else
+              tma_load_5d_pair(dst + ph * kPhaseStride, &xmap, BAR(stage), 0, 2 * w0 - (ph & 1), 2 * h0 - (ph >> 1), kb * kChunks, b);
+          }
+          tma_load_3d_pair(dst + kAStage, &wmap, BAR(stage), 0, 0, (int)rank * KB + kb);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -284,9 +292,18 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_pack_weight(const float *w3, void *wpk,
   return check_launch("cdfo_conv4x4s2_pair_sm100_pack_weight");
 }
 
+extern "C" int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
+                                                    int B, int Cin, int H_in, int W_in, int x_planes, void *stream);
+
 extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B,
                                              int Cin, int H_in, int W_in, void *stream) {
+  return cdfo_conv4x4s2_pair_sm100_planes_fwd(x_c8, wpk, bias, resid_c8, y_c8, B, Cin, H_in, W_in, 0, stream);
+}
+
+extern "C" int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
+                                                    int B, int Cin, int H_in, int W_in, int x_planes, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv4x4s2_pair_sm100_fwd: NULL pointer");
+  CDFO_REQUIRE(x_planes == 0 || x_planes == 1, CDFO_ERR_UNSUPPORTED, "cdfo_conv4x4s2_pair_sm100_planes_fwd: x_planes %d", x_planes);
   CDFO_REQUIRE(B > 0 && H_in > 0 && W_in > 0 && H_in % 2 == 0 && W_in % 2 == 0, CDFO_ERR_SHAPE,
                "cdfo_conv4x4s2_pair_sm100_fwd: the input size must be even (got %d x %d)", H_in, W_in);
   CDFO_REQUIRE(cdfo_conv4x4s2_pair_sm100_supported(64, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv4x4s2_pair_sm100_fwd: unsupported input channels %d", Cin);
@@ -295,7 +312,20 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, 
   c4::EncodeTiledFn enc = c4::encode_tiled_fn();
   CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv4x4s2_pair_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap xm, wm;
-  {
+  if (x_planes) {
+    // [B * Cin/8][4 planes][H][W][8]: a box of 4 channel chunks starts at a multiple of 4 and never crosses a sample
+    const cuuint64_t Ho = H_in / 2, Wo = W_in / 2;
+    CDFO_REQUIRE((long long)B * (Cin / 8) < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_conv4x4s2_pair_sm100_planes_fwd: too many chunks");
+    // the pixel and channel axes are merged (a window row of 9 pixels = 72 contiguous elements): 17 x 4 requests of 144 bytes per
+    // box instead of 9 x 17 x 4 of 16 bytes
+    const cuuint64_t gdim[5] = {Wo * 8, Ho, 4, (cuuint64_t)B * (Cin / 8), 1};
+    const cuuint64_t gstr[4] = {Wo * 16, Ho * Wo * 16, 4 * Ho * Wo * 16, (cuuint64_t)B * (Cin / 8) * 4 * Ho * Wo * 16};
+    const cuuint32_t box[5] = {8 * c4::kPW, c4::kPH, 1, c4::kChunks, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(x_c8), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled(x, parity planes) failed with CUresult %d", (int)cr);
+  } else {
     const cuuint64_t gdim[5] = {8, (cuuint64_t)W_in, (cuuint64_t)H_in, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
     const cuuint64_t gstr[4] = {16, (cuuint64_t)W_in * 16, (cuuint64_t)H_in * W_in * 16, (cuuint64_t)(Cin / 8) * H_in * W_in * 16};
     const cuuint32_t box[5] = {8, 2 * c4::kPW, 2 * c4::kPH, c4::kChunks, 1};      // traversed with stride 2 -> 9 x 17 pixels landed
@@ -305,10 +335,10 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, 
     CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled(x, stride 2) failed with CUresult %d", (int)cr);
   }
   {
-    const cuuint64_t rows = (cuuint64_t)2 * (Cin / 32) * 8;      // blocks of 256 rows of 16 bytes: 8 per (half, K block)
-    const cuuint64_t gdim[3] = {8, 256, rows};
-    const cuuint64_t gstr[2] = {16, 4096};
-    const cuuint32_t box[3] = {8, 256, 8};
+    // one (half, K block) = 32 KB contiguous = 64 rows of 256 elements (512-byte requests)
+    const cuuint64_t gdim[3] = {256, 64, (cuuint64_t)2 * (Cin / 32)};
+    const cuuint64_t gstr[2] = {512, 32768};
+    const cuuint32_t box[3] = {256, 64, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = enc(&wm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(wpk), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -316,7 +346,7 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, 
   }
   c4::Params p;
   p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = (uint4 *)y_c8;
-  p.B = B; p.Cin = Cin; p.H = H_in / 2; p.W = W_in / 2;
+  p.B = B; p.Cin = Cin; p.H = H_in / 2; p.W = W_in / 2; p.x_planes = x_planes;
   p.tiles_x = ceil_div(p.W, c4::kTileW); p.tiles_y = ceil_div(p.H, c4::kTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;
   CDFO_REQUIRE(mt < (1ll << 30), CDFO_ERR_UNSUPPORTED, "cdfo_conv4x4s2_pair_sm100_fwd: too many tiles");

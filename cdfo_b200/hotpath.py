@@ -302,11 +302,13 @@ def cross_scale_block(blk, x8):
     xd = conv.conv3x3(conv.resample(x8, 0), dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
     cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
     xu = conv.resample(conv.conv3x3(x8, up.weight, up.bias, conv.ACT_NONE), 1)               # 1x1
-    t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU)
     if config.conv_fold_half:
+        # the 2x-resolution intermediate lives as its four parity planes: the stride-2 taps of the folded convolution are dense boxes
+        t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU, parity_planes=config.conv_parity_planes and config.conv_pair)
         # bilinear x0.5 of a 3x3 convolution = one 4x4 / stride-2 convolution: evaluated at 1x, the branch sum starts in its epilogue
         yb = conv.conv3x3_then_half(t2, wts["dn_body2"][0], wts["dn_body2"][1], resid8=y)
         return conv.resample(None, 3, b=cu, base=yb)
+    t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU)
     b3 = conv.conv3x3(t2, wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
     return conv.resample(b3, 2, b=cu, base=y)
 

@@ -124,6 +124,25 @@ def test_conv3x3_then_half_as_4x4_stride2(cuda_dev, case):
     print("conv4x4s2 %s: max err %.3g (max|ref| %.3g)" % (case, err, scale))
     assert torch.equal(y, y2)
     assert err <= 1.2e-2 * scale          # bf16 rounding of the output and of the folded weights (sums of up to four bf16 values / 4)
+    # the same input stored as its four parity planes (dense TMA boxes instead of stride-2 loads): bit-identical result
+    xp = x8.view(B, Cin // 8, Hi // 2, 2, Wi // 2, 2, 8).permute(0, 1, 3, 5, 2, 4, 6).contiguous()
+    y3 = conv.from_c8(conv.conv3x3_then_half(xp, w, b, conv.to_c8(r) if use_res else None))
+    assert torch.equal(y, y3)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(1, 64, 256, 32, 16), (2, 64, 256, 66, 42), (1, 256, 64, 34, 18), (1, 64, 256, 544, 960)])
+def test_conv3x3_pair_parity_plane_output(cuda_dev, B, Cin, Cout, H, W):
+    """The CTA-pair convolution writing its output as four parity planes [B, C/8, 2, 2, H/2, W/2, 8] (the layout the folded
+    4x4 / stride-2 convolution reads) = a permutation of its plain c8 output, bit for bit."""
+    from cdfo_b200 import conv
+    g = torch.Generator().manual_seed(B + Cin + H)
+    x8 = conv.to_c8(torch.randn(B, Cin, H, W, generator=g).to(cuda_dev))
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(cuda_dev)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(cuda_dev)
+    y = conv.conv3x3(x8, w, b, conv.ACT_LRELU)
+    yp = conv.conv3x3(x8, w, b, conv.ACT_LRELU, parity_planes=True)
+    assert tuple(yp.shape) == (B, Cout // 8, 2, 2, H // 2, W // 2, 8)
+    assert torch.equal(yp, y.view(B, Cout // 8, H // 2, 2, W // 2, 2, 8).permute(0, 1, 3, 5, 2, 4, 6).contiguous())
 
 
 def test_resample_mode3(cuda_dev):

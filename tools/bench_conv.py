@@ -58,10 +58,19 @@ def main():
         x8 = conv.to_c8(x)
         base = conv.to_c8(torch.randn(B, 64, H, W, device=dev))
         t_fold = timeit(lambda: conv.conv3x3_then_half(x8, wt, b, base))
+        xp = x8.view(B, 32, H, 2, W, 2, 8).permute(0, 1, 3, 5, 2, 4, 6).contiguous()
+        t_planes = timeit(lambda: conv.conv3x3_then_half(xp, wt, b, base))
         t_two = timeit(lambda: conv.resample(conv.conv3x3(x8, wt, b, conv.ACT_NONE), 0))
         flops = 2.0 * B * H * W * 256 * 64 * 16
         out.append({"shape": [B, 256, 64, 2 * H, 2 * W], "folded_4x4s2_us": round(t_fold, 1), "folded_TFLOPs": round(flops / t_fold / 1e6, 1),
+                    "folded_parity_planes_us": round(t_planes, 1), "folded_parity_planes_TFLOPs": round(flops / t_planes / 1e6, 1),
                     "conv3x3_plus_resample_us": round(t_two, 1)})
+    # 64 -> 256 at 2x writing plain c8 against parity planes
+    x8 = conv.to_c8(torch.randn(2, 64, 2 * H, 2 * W, device=dev))
+    wt = torch.randn(256, 64, 3, 3, device=dev) * 0.05
+    b = torch.randn(256, device=dev)
+    out.append({"shape": [2, 64, 256, 2 * H, 2 * W], "c8_out_us": round(timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU)), 1),
+                "parity_planes_out_us": round(timeit(lambda: conv.conv3x3(x8, wt, b, conv.ACT_LRELU, parity_planes=True)), 1)})
     for o in out:
         print(json.dumps(o))
 
