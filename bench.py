@@ -170,6 +170,11 @@ def run_ours(args):
         pool.append(host)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     noise = [torch.rand((S, 64, H, W), device=dev, generator=g).clamp_min_(1e-12) for _ in range(6)]
+    if not args.graph:
+        # eager steps: the window's L1 features live in a frame-major ring (model.FeatureRing: no per-frame copy of the 7-frame cache)
+        # and the six noise tensors are handed over as one neighbour-major batch
+        model.feature_ring = True
+        noise = torch.cat(noise, 0)
 
     def decode_mv(mv_dev, mv1_dev=None):
         if mv1_dev is not None:      # config c5: bidirectional decoding of the (l0, l1) pair (opt/data_RA_bi.py:496-533)

@@ -10,12 +10,17 @@ _wcache = {}
 
 
 @torch.no_grad()
-def to_c8(x: torch.Tensor) -> torch.Tensor:
-    """NCHW fp32 -> [B, C/8, H, W, 8] bf16."""
+def to_c8(x: torch.Tensor, out: torch.Tensor = None, channel0: int = 0) -> torch.Tensor:
+    """NCHW fp32 -> [B, C/8, H, W, 8] bf16; with `out` ([B, Cout/8, H, W, 8], contiguous) into its channels [channel0, channel0 + C)."""
     B, C, H, W = x.shape
     x = x.contiguous().float()
-    out = torch.empty((B, C // 8, H, W, 8), dtype=torch.bfloat16, device=x.device)
-    _lib.call("cdfo_pack_c8", _lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
+    if out is None:
+        out = torch.empty((B, C // 8, H, W, 8), dtype=torch.bfloat16, device=x.device)
+        _lib.call("cdfo_pack_c8", _lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.stream_ptr(x.device))
+        return out
+    if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.dim() != 5 or (out.size(0), out.size(2), out.size(3), out.size(4)) != (B, H, W, 8):
+        raise _lib.CdfoError("to_c8: out must be a contiguous bf16 c8 tensor of the same batch and size")
+    _lib.call("cdfo_pack_c8_into", _lib.ptr(x), _lib.ptr(out), B, C, H, W, out.size(1) * 8, int(channel0), _lib.stream_ptr(x.device))
     return out
 
 

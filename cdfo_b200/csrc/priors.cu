@@ -112,7 +112,9 @@ __global__ void flow_warp_kernel(const float *__restrict__ x, const float *__res
 }
 
 // ---------------------------------------------------------------- layout adapters
-__global__ void pack_c8_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int C, int HW) {
+// out has out_chunks 8-channel chunks per sample; the C / 8 chunks of x go to [chunk0, chunk0 + C / 8) (a channel concatenation
+// is then two packs into one tensor instead of a cat + pack)
+__global__ void pack_c8_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int C, int HW, int out_chunks, int chunk0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   const int c8 = blockIdx.y, b = blockIdx.z;
@@ -120,7 +122,7 @@ __global__ void pack_c8_kernel(const float *__restrict__ x, uint4 *__restrict__ 
   __nv_bfloat162 v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __floats2bfloat162_rn(src[(size_t)(2 * i) * HW], src[(size_t)(2 * i + 1) * HW]);
-  out[((size_t)b * (C / 8) + c8) * HW + p] = *reinterpret_cast<uint4 *>(v);
+  out[((size_t)b * out_chunks + chunk0 + c8) * HW + p] = *reinterpret_cast<uint4 *>(v);
 }
 
 __global__ void unpack_c8_kernel(const uint4 *__restrict__ in, float *__restrict__ y, int C, int HW) {
@@ -230,8 +232,18 @@ extern "C" int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H
   CDFO_REQUIRE(x_nchw && x_c8, CDFO_ERR_NULL, "cdfo_pack_c8: NULL pointer");
   CDFO_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_pack_c8: C %% 8 != 0 or bad shape");
   dim3 grid(ceil_div(H * W, 128), C / 8, B);
-  pack_c8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, (uint4 *)x_c8, C, H * W);
+  pack_c8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, (uint4 *)x_c8, C, H * W, C / 8, 0);
   return check_launch("cdfo_pack_c8");
+}
+
+extern "C" int cdfo_pack_c8_into(const float *x_nchw, void *x_c8, int B, int C, int H, int W, int out_channels, int channel0, void *stream) {
+  CDFO_REQUIRE(x_nchw && x_c8, CDFO_ERR_NULL, "cdfo_pack_c8_into: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_pack_c8_into: C %% 8 != 0 or bad shape");
+  CDFO_REQUIRE(out_channels % 8 == 0 && channel0 % 8 == 0 && channel0 >= 0 && channel0 + C <= out_channels, CDFO_ERR_SHAPE,
+               "cdfo_pack_c8_into: channels [%d, %d) do not fit %d output channels (multiples of 8)", channel0, channel0 + C, out_channels);
+  dim3 grid(ceil_div(H * W, 128), C / 8, B);
+  pack_c8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, (uint4 *)x_c8, C, H * W, out_channels / 8, channel0 / 8);
+  return check_launch("cdfo_pack_c8_into");
 }
 
 extern "C" int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, void *stream) {

@@ -230,9 +230,19 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     H, W = center.shape[2:]
     ufs_prior = prior_conv(model.conv_expand_ufs, ufs_nb)
     rms_prior = prior_conv(model.conv_expand_rms, rms_nb)
-    x_n = long_range_attention(model.RDAB, rms_prior, fea_nb, u_nb, x2=rms_prior)
+    # fea_nb: [6B, 64, H, W], or the contiguous runs of it (model.FeatureRing: frames 0-2 and 4-6); cat([fea, x_n]) (arch:4454) is
+    # two packs into one c8 tensor
+    runs = fea_nb if isinstance(fea_nb, (tuple, list)) else (fea_nb,)
+    cat8 = torch.empty((6 * B, 16, H, W, 8), dtype=torch.bfloat16, device=center.device)
+    off = 0
+    for run in runs:
+        sl = slice(off, off + run.size(0))
+        x_n = long_range_attention(model.RDAB, rms_prior[sl], run, u_nb[sl], x2=rms_prior[sl])
+        conv.to_c8(run, out=cat8[sl], channel0=0)
+        conv.to_c8(x_n, out=cat8[sl], channel0=64)
+        off += run.size(0)
     fr = model.conv_expand_fea_r
-    fea_i = conv.conv3x3(conv.to_c8(torch.cat([fea_nb, x_n], 1)), fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
+    fea_i = conv.conv3x3(cat8, fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
     stack = torch.empty((B, 56, H, W, 8), dtype=torch.bfloat16, device=center.device)
     stack[:, 24:32] = conv.to_c8(center)
     al = model.MV_deform_align

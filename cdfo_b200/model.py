@@ -279,6 +279,38 @@ class MVDualAttAlignment(_Holder):
         return hotpath.mv_dual_att_alignment(self, x, extra_feat, pred_feat, flow_1)
 
 
+class FeatureRing:
+    """The sliding window's L1 features (arch:4417-4427 keeps them as `pre_L1_fea` and rebuilds the [B*N] tensor with a cat per
+    frame) as a frame-major ring in HBM: 2N slots of [B, C, H, W] fp32, frame t stored at t % N and t % N + N, so the window is
+    always ONE contiguous view buf[head : head + N] -- a step writes the new frame twice (2 x B x 33 MB at c3) instead of copying
+    all N frames, the centre frame and the two neighbour runs (frames 0-2 and 4-6) are contiguous views."""
+
+    def __init__(self, l1_bn, B, N):
+        C, H, W = l1_bn.shape[1:]
+        self.B, self.N, self.head, self.serial = B, N, 0, 0
+        self.buf = torch.empty((2 * N, B, C, H, W), dtype=torch.float32, device=l1_bn.device)
+        fm = l1_bn.view(B, N, C, H, W).transpose(0, 1)
+        self.buf[:N].copy_(fm)
+        self.buf[N:].copy_(fm)
+
+    def push(self, new):
+        self.buf[self.head].copy_(new)
+        self.buf[self.head + self.N].copy_(new)
+        self.head = (self.head + 1) % self.N
+        self.serial += 1
+
+    def window(self):
+        return self.buf[self.head:self.head + self.N]
+
+    def handle(self):
+        """What forward() returns as L1_fea in ring mode: a view of the window (FRAME-major [N*B, C, H, W]; equal to the
+        reference's tensor for B = 1) tagged with the ring, valid until the next step."""
+        w = self.window()
+        t = w.view(self.N * self.B, *w.shape[2:])
+        t._cdfo_ring = (self, self.serial)
+        return t
+
+
 # ------------------------------------------------------------------------------------------ the model
 class CVSR_V8(nn.Module):
     def __init__(self, nf=64, nframes=7, fea_ext_RBs=7, SCGs=4, istraining=False, alignment="dual_att"):
@@ -307,6 +339,7 @@ class CVSR_V8(nn.Module):
         self.lowp = None            # torch dtype for the non-hot-path convolutions (None: fp32)
         self.noise_generator = None
         self.trunk_backend = "cuda"   # "cuda": tcgen05 convs + resample kernels on c8 bf16; "cudnn": torch convolutions
+        self.feature_ring = False     # True: the returned L1_fea is a FeatureRing handle (no per-frame copies of the window's features)
 
     # -- feature extraction of `n` frames ("next" row f2; cuDNN for now)
     def _features(self, x, pms):
@@ -338,12 +371,26 @@ class CVSR_V8(nn.Module):
         B, N, C, H, W = x.shape
         assert N == 7 and C == 1 and H % 8 == 0 and W % 8 == 0
         ctr = self.center
+        ring = None
         if pre_L1_fea is None:
             l1 = self._features(x.reshape(-1, C, H, W), pms.reshape(-1, C, H, W))
+            if self.feature_ring:
+                ring = FeatureRing(l1, B, N)
+        elif getattr(pre_L1_fea, "_cdfo_ring", None) is not None:
+            ring, serial = pre_L1_fea._cdfo_ring
+            if serial != ring.serial or ring.B != B or tuple(ring.buf.shape[3:]) != (H, W):
+                raise hotpath._lib.CdfoError("CVSR_V8: stale or mismatched feature-ring handle (pass the L1_fea of the previous step)")
+            ring.push(self._features(x[:, -1], pms[:, -1]))
         else:
             new = self._features(x[:, -1], pms[:, -1])
             l1 = torch.cat([pre_L1_fea.view(B, N, -1, H, W)[:, 1:], new.unsqueeze(1)], 1).reshape(B * N, -1, H, W)
-        fea = l1.view(B, N, -1, H, W)
+        if ring is not None:
+            win = ring.window()                                                      # [N, B, 64, H, W], frame-major
+            l1 = ring.handle()
+            center = win[ctr]
+            fea_nb = (win[:ctr].reshape(ctr * B, -1, H, W), win[ctr + 1:].reshape((N - 1 - ctr) * B, -1, H, W))   # two contiguous views
+        else:
+            fea = l1.view(B, N, -1, H, W)
         if ufs.shape[1] != N:  # reference accepts [B,1,N,H,W] as well (arch:4434-4437)
             ufs, rms = ufs.transpose(1, 2), rms.transpose(1, 2)
         if noise is None:
@@ -353,12 +400,16 @@ class CVSR_V8(nn.Module):
         # host-to-device copy per call, which also cannot be captured in a CUDA graph)
         def neighbours(t):
             return torch.cat([t[:, :ctr], t[:, ctr + 1:]], 1).transpose(0, 1)
-        fea_nb = neighbours(fea).reshape(6 * B, -1, H, W)
+        if ring is None:
+            fea_nb = neighbours(fea).reshape(6 * B, -1, H, W)
+            center = fea[:, ctr]
         ufs_nb = neighbours(ufs).reshape(6 * B, 1, H, W)
         rms_nb = neighbours(rms).reshape(6 * B, 1, H, W)
         mv_nb = neighbours(mvs1).reshape(6 * B, 2, H, W).contiguous()
-        u_nb = torch.cat([u.to(x.device, torch.float32) for u in noise], 0)
-        center = fea[:, ctr]
+        if torch.is_tensor(noise):       # already neighbour-major [6 * B, 64, H, W]
+            u_nb = noise
+        else:
+            u_nb = torch.cat([u.to(x.device, torch.float32) for u in noise], 0)
         fused8 = hotpath.align_and_fuse(self, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B)   # c8 bf16 [B,8,H,W,8]
         t = self._trunk(fused8)
         out = hotpath.tail(self, t, x[:, ctr])

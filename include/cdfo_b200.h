@@ -93,6 +93,9 @@ int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float
 
 /* ---- layout adapters: NCHW fp32 <-> "c8" = [B, C/8, H, W, 8] bf16 (C % 8 == 0). ---- */
 int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H, int W, void *stream);
+/* Same, into channels [channel0, channel0 + C) of a c8 tensor with out_channels channels (both multiples of 8): the channel
+ * concatenations of the model (arch/SIDECVSR_our.py:4454 cat([fea, x_n])) become two packs into one tensor. */
+int cdfo_pack_c8_into(const float *x_nchw, void *x_c8, int B, int C, int H, int W, int out_channels, int channel0, void *stream);
 int cdfo_unpack_c8(const void *x_c8, float *x_nchw, int B, int C, int H, int W, void *stream);
 
 /* ---- A6 at the model's hot shape on the 5th-generation tensor cores (tcgen05, TMEM) ----

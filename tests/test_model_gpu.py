@@ -193,3 +193,38 @@ def test_graphed_step_matches_eager(cuda_dev):
         sr_g, l1_g = gs(c["x"], mvs, c["pms"], c["rms"], c["ufs"], l1, noise)
         torch.cuda.synchronize()
         assert torch.equal(sr_g, sr_e) and torch.equal(l1_g, l1_e)
+
+
+def test_feature_ring_matches_window_cat(cuda_dev):
+    """model.feature_ring: the L1 features of the sliding window kept as a frame-major ring (no per-frame copy of the window, RDAB on
+    the two contiguous neighbour runs, noise passed pre-concatenated) gives the outputs of the plain `pre_L1_fea` path over
+    several steps; a stale handle is refused."""
+    from cdfo_b200 import synthetic, _lib
+    from oracle import priors_ref
+    H, W, B = 32, 48, 2
+    m = _model("O2", cuda_dev, torch.bfloat16)
+    clip = synthetic.make_clip(7, H, W, B)
+    c = _dev(clip, cuda_dev)
+    mvs = torch.stack([torch.from_numpy(priors_ref.mv2mvs_model_layout(clip["mv_l0"][b].numpy())[0]) for b in range(B)]).to(cuda_dev)
+    noise = [u.to(cuda_dev) for u in synthetic.gumbel_uniforms(4, 9, 0, B, H, W)]
+
+    def run(ring, steps=9):      # more steps than ring slots: the head wraps
+        m.feature_ring = ring
+        srs, l1, first = [], None, None
+        for s in range(steps):
+            x = torch.roll(c["x"], s, dims=1)           # a different "new frame" every step
+            pms = torch.roll(c["pms"], s, dims=1)
+            sr, l1 = m(x, None, mvs, pms, c["rms"], c["ufs"], l1, noise=torch.cat(noise, 0) if ring else noise)
+            first = l1 if first is None else first
+            srs.append(sr)
+        m.feature_ring = False
+        return srs, l1, first
+
+    srs_a, l1_a, _ = run(False)
+    srs_b, l1_b, stale = run(True)
+    for s, (a, b) in enumerate(zip(srs_a, srs_b)):
+        err = (a - b).abs().max().item()
+        assert err <= 2e-3, "step %d: ring vs cat differ by %.3g" % (s, err)      # cuDNN picks algorithms per call (DESIGN.md 4)
+    assert torch.equal(l1_b.view(7, B, 64, H, W).transpose(0, 1).reshape(B * 7, 64, H, W), l1_a)
+    with pytest.raises(_lib.CdfoError):
+        m(c["x"], None, mvs, c["pms"], c["rms"], c["ufs"], stale, noise=noise)
