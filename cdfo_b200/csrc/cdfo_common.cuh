@@ -51,7 +51,8 @@ __device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
 
 // csrc/pointwise.cu: tensor-core 1x1 convolution (see cdfo_pointwise_conv_fwd in include/cdfo_b200.h)
 int pointwise_conv(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1, const float *resid2,
-                   float *out, int B, int K, int Co, int HW, int act, int mode, cudaStream_t s);
+                   float *out, int B, int K, int Co, int HW, int act, int mode, cudaStream_t s, void *out_c8 = nullptr,
+                   int out_channels = 0, int channel0 = 0);
 
 // csrc/conv3x3_sm100.cu: weight [Cout][Cin][k][k] fp32 -> [n_tile][tap][Cin/8][NT][8] bf16 (streamed: [n_tile][K block][tap][8][NT][8])
 int conv3x3_pack_weight_raw(const float *w, void *out, int Cout, int Cin, int NT, int n_tiles, int streamed, int taps, cudaStream_t s);

@@ -510,6 +510,179 @@ __global__ void __launch_bounds__(kColThreads, 1) lra_col_kernel(const float *__
   }
 }
 
+// ---- bf16 variant of the column pass (the one cdfo_lra_fwd launches) ----
+// Same flash pass on mma.sync m16n8k16 bf16 (fp32 accumulate): half the MMA and fragment-load count of the TF32 kernel, and the
+// operands take half the shared memory (Q [Hk][64] bf16 with 72-element rows, V TRANSPOSED [64][Hk] bf16 with Hk + 8 element rows:
+// both strides are 4 mod 32 words, every fragment load conflict-free), so two CTAs fit an SM and one column's load phase hides
+// behind the other's MMAs.  Q is built straight from the compact mask info (no fp32 sq scratch).  With V transposed the
+// probabilities feed the second MMA in their natural C-fragment order (keys 2t, 2t+1 of n-tiles 2s and 2s+1 are exactly the A
+// fragment of key step s).  bf16 keeps 8 mantissa bits: logits are O(1), so softmax weights move by < 4e-3 relative, the same
+// order as the bf16 rounding the consumer (conv_expand_fea_r, c8 bf16 input) applies to the result anyway.
+constexpr int kQw = 36;   // Q row stride in 32-bit words
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(kColThreads, 2) lra_col_bf16_kernel(const float *__restrict__ vrow_t, const uint8_t *__restrict__ midx,
+                                                                     const float *__restrict__ qsel, float *__restrict__ long_out,
+                                                                     LraTables t, int H, int W) {
+  extern __shared__ __align__(16) uint32_t smu[];
+  const int b = blockIdx.y, w = blockIdx.x;
+  const int HW = H * W;
+  const int Hk = (H + 63) & ~63;          // keys padded to whole 64-key blocks (rows >= H are zero and masked)
+  const int SW = Hk / 2 + 4;              // V^T row stride in words
+  uint32_t *Qw = smu;                     // [Hk][kQw]
+  uint32_t *Vt = Qw + Hk * kQw;           // [64][SW]
+  float *cq = reinterpret_cast<float *>(Vt + 64 * SW);      // [H + 8] q value of the masked channel (rows -4 .. H + 3)
+  int *cm = reinterpret_cast<int *>(cq + H + 8);            // [H + 8] masked channel, 255 = none, -1 = outside the frame
+  float *kws = reinterpret_cast<float *>(cm + H + 8);       // [9]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  float kh[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) kh[i] = t.kh[i];
+  if (tid < 9) kws[tid] = t.kw[tid];
+  for (int e = tid; e < H + 8; e += kColThreads) {
+    const int h = e - 4;
+    int c = -1;
+    float q = 0.f;
+    if (h >= 0 && h < H) {
+      c = midx[(size_t)b * HW + h * W + w];
+      q = qsel[(size_t)b * HW + h * W + w];
+    }
+    cm[e] = c;
+    cq[e] = q;
+  }
+  {  // V^T: a thread takes two consecutive keys x four channels; store order rotated per thread so that a warp's 32 words of one
+     // store instruction fall into 32 different banks
+    const float *vsrc = vrow_t + ((size_t)b * W + w) * H * 64;   // contiguous [H][64]
+    for (int e = tid; e < (Hk / 2) * 16; e += kColThreads) {
+      const int kp = (e >> 6) * 4 + (e & 3), c4 = (e >> 2) & 15;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (2 * kp < H) v0 = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp) * 64 + c4 * 4));
+      if (2 * kp + 1 < H) v1 = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp + 1) * 64 + c4 * 4));
+      const uint32_t wv[4] = {pack_bf16x2(v0.x, v1.x), pack_bf16x2(v0.y, v1.y), pack_bf16x2(v0.z, v1.z), pack_bf16x2(v0.w, v1.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = (i + (c4 >> 1)) & 3;
+        Vt[(c4 * 4 + j) * SW + kp] = j == 0 ? wv[0] : (j == 1 ? wv[1] : (j == 2 ? wv[2] : wv[3]));
+      }
+    }
+  }
+  __syncthreads();
+  // Q[h][c] = bh + sum_i kh[i] sq[h + i - 4][c],  sq[h'][c] = beta + kw[cm - c + 4] q (inside the frame), 0 outside; rows >= H: zero
+  for (int e = tid; e < Hk * 32; e += kColThreads) {
+    const int h = e >> 5, c0 = (e & 31) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    if (h < H) {
+      a0 = a1 = t.bh;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int c = cm[h + i];
+        if (c < 0) continue;
+        float s0 = t.beta, s1 = t.beta;
+        if (c != 255) {
+          const int t0 = c - c0 + 4, t1 = t0 - 1;
+          const float q = cq[h + i];
+          if (t0 >= 0 && t0 <= 8) s0 = fmaf(kws[t0], q, s0);
+          if (t1 >= 0 && t1 <= 8) s1 = fmaf(kws[t1], q, s1);
+        }
+        a0 = fmaf(kh[i], s0, a0);
+        a1 = fmaf(kh[i], s1, a1);
+      }
+    }
+    Qw[h * kQw + (e & 31)] = pack_bf16x2(a0, a1);
+  }
+  __syncthreads();
+
+  const int n_qt = (H + 15) >> 4, n_kb = Hk >> 6;
+  for (int qt = warp; qt < n_qt; qt += kColWarps) {
+    const int q0 = qt * 16;
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};   // rows g and g + 8
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int key0 = kb * 64;
+      float sc[8][4];
+      {
+        uint32_t aq[4][4];   // A fragments of the 16 x 64 query tile (four 16-channel steps), re-read per key block: 16 conflict-free
+                             // loads against 64 MMAs, and 16 registers less across the softmax / P V part (two CTAs per SM: 112 regs)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          aq[s][0] = Qw[(q0 + g) * kQw + 8 * s + tq];
+          aq[s][1] = Qw[(q0 + g + 8) * kQw + 8 * s + tq];
+          aq[s][2] = Qw[(q0 + g) * kQw + 8 * s + tq + 4];
+          aq[s][3] = Qw[(q0 + g + 8) * kQw + 8 * s + tq + 4];
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sc[n][i] = 0.f;
+          const uint32_t *kr = Qw + (key0 + 8 * n + g) * kQw + tq;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) mma_bf16(sc[n], aq[s], kr[8 * s], kr[8 * s + 4]);
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int key = key0 + 8 * n + 2 * tq;
+        if (key >= H) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
+        if (key + 1 >= H) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
+        mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+      }
+      float scale[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);    // every block holds at least one live key (key0 < H)
+        scale[r] = expf(m_run[r] - m_new);
+        m_run[r] = m_new;
+        l_run[r] *= scale[r];
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        sc[n][0] = expf(sc[n][0] - m_run[0]); sc[n][1] = expf(sc[n][1] - m_run[0]);
+        sc[n][2] = expf(sc[n][2] - m_run[1]); sc[n][3] = expf(sc[n][3] - m_run[1]);
+        l_run[0] += sc[n][0] + sc[n][1];
+        l_run[1] += sc[n][2] + sc[n][3];
+        o[n][0] *= scale[0]; o[n][1] *= scale[0]; o[n][2] *= scale[1]; o[n][3] *= scale[1];
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {      // 16 keys per step: A = probabilities of n-tiles 2s (keys +0..7) and 2s + 1 (keys +8..15)
+        const uint32_t ap[4] = {pack_bf16x2(sc[2 * s][0], sc[2 * s][1]), pack_bf16x2(sc[2 * s][2], sc[2 * s][3]),
+                                pack_bf16x2(sc[2 * s + 1][0], sc[2 * s + 1][1]), pack_bf16x2(sc[2 * s + 1][2], sc[2 * s + 1][3])};
+        const uint32_t *vr = Vt + g * SW + (key0 >> 1) + 8 * s + tq;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) mma_bf16(o[n], ap, vr[8 * n * SW], vr[8 * n * SW + 4]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    const int h0 = q0 + g, h1 = q0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (h0 < H) *reinterpret_cast<float2 *>(long_out + (((size_t)b * H + h0) * W + w) * 64 + 8 * n + 2 * tq) = make_float2(o[n][0] * inv0, o[n][1] * inv0);
+      if (h1 < H) *reinterpret_cast<float2 *>(long_out + (((size_t)b * H + h1) * W + w) * 64 + 8 * n + 2 * tq) = make_float2(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ 8x8 windows
 // CTA per window; tokens = 64 pixels, sq = q with the masked channel zeroed ((1 - mask) * q, arch:2236-2239).
 constexpr int kWinThreads = 256;
@@ -543,16 +716,41 @@ __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__res
 
 using namespace cdfo;
 
+static bool g_lra_col_tf32 = false;   // cdfo_lra_set_col_precision: A/B switch (tests, tools)
+extern "C" int cdfo_lra_set_col_precision(int tf32) {
+  g_lra_col_tf32 = tf32 != 0;
+  return CDFO_OK;
+}
+
 // tables: float[9 kw | 9 kh | 64 k1 | 4096 r] on the device; scratch sizes are the caller's (see cdfo_lra_workspace_bytes).
 extern "C" size_t cdfo_lra_workspace_bytes(int B, int H, int W) {
   const size_t P = (size_t)B * H * W;
   return P * (1 + 4) + 3 * P * 64 * 4 + 256;   // midx + qsel + vrow_t + long_out + loc_out
 }
 
+static int lra_run(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                   float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *out_c8, int out_channels,
+                   int channel0, void *workspace, int B, int H, int W, void *stream);
+
 extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
                             float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B,
                             int H, int W, void *stream) {
-  CDFO_REQUIRE(qv && u && vmax && x && tables && fuse_w && fuse_b && out && workspace, CDFO_ERR_NULL, "cdfo_lra_fwd: NULL pointer");
+  return lra_run(qv, u, vmax, x, x2, tables, beta, bh, fuse_w, fuse_b, out, nullptr, 0, 0, workspace, B, H, W, stream);
+}
+
+extern "C" int cdfo_lra_c8_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                               float beta, float bh, const float *fuse_w, const float *fuse_b, void *out_c8, int out_channels,
+                               int channel0, void *workspace, int B, int H, int W, void *stream) {
+  CDFO_REQUIRE(out_c8 && ((uintptr_t)out_c8 & 15) == 0, CDFO_ERR_NULL, "cdfo_lra_c8_fwd: out_c8 must be a 16-byte aligned pointer");
+  CDFO_REQUIRE(out_channels % 8 == 0 && channel0 % 8 == 0 && channel0 >= 0 && channel0 + 64 <= out_channels, CDFO_ERR_SHAPE,
+               "cdfo_lra_c8_fwd: channels [%d, %d) do not fit %d output channels (multiples of 8)", channel0, channel0 + 64, out_channels);
+  return lra_run(qv, u, vmax, x, x2, tables, beta, bh, fuse_w, fuse_b, nullptr, out_c8, out_channels, channel0, workspace, B, H, W, stream);
+}
+
+static int lra_run(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                   float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *out_c8, int out_channels,
+                   int channel0, void *workspace, int B, int H, int W, void *stream) {
+  CDFO_REQUIRE(qv && u && vmax && x && tables && fuse_w && fuse_b && (out || out_c8) && workspace, CDFO_ERR_NULL, "cdfo_lra_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, CDFO_ERR_SHAPE,
                "cdfo_lra_fwd: H and W must be multiples of the window size 8 (got %d x %d)", H, W);
   cudaStream_t s = (cudaStream_t)stream;
@@ -581,15 +779,21 @@ extern "C" int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, 
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e2 = cudaFuncSetAttribute(lra_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(lra_col_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e3 = cudaFuncSetAttribute(lra_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
       return fail(CDFO_ERR_CUDA, "cdfo_lra_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     attr = true;
   }
   lra_row_kernel<<<dim3(H, B), kRowThreads, row_smem, s>>>(qv, midx, qsel, vrow_t, t, H, W);
-  lra_col_kernel<<<dim3(W, B), kColThreads, col_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
+  if (g_lra_col_tf32) {
+    lra_col_kernel<<<dim3(W, B), kColThreads, col_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
+  } else {
+    const size_t col16_smem = ((size_t)Hk * kQw + 64 * ((size_t)Hk / 2 + 4) + 2 * (size_t)(H + 8) + 16) * 4;
+    lra_col_bf16_kernel<<<dim3(W, B), kColThreads, col16_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
+  }
   lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, win_smem, s>>>(qv, midx, loc_out, H, W);
   if (int rc = check_launch("cdfo_lra_fwd")) return rc;
   // fuse: 1x1 conv(128 -> 64) over cat[long, local] (pixel-major) + bias + x (+ x2): tensor-core pointwise kernel
-  return pointwise_conv(long_out, loc_out, fuse_w, fuse_b, x, x2, out, B, 128, 64, HW, 0, 1, s);
+  return pointwise_conv(long_out, loc_out, fuse_w, fuse_b, x, x2, out, B, 128, 64, HW, 0, 1, s, out_c8, out_channels, channel0);
 }

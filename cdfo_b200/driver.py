@@ -219,6 +219,8 @@ class FrameDriver:
         self._fill(slots[0], seqs, o0[-1], 0, h)       # step 0 needs only the MV field (+ GT) from its slot
         self._upload(slots[0])
         l1, pending = None, None
+        ring_before = self.model.feature_ring
+        self.model.feature_ring = not self.use_graph      # eager steps keep the window's L1 features in a ring (model.FeatureRing)
         for i in range(T):
             slot = slots[i % 2]
             if i + 1 < T:                               # stage step i+1 while step i computes
@@ -264,6 +266,7 @@ class FrameDriver:
         if sink is not None and pending is not None:
             self._deliver(sink, pending, out_host, out_done)
         torch.cuda.current_stream(dev).synchronize()
+        self.model.feature_ring = ring_before
         res = {"frames": T, "sums": sums, "psnr": None, "ssim": None}
         if with_gt:
             host = sums.cpu()

@@ -178,11 +178,13 @@ def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
 
 
 @torch.no_grad()
-def long_range_attention(mod, res, x, u, x2=None):
+def long_range_attention(mod, res, x, u, x2=None, out8=None, channel0=0):
     """LLongRangAttention.forward, arch:2179-2249, on the input x (+ x2: the model's `fea + rms_prior`, arch:4449, is formed
     inside the kernels and never written); u = uniform noise of gumbel_softmax (arch:2169).
     The 1x1 convolutions (conv_du_re.0, input_conv, fuse) are tensor-core pointwise kernels, the mask / row / column /
-    window attentions csrc/lra.cu; only the stride-2 3x3 of the mask logits and its global mean are cuDNN / ATen calls."""
+    window attentions csrc/lra.cu; only the stride-2 3x3 of the mask logits and its global mean are cuDNN / ATen calls.
+    With out8 (contiguous bf16 c8 [B, C8, H, W, 8]) the result leaves as bf16 in its channels [channel0, channel0 + 64) instead of a
+    new fp32 tensor (the fuse kernel's epilogue packs it)."""
     B, C, H, W = x.shape
     res, x = _f32(res), _f32(x)
     x2 = None if x2 is None else _f32(x2)
@@ -192,10 +194,18 @@ def long_range_attention(mod, res, x, u, x2=None):
     v = v.mean(dim=(2, 3), keepdim=True)
     vmax = F.relu(_c(mod.conv_du_re2._modules["0"], v)).reshape(B, C).contiguous()   # bilinear up of a 1x1 map = broadcast
     qv = _pointwise(x, x2, mod.input_conv.weight, mod.input_conv.bias, act=0)
-    out = torch.empty_like(x)
     nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     tab, beta, bh = _lra_tap_tables(mod)
+    if out8 is not None:
+        if out8.dtype != torch.bfloat16 or not out8.is_contiguous() or out8.dim() != 5 or (out8.size(0), out8.size(2), out8.size(3), out8.size(4)) != (B, H, W, 8):
+            raise _lib.CdfoError("long_range_attention: out8 must be a contiguous bf16 c8 tensor of the same batch and size")
+        _lib.call("cdfo_lra_c8_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(x2), _lib.ptr(tab),
+                  ctypes.c_float(beta), ctypes.c_float(bh),
+                  _lib.ptr(_f32(mod.fuse.weight).reshape(64, 128)), _lib.ptr(_f32(mod.fuse.bias)),
+                  _lib.ptr(out8), out8.size(1) * 8, int(channel0), _lib.ptr(ws), B, H, W, _lib.stream_ptr(x.device))
+        return out8
+    out = torch.empty_like(x)
     _lib.call("cdfo_lra_fwd", _lib.ptr(qv), _lib.ptr(u.contiguous()), _lib.ptr(vmax), _lib.ptr(x), _lib.ptr(x2), _lib.ptr(tab),
               ctypes.c_float(beta), ctypes.c_float(bh),
               _lib.ptr(_f32(mod.fuse.weight).reshape(64, 128)), _lib.ptr(_f32(mod.fuse.bias)),
@@ -237,9 +247,8 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     off = 0
     for run in runs:
         sl = slice(off, off + run.size(0))
-        x_n = long_range_attention(model.RDAB, rms_prior[sl], run, u_nb[sl], x2=rms_prior[sl])
+        long_range_attention(model.RDAB, rms_prior[sl], run, u_nb[sl], x2=rms_prior[sl], out8=cat8[sl], channel0=64)
         conv.to_c8(run, out=cat8[sl], channel0=0)
-        conv.to_c8(x_n, out=cat8[sl], channel0=64)
         off += run.size(0)
     fr = model.conv_expand_fea_r
     fea_i = conv.conv3x3(cat8, fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)

@@ -221,12 +221,24 @@ int cdfo_resample_c8(const void *a, const void *b, const void *base, void *y, in
 int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
                  float beta, float bh, const float *fuse_w, const float *fuse_b, float *out, void *workspace, int B, int H, int W,
                  void *stream);
+/* Same, with the result leaving as bf16 in channels [channel0, channel0 + 64) of a c8 tensor [B,out_channels/8,H,W,8] -- the second
+ * half of the model's cat([fea, x_n]) (arch:4454), the input of conv_expand_fea_r; no fp32 copy of x_n exists. */
+/* Column pass operands: 0 (default) = bf16 mma.sync m16n8k16, 1 = TF32 m16n8k8 (the first-generation kernel; A/B switch). */
+int cdfo_lra_set_col_precision(int tf32);
+int cdfo_lra_c8_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
+                    float beta, float bh, const float *fuse_w, const float *fuse_b, void *out_c8, int out_channels, int channel0,
+                    void *workspace, int B, int H, int W, void *stream);
 /* ---- 1x1 convolutions of A8 on the tensor cores (csrc/pointwise.cu), NCHW fp32 in / out ----
  *   y[b,co,p] = act(bias[co] + sum_k w[co,k] x[b,k,p]) + resid1[b,co,p] + resid2[b,co,p]        (act 0 none / 1 ReLU)
  *   mode 0: x = in1 + in2 (in2 may be NULL), [B,K,H,W]; supported K -> Co: 64 -> 64 (conv_du_re.0, arch:2183), 64 -> 128 (input_conv
  *           on fea + residual prior, arch:2206/:4449);  mode 1: x = cat(in1, in2), both pixel-major [B,H*W,64], 128 -> 64 (fuse, arch:2246). */
 int cdfo_pointwise_conv_fwd(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1,
                             const float *resid2, float *out, int B, int K, int Co, int H, int W, int act, int mode, void *stream);
+/* Same, the Co output channels leaving as bf16 in channels [channel0, channel0 + Co) of a c8 tensor [B,out_channels/8,H,W,8]
+ * (H * W a multiple of 4). */
+int cdfo_pointwise_conv_c8_fwd(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1,
+                               const float *resid2, void *out_c8, int B, int K, int Co, int H, int W, int act, int mode,
+                               int out_channels, int channel0, void *stream);
 size_t cdfo_lra_workspace_bytes(int B, int H, int W);
 /* ---- pieces of the feature extraction, NCHW, dtype CDFO_F32 or CDFO_BF16 storage, fp32 arithmetic ----
  * LayerNorm over the 64 channels of each pixel, WithBias (arch/SIDECVSR_our.py:1169-1198): y = (x - mu) rsqrt(var + eps) gamma + beta. */

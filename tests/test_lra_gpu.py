@@ -63,3 +63,63 @@ def test_lra_dense_mask(cuda_dev):
     print("LRA dense mask: masked tokens %.1f%% on channels %s, max err %.3g" % (100 * frac, chans, err))
     assert frac > 0.9 and len(chans) >= 2
     assert err <= 2e-3
+
+
+def test_lra_c8_output_is_the_rounded_fp32_output(cuda_dev):
+    """long_range_attention(out8=...): the fuse kernel packs its result as bf16 into a channel range of the consumer's c8 tensor
+    (the model's cat([fea, x_n]), arch:4454); equals the bf16 rounding of the fp32 output, other channels untouched."""
+    from cdfo_b200 import conv, hotpath
+    B, H, W = 2, 24, 40
+    res, x, u = _inputs(B, H, W, seed=77)
+    m = _model(cuda_dev)
+    res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
+    ref = hotpath.long_range_attention(m.RDAB, res, x, u, x2=res)
+    out8 = torch.full((B, 16, H, W, 8), 3.0, dtype=torch.bfloat16, device=cuda_dev)
+    hotpath.long_range_attention(m.RDAB, res, x, u, x2=res, out8=out8, channel0=64)
+    conv.to_c8(x, out=out8, channel0=0)
+    got = conv.from_c8(out8)
+    assert torch.equal(got[:, 64:], ref.to(torch.bfloat16).float())
+    assert torch.equal(got[:, :64], x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("K,Co,mode,H,W", [(64, 64, 0, 9, 7), (64, 128, 0, 10, 13), (128, 64, 1, 5, 9), (64, 128, 0, 16, 20), (128, 64, 1, 12, 12)])
+def test_pointwise_conv_shapes(cuda_dev, K, Co, mode, H, W):
+    """Tensor-core 1x1 convolution (TF32): pipelined kernel (H*W % 4 == 0, ragged last tile) and the scalar fallback (odd sizes)."""
+    from cdfo_b200 import hotpath
+    g = torch.Generator().manual_seed(K + Co + H)
+    B = 2
+    wgt = (torch.randn(Co, K, generator=g) / K ** 0.5).to(cuda_dev)
+    bias = torch.randn(Co, generator=g).to(cuda_dev)
+    r1 = torch.randn(B, Co, H, W, generator=g).to(cuda_dev)
+    if mode == 0:
+        a, b2 = torch.randn(B, K, H, W, generator=g).to(cuda_dev), torch.randn(B, K, H, W, generator=g).to(cuda_dev)
+        ref = torch.einsum("ok,bkhw->bohw", wgt.double(), (a + b2).double()) + bias.view(1, -1, 1, 1).double()
+    else:
+        a, b2 = torch.randn(B, H * W, 64, generator=g).to(cuda_dev), torch.randn(B, H * W, 64, generator=g).to(cuda_dev)
+        cat = torch.cat([a, b2], 2).double()
+        ref = torch.einsum("ok,bpk->bop", wgt.double(), cat).view(B, Co, H, W) + bias.view(1, -1, 1, 1).double()
+    ref = torch.relu(ref) + r1.double()
+    out = torch.empty((B, Co, H, W), dtype=torch.float32, device=cuda_dev)
+    from cdfo_b200 import _lib
+    _lib.call("cdfo_pointwise_conv_fwd", _lib.ptr(a), _lib.ptr(b2), _lib.ptr(wgt), _lib.ptr(bias), _lib.ptr(r1), _lib.ptr(None), _lib.ptr(out),
+              B, K, Co, H, W, 1, mode, _lib.stream_ptr(cuda_dev))
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 5e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_lra_col_bf16_vs_tf32(cuda_dev):
+    """The bf16 column pass (mma.sync m16n8k16, the default) against the TF32 one: same result to bf16-operand accuracy."""
+    from cdfo_b200 import _lib
+    B, H, W = 2, 72, 40          # H not a multiple of 64: masked keys in the last block; 5 query tiles over 9 warps
+    res, x, u = _inputs(B, H, W, seed=3)
+    m = _model(cuda_dev)
+    res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
+    try:
+        _lib.call("cdfo_lra_set_col_precision", 1)
+        ref = m.RDAB(res, x, u)
+    finally:
+        _lib.call("cdfo_lra_set_col_precision", 0)
+    out = m.RDAB(res, x, u)
+    err = (out - ref).abs().max().item()
+    print("LRA column pass bf16 vs tf32: max diff %.3g (max|out| %.3g)" % (err, ref.abs().max().item()))
+    assert err <= 4e-3
