@@ -23,3 +23,7 @@ conv_fold_half = os.environ.get("CDFO_CONV_FOLD_HALF", "1") != "0"
 # loaded with elementStrides = 2.  Measured (tools/bench_conv.py): no gain for the folded convolution once its streamed weights arrive
 # as 512-byte TMA rows (212 us either way at 2 x 544x960), and the producer's scattered stores cost 5 % -- kept as an option, off.
 conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "0") != "0"
+
+# Offset / mask head of MVDualAttAlignment: True = both evaluations of conv_offset[-1] in one launch (the first one stays in the
+# epilogue's registers, cdfo_mv_offset_head_dual_sm100_fwd); False = two launches with the intermediate fields in HBM.
+head_dual = os.environ.get("CDFO_HEAD_DUAL", "1") != "0"

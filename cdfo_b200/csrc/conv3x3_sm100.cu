@@ -77,9 +77,15 @@ __device__ __forceinline__ uint32_t cv_pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int NT, int kStages, int KBLK, int KS>
+// DUAL (offset / mask head only, NT = 144): the input holds 2 B samples, sample b and b + B are the two hidden maps of
+// MVDualAttAlignment (arch/SIDECVSR_our.py:3339-3350).  A CTA computes the SAME pixel tile of both back to back; the epilogue keeps
+// the first evaluation (mag tanh(dy1), mag tanh(dx1), m1) in registers, rounded to fp16 exactly as the two-launch path stores it, and
+// combines it with the second: the intermediate fields (1152 B per pixel written and read again) never reach HBM.
+template <int NT, int kStages, int KBLK, int KS, bool DUAL = false>
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Params p) {
+  static_assert(!DUAL || NT == 144, "the dual head uses the 144-channel N tile");
+  constexpr int kEvals = DUAL ? 2 : 1;
   constexpr int kAccCols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));  // per accumulator buffer
   constexpr int kTmemCols = 2 * kAccCols;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -141,13 +147,15 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       const int b = mt / (p.tiles_x * p.tiles_y);
       const int r = mt - b * p.tiles_x * p.tiles_y;
       const int h0 = (r / p.tiles_x) * kCvTileH, w0 = (r % p.tiles_x) * kCvTileW;
+      for (int ev = 0; ev < kEvals; ++ev)
       for (int kb = 0; kb < KB; ++kb) {
         if (lane == 0) {
           ptx::mbar_wait(BAR(4 + stage), phase ^ 1);
           const uint32_t dst = ptx::smem_u32(asmem) + stage * stage_stride;
           ptx::mbar_arrive_expect_tx(BAR(stage), kABytes + (p.stream_w ? kTaps * kPiece : 0));
-          if (p.tma_wide) ptx::tma_load_5d(dst, &tmap, BAR(stage), (w0 - KS / 2) * 8, h0 - KS / 2, kb * kChunks, b, 0);
-          else ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - KS / 2, h0 - KS / 2, kb * kChunks, b);
+          const int bi = b + ev * p.B;       // DUAL: the second hidden map of the pair
+          if (p.tma_wide) ptx::tma_load_5d(dst, &tmap, BAR(stage), (w0 - KS / 2) * 8, h0 - KS / 2, kb * kChunks, bi, 0);
+          else ptx::tma_load_5d(dst, &tmap, BAR(stage), 0, w0 - KS / 2, h0 - KS / 2, kb * kChunks, bi);
           if (p.stream_w) {
             // streamed weights are packed [n_tile][K block][tap][chunk][NT][8]: one bulk copy per stage
             ptx::bulk_g2s(dst + kABytes, p.wpk + (size_t)n_tile * w_bytes + (size_t)kb * kTaps * kPiece, kTaps * kPiece, BAR(stage));
@@ -162,7 +170,8 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
     const uint32_t idesc = ptx::make_idesc_bf16(128, NT);
     if (!p.stream_w) ptx::mbar_wait(BAR(12), 0);
     int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+    for (int mt = m_first; mt < p.m_tiles; mt += m_step)
+    for (int ev = 0; ev < kEvals; ++ev) {
       ptx::mbar_wait(BAR(10 + acc), acc_phase ^ 1);
       ptx::tc_fence_after();
       for (int kb = 0; kb < KB; ++kb) {
@@ -204,6 +213,77 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       const int h = (r / p.tiles_x) * kCvTileH + ty, w = (r % p.tiles_x) * kCvTileW + tx;
       const bool live = h < p.H && w < p.W;
       const size_t pix = (size_t)h * p.W + w;
+      if constexpr (DUAL) {
+        uint2 stash[2][16];      // first evaluation of this thread's (up to) two 48-channel chunks, as the fp16 fields of epi 1
+        const int dgn = p.Cout / 27;
+        const bool vec = dgn == 16;
+#pragma unroll
+        for (int ev = 0; ev < 2; ++ev) {
+          ptx::mbar_wait(BAR(8 + acc), acc_phase);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0 = ehalf * 48 + ci * 96;
+            if (c0 < NT) {
+              uint32_t r0[16], r1[16], r2[16];
+              const uint32_t ta = tmem_base + acc * kAccCols + ((uint32_t)(quarter * 32) << 16) + c0;
+              tmem_ld16(ta, r0);
+              tmem_ld16(ta + 16, r1);
+              tmem_ld16(ta + 32, r2);
+              ptx::tmem_ld_wait();
+              if (c0 + 96 >= NT) {           // this warp's last read of the accumulator buffer
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(BAR(10 + acc));
+              }
+              if (live) {
+                float v[48];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  v[i] = __uint_as_float(r0[i]) + bias_s[c0 + i];
+                  v[16 + i] = __uint_as_float(r1[i]) + bias_s[c0 + 16 + i];
+                  v[32 + i] = __uint_as_float(r2[i]) + bias_s[c0 + 32 + i];
+                }
+                const int k0 = (n0 + c0) / 3;
+                const size_t base16 = (((size_t)b * 9 + k0 / 16) * 8 * HW + pix) * 2;   // dg == 16: pair plane 0 of this tap
+                uint2 outv[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  float dy, dx, m = v[3 * t + 2];
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(dy) : "f"(v[3 * t]));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(dx) : "f"(v[3 * t + 1]));
+                  dy *= p.mag;
+                  dx *= p.mag;
+                  if (ev == 1) {
+                    const float2 pd = __half22float2(*reinterpret_cast<const __half2 *>(&stash[ci][t].x));
+                    const float pm = __low2float(*reinterpret_cast<const __half2 *>(&stash[ci][t].y));
+                    dy += pd.x;                                       // offset_1 + offset_2 (arch:3347)
+                    dx += pd.y;
+                    m = __fdividef(1.f, 1.f + __expf(-(pm + m)));     // sigmoid(mask_1 + mask_2) (arch:3350)
+                  }
+                  const __half2 h0 = __floats2half2_rn(dy, dx), h1 = __floats2half2_rn(m, 0.f);
+                  const uint2 o = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                  if (ev == 0) stash[ci][t] = o;
+                  else outv[t] = o;
+                }
+                if (ev == 1) {
+                  uint2 *y = reinterpret_cast<uint2 *>(p.y);
+                  if (vec) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                      *reinterpret_cast<uint4 *>(y + base16 + (size_t)t * 2 * HW) = make_uint4(outv[2 * t].x, outv[2 * t].y, outv[2 * t + 1].x, outv[2 * t + 1].y);
+                  } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) y[((size_t)b * 9 * dgn + k0 + t) * HW + pix] = outv[t];
+                  }
+                }
+              }
+            }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        continue;
+      }
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
       if (p.epi == 3) {
@@ -444,9 +524,9 @@ bool conv3x3_streams(int Cout, int Cin, int taps = 9) {
 }
 int conv3x3_ntile(int Cout, int Cin, int taps = 9) { return conv3x3_streams(Cout, Cin, taps) ? 64 : conv3x3_ntile_resident(Cout, Cin, taps); }
 
-template <int NT, int kStages, int KBLK, int KS>
+template <int NT, int kStages, int KBLK, int KS, bool DUAL = false>
 static int launch_conv3x3(const CUtensorMap &tm, const Conv3x3Params &p, int grid, cudaStream_t s) {
-  auto kern = conv3x3_sm100_kernel<NT, kStages, KBLK, KS>;
+  auto kern = conv3x3_sm100_kernel<NT, kStages, KBLK, KS, DUAL>;
   constexpr int kTaps = KS * KS;
   const int w_bytes = kTaps * p.Cin * NT * 2;
   constexpr int kABytes = (KBLK / 8) * CvGeom<KS>::kPlane;
@@ -515,6 +595,16 @@ extern "C" int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, 
   return conv3x3_run(z_c8, wpk, bias, nullptr, out, B, Cin, dg * 27, H, W, 0, 0, first ? 2 : 1, magnitude, first, stream);
 }
 
+extern "C" int cdfo_mv_offset_head_dual_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, void *out, int B, int Cin, int dg,
+                                                  int H, int W, float magnitude, void *stream) {
+  CDFO_REQUIRE(dg > 0 && (dg * 27) % 144 == 0, CDFO_ERR_UNSUPPORTED,
+               "cdfo_mv_offset_head_dual_sm100_fwd: deformable_groups * 27 must be a multiple of 144 (got dg = %d)", dg);
+  CDFO_REQUIRE(conv3x3_ntile(dg * 27, Cin) == 144, CDFO_ERR_UNSUPPORTED,
+               "cdfo_mv_offset_head_dual_sm100_fwd: needs the 144-channel N tile (Cin = %d too large)", Cin);
+  CDFO_REQUIRE(((uintptr_t)out & 15) == 0, CDFO_ERR_SHAPE, "cdfo_mv_offset_head_dual_sm100_fwd: fields must be 16-byte aligned");
+  return conv3x3_run(z_c8, wpk, bias, nullptr, out, B, Cin, dg * 27, H, W, 0, 0, 4, magnitude, nullptr, stream);
+}
+
 extern "C" int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const float *lr, float *y, int B,
                                              int Cin, int H, int W, void *stream) {
   CDFO_REQUIRE(lr, CDFO_ERR_NULL, "cdfo_conv_last_skip_sm100_fwd: NULL pointer");
@@ -540,12 +630,13 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
   CDFO_REQUIRE(enc, CDFO_ERR_CUDA, "cdfo_conv3x3_sm100_fwd: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tm;
   static const bool wide = getenv("CDFO_TMA_WIDE1") == nullptr || getenv("CDFO_TMA_WIDE1")[0] != '0';
-  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)B};
+  const int Bx = epi == 4 ? 2 * B : B;          // dual head: the input holds both hidden maps, [2 B] samples
+  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)Bx};
   cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(Cin / 8) * H * W * 16};
   cuuint32_t box[5] = {8, (cuuint32_t)(kCvTileW + ksize - 1), (cuuint32_t)(kCvTileH + ksize - 1), 8, 1};
   if (wide) {   // same bytes, same landing order; TMA issues one request per halo row (up to 160 bytes) instead of one per 16-byte chunk
-    gdim[0] = (cuuint64_t)W * 8; gdim[1] = H; gdim[2] = Cin / 8; gdim[3] = B; gdim[4] = 1;
-    gstr[0] = (cuuint64_t)W * 16; gstr[1] = (cuuint64_t)H * W * 16; gstr[2] = (cuuint64_t)(Cin / 8) * H * W * 16; gstr[3] = gstr[2] * B;
+    gdim[0] = (cuuint64_t)W * 8; gdim[1] = H; gdim[2] = Cin / 8; gdim[3] = Bx; gdim[4] = 1;
+    gstr[0] = (cuuint64_t)W * 16; gstr[1] = (cuuint64_t)H * W * 16; gstr[2] = (cuuint64_t)(Cin / 8) * H * W * 16; gstr[3] = gstr[2] * Bx;
     box[0] = 8 * (kCvTileW + ksize - 1); box[1] = kCvTileH + ksize - 1; box[2] = 8; box[3] = 1; box[4] = 1;
   }
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -575,6 +666,10 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
       case 128: return launch_conv3x3<128, 4, 64, 1>(tm, p, grid, s);
     }
     return fail(CDFO_ERR_UNSUPPORTED, "cdfo_conv_sm100_fwd: N tile %d", nt);
+  }
+  if (epi == 4) {
+    CDFO_REQUIRE(nt == 144, CDFO_ERR_UNSUPPORTED, "cdfo_mv_offset_head_dual_sm100_fwd: needs the 144-channel N tile");
+    return launch_conv3x3<144, 2, 64, 3, true>(tm, p, grid, s);
   }
   switch (nt) {
     case 16: return launch_conv3x3<16, 2, 64, 3>(tm, p, grid, s);

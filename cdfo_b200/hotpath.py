@@ -112,9 +112,13 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     H, W = z.shape[2:4]
     dg = mod.deformable_groups
     wpk, bias = _head_weights(c2, dg)
-    first = torch.empty(dcn_sm100.fields_shape(B, dg, H, W), dtype=torch.float16, device=z.device)
-    fields = torch.empty_like(first)
+    fields = torch.empty(dcn_sm100.fields_shape(B, dg, H, W), dtype=torch.float16, device=z.device)
     args = (B, 64, dg, H, W, ctypes.c_float(float(mod.max_residue_magnitude)), _lib.stream_ptr(z.device))
+    if config.head_dual:
+        # both evaluations in one launch: the first stays in the epilogue's registers (bit-identical to the two-launch path)
+        _lib.call("cdfo_mv_offset_head_dual_sm100_fwd", _lib.ptr(z), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(fields), *args)
+        return fields
+    first = torch.empty_like(fields)
     _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[:B]), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(None),
               _lib.ptr(first), *args)
     _lib.call("cdfo_mv_offset_head_sm100_fwd", _lib.ptr(z[B:]), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(first),

@@ -169,6 +169,11 @@ int cdfo_conv3x3_sm100_fwd(const void *x_c8, const void *wpk, const float *bias,
  *   z_c8 [B, Cin/8, H, W, 8] bf16. */
 int cdfo_mv_offset_head_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, const void *first, void *out,
                                   int B, int Cin, int dg, int H, int W, float magnitude, void *stream);
+/* Both evaluations in ONE launch: z_c8 [2 B,Cin/8,H,W,8] holds the two hidden maps (sample b and b + B); every CTA computes the same
+ * pixel tile of both back to back and keeps the first evaluation in registers (rounded to fp16 exactly as the two-launch path
+ * stores it: bit-identical fields), so the intermediate fields (1152 B per pixel written, then read) never reach HBM. */
+int cdfo_mv_offset_head_dual_sm100_fwd(const void *z_c8, const void *wpk, const float *bias, void *out, int B, int Cin, int dg, int H,
+                                       int W, float magnitude, void *stream);
 /* conv_last (Cin -> 1, 3x3; weight packed with Cout padded to 16) + bias + bilinear x4 skip (align_corners=False) of the
  * 1-channel LR image lr [B, H/4, W/4] fp32 (arch/SIDECVSR_our.py:4477-4480); x_c8 [B, Cin/8, H, W, 8] bf16; y [B, 1, H, W] fp32. */
 int cdfo_conv_last_skip_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const float *lr, float *y, int B,

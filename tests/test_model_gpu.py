@@ -228,3 +228,21 @@ def test_feature_ring_matches_window_cat(cuda_dev):
     assert torch.equal(l1_b.view(7, B, 64, H, W).transpose(0, 1).reshape(B * 7, 64, H, W), l1_a)
     with pytest.raises(_lib.CdfoError):
         m(c["x"], None, mvs, c["pms"], c["rms"], c["ufs"], stale, noise=noise)
+
+
+def test_dual_head_launch_equals_two_launches(cuda_dev):
+    """cdfo_mv_offset_head_dual_sm100_fwd (both evaluations of conv_offset[-1] in one launch, the first kept in registers)
+    writes the same fields, bit for bit, as the two-launch path with its fp16 intermediate in HBM (ragged tiles included)."""
+    from cdfo_b200 import config, hotpath
+    m = _model("O2", cuda_dev)
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 3, 40, 56                      # 40 x 56: partial 16 x 8 tiles on both axes
+    x = torch.randn(1, 64, H, W, generator=g).to(cuda_dev)
+    extra, pred = torch.randn(B, 64, H, W, generator=g).to(cuda_dev), torch.randn(B, 64, H, W, generator=g).to(cuda_dev)
+    flow = (torch.randn(B, 2, H, W, generator=g) * 2).to(cuda_dev)
+    out = {}
+    for dual in (True, False):
+        config.head_dual = dual
+        out[dual] = hotpath.mv_offset_fields(m.MV_deform_align, x, extra, pred, flow)
+    config.head_dual = True
+    assert torch.equal(out[True].view(torch.int16), out[False].view(torch.int16))
