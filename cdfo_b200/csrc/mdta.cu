@@ -312,7 +312,17 @@ struct ApplyParams {
   void *out;              // mode 0: c8 bf16 [2B][8][HW][8]; mode 1: NCHW fp32 [B][64][HW]
   float *ca_partial;      // mode 1: [B][parts][64] channel sums of out
   int H, W, B, x_batch, mode;
+  int nstages;            // 2: input tiles double-buffered by cp.async (H * W % 4 == 0, mode 0); 1: one stage
 };
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -321,28 +331,60 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 
 __global__ void __launch_bounds__(kThreads, 2) mdta_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) float sm[];
-  float *Wt = sm, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
-  float *Mm = Xt + 64 * kLd;         // [3][64][68] TF32 bits
   const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
   const int HW = p.H * p.W;
   const int ntiles = (HW + kTP - 1) / kTP;
   const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
   const int nm = p.mode == 1 ? 3 : 2;
+  float *Mm = sm;                    // [nm][64][68] TF32 bits
+  float *St = Mm + nm * 64 * 68;     // [nstages][nm][64][kLd] input tiles (warped, pred, x); the outputs are staged over them
+  const int stage_f = nm * 64 * kLd;
   for (int e = tid; e < nm * 4096; e += kThreads)
     Mm[(e >> 12) * 64 * 68 + ((e >> 6) & 63) * 68 + (e & 63)] = __uint_as_float(to_tf32(p.mats[(size_t)b * 3 * 4096 + e]));
   const float *wp = p.warped + (size_t)b * 64 * HW, *pr = p.pred + (size_t)b * 64 * HW;
   const float *xs = p.x ? p.x + (size_t)(b % p.x_batch) * 64 * HW : nullptr;
   const int cb = tid >> 5, pg = tid & 31;
+  const bool vec = (HW & 3) == 0;
+  // input tiles arrive by cp.async (16-byte rows); with two stages tile i + 1 is in flight while tile i is multiplied and stored
+  auto load_tile = [&](int tile, float *dst) {
+    const int p0 = tile * kTP, npx = min(kTP, HW - p0);
+    if (vec) {
+      for (int e = tid; e < 64 * (kTP / 4); e += kThreads) {
+        const int c = e / (kTP / 4), q = (e % (kTP / 4)) * 4;
+        const bool ok = q < npx;
+        const size_t o = (size_t)c * HW + p0 + (ok ? q : 0);
+        cp_async16(dst + c * kLd + q, wp + o, ok);
+        cp_async16(dst + 64 * kLd + c * kLd + q, pr + o, ok);
+        if (p.mode == 1) cp_async16(dst + 128 * kLd + c * kLd + q, xs + o, ok);
+      }
+    } else {
+      for (int e = tid; e < 64 * kTP; e += kThreads) {
+        const int c = e >> kTPShift, q = e & (kTP - 1);
+        const bool ok = q < npx;
+        dst[c * kLd + q] = ok ? __ldg(wp + (size_t)c * HW + p0 + q) : 0.f;
+        dst[64 * kLd + c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
+        if (p.mode == 1) dst[128 * kLd + c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+  const bool two = p.nstages == 2;
+  if (two && t0 < t1) load_tile(t0, St);
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int tile = t0; tile < t1; ++tile) {
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
-    __syncthreads();
-    for (int e = tid; e < 64 * kTP; e += kThreads) {
-      const int c = e >> kTPShift, q = e & (kTP - 1);
-      const bool ok = q < npx;
-      Wt[c * kLd + q] = ok ? __ldg(wp + (size_t)c * HW + p0 + q) : 0.f;
-      Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
-      if (p.mode == 1) Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+    float *Wt = St + (two ? ((tile - t0) & 1) * stage_f : 0), *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
+    __syncthreads();       // the stage about to be refilled (two: the other one, used by tile - 1) has no readers left; Mm is complete
+    if (two) {
+      if (tile + 1 < t1) {
+        load_tile(tile + 1, St + ((tile + 1 - t0) & 1) * stage_f);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+    } else {
+      load_tile(tile, St);
+      cp_async_wait<0>();
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -498,11 +540,14 @@ extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, co
   float *partial = ws;
   float *mats = partial + (size_t)B * parts * mdta::stats_len(hc);
   float *warped = mats + (size_t)B * 3 * 4096;
-  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 64 * 132) * 4, smem3 = (size_t)(3 * 64 * mdta::kLd + 3 * 64 * 68) * 4;
+  const int nm = mode == 1 ? 3 : 2;
+  const int nstages = (mode == 0 && (H * W) % 4 == 0) ? 2 : 1;
+  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 64 * 132) * 4;
+  const size_t smem3 = (size_t)(nstages * nm * 64 * mdta::kLd + nm * 64 * 68) * 4, smem3_max = (size_t)(4 * 64 * mdta::kLd + 3 * 64 * 68) * 4;
   static bool attr = false;
   if (!attr) {
     cudaError_t e1 = cudaFuncSetAttribute(mdta::mdta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    cudaError_t e2 = cudaFuncSetAttribute(mdta::mdta_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    cudaError_t e2 = cudaFuncSetAttribute(mdta::mdta_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_max);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return fail(CDFO_ERR_CUDA, "cdfo_mdta_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     attr = true;
@@ -511,7 +556,7 @@ extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, co
   mdta::mdta_stats_kernel<<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
   mdta::AttnParams ap{partial, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, mode == 1 ? fusion_w : nullptr, mats, parts, hc, HW};
   mdta::mdta_attn_kernel<<<B, 256, 0, s>>>(ap);
-  mdta::ApplyParams pp{warped, pred, x, mats, out, ca_sums, H, W, B, x_batch, mode};
+  mdta::ApplyParams pp{warped, pred, x, mats, out, ca_sums, H, W, B, x_batch, mode, nstages};
   mdta::mdta_apply_kernel<<<dim3(parts, B), mdta::kThreads, smem3, s>>>(pp);
   return check_launch("cdfo_mdta_fwd");
 }
