@@ -103,6 +103,15 @@ __device__ __forceinline__ void zero_frags(float (&acc)[2][2][4]) {
       for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
 }
 
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsParams p) {
   extern __shared__ __align__(16) float sm[];
   float *Wt = sm;                    // [64][kLd] warped, later fused
@@ -124,6 +133,17 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
   for (int tile = t0; tile < t1; ++tile) {
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
     __syncthreads();   // previous tile's readers are done (and Wm is complete on the first pass)
+    const bool vec = (HW & 3) == 0;
+    if (vec) {   // pred and x tiles: asynchronous 16-byte copies, in flight while this thread gathers its 16 channels below
+      for (int e = tid; e < 64 * (kTP / 4); e += kThreads) {
+        const int c = e / (kTP / 4), q = (e % (kTP / 4)) * 4;
+        const bool ok = q < npx;
+        const size_t o = (size_t)c * HW + p0 + (ok ? q : 0);
+        cp_async16(Pt + c * kLd + q, pr + o, ok);
+        cp_async16(Xt + c * kLd + q, xs + o, ok);
+      }
+      cp_async_commit();
+    }
     {  // ---- A: gather warped, load pred and x
       const int px = tid & (kTP - 1), part = tid >> kTPShift;   // 4 parts x 16 channels
       const int pp = p0 + px;
@@ -148,27 +168,41 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
         const int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x1, 0), p.W - 1);
         o00 = cy0 * p.W + cx0; o01 = cy0 * p.W + cx1; o10 = cy1 * p.W + cx0; o11 = cy1 * p.W + cx1;
       }
-#pragma unroll 4
-      for (int c = part * 16; c < part * 16 + 16; ++c) {
-        float v = 0.f;
-        if (valid) {
-          const float *plane = ex + (size_t)c * HW;
-          // same accumulation order as grid_sample: nw, ne, sw, se
-          v = __ldg(plane + o00) * nw;
-          v += __ldg(plane + o01) * ne;
-          v += __ldg(plane + o10) * sw;
-          v += __ldg(plane + o11) * se;
-          wo[(size_t)c * HW + pp] = v;
+      // two batches of 8 channels: 32 independent loads in flight per thread (the kernel is latency-bound: 16 warps per SM)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float c00[8], c01[8], c10[8], c11[8];
+        const float *plane0 = ex + (size_t)(part * 16 + half * 8) * HW;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float *plane = plane0 + (size_t)i * HW;
+          c00[i] = valid ? __ldg(plane + o00) : 0.f;
+          c01[i] = valid ? __ldg(plane + o01) : 0.f;
+          c10[i] = valid ? __ldg(plane + o10) : 0.f;
+          c11[i] = valid ? __ldg(plane + o11) : 0.f;
         }
-        Wt[c * kLd + px] = v;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = part * 16 + half * 8 + i;
+          // same accumulation order as grid_sample: nw, ne, sw, se
+          float v = c00[i] * nw;
+          v += c01[i] * ne;
+          v += c10[i] * sw;
+          v += c11[i] * se;
+          if (valid) wo[(size_t)c * HW + pp] = v;
+          Wt[c * kLd + px] = v;
+        }
       }
-      for (int e = tid; e < 64 * kTP; e += kThreads) {
-        const int c = e >> kTPShift, q = e & (kTP - 1);
-        const bool ok = q < npx;
-        Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
-        Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+      if (!vec) {
+        for (int e = tid; e < 64 * kTP; e += kThreads) {
+          const int c = e >> kTPShift, q = e & (kTP - 1);
+          const bool ok = q < npx;
+          Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
+          Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
+        }
       }
     }
+    cp_async_wait<0>();
     __syncthreads();
     // ---- B: row sums of warped / pred / x^2, then fused = Wf [warped; pred]
     if (tid < 192) {
@@ -314,15 +348,6 @@ struct ApplyParams {
   int H, W, B, x_batch, mode;
   int nstages;            // 2: input tiles double-buffered by cp.async (H * W % 4 == 0, mode 0); 1: one stage
 };
-
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const int n = valid ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled, nothing is read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
