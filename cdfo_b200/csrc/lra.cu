@@ -154,10 +154,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__
   // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219): the raw row is read from
   // global once (coalesced along w) into vr[w][c]; then one thread per pixel slides the 9 taps over its 64 channels in place
   const float *vbase = qv + ((size_t)b * 128 + 64) * HW + (size_t)h * W;
+  // (4-byte cp.async: the ~107 copies of a thread are all in flight at once -- with one CTA of 9 warps per SM a load -> store loop
+  // through registers leaves the SM waiting on one DRAM round trip per iteration)
   for (int e = tid; e < 64 * Wk; e += kRowThreads) {
     const int c = e / Wk, w = e - c * Wk;
-    vr[w * kLd + c] = w < W ? __ldg(vbase + (size_t)c * HW + w) : 0.f;
+    const bool ok = w < W;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(vr + w * kLd + c);
+    const float *src = vbase + (size_t)c * HW + (ok ? w : 0);
+    const int nb = ok ? 4 : 0;            // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nb) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int w = tid; w < W; w += kRowThreads) {
     float *row = vr + w * kLd;
@@ -695,14 +703,26 @@ __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__res
   const int b = blockIdx.z, wy = blockIdx.y, wx = blockIdx.x;
   const int HW = H * W;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 64; e += kWinThreads) {
-    const int c = e >> 6, tok = e & 63;                      // tok = dh*8 + dw
+  static_assert(kWinThreads == 256, "one token and 16 + 16 channels per thread");
+  {
+    // a thread owns one token (tok = dh*8 + dw) and channels cg, cg + 4, ...: its 32 loads are issued back to back, then stored
+    const int tok = tid & 63, cg = tid >> 6;
     const int h = wy * 8 + (tok >> 3), w = wx * 8 + (tok & 7);
     const size_t pix = (size_t)h * W + w;
-    float qq = qv[((size_t)b * 128 + c) * HW + pix];
-    if (midx[(size_t)b * HW + pix] == c) qq = 0.f;
-    q[tok * kLd + c] = qq;
-    v[tok * kLd + c] = qv[((size_t)b * 128 + 64 + c) * HW + pix];
+    const int cm = midx[(size_t)b * HW + pix];
+    const float *qp = qv + ((size_t)b * 128 + cg) * HW + pix;
+    float qr[16], vv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      qr[k] = __ldg(qp + (size_t)(4 * k) * HW);
+      vv[k] = __ldg(qp + (size_t)(64 + 4 * k) * HW);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int c = 4 * k + cg;
+      q[tok * kLd + c] = cm == c ? 0.f : qr[k];
+      v[tok * kLd + c] = vv[k];
+    }
   }
   __syncthreads();
   const float *Kcur = q;
