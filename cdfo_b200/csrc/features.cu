@@ -101,6 +101,94 @@ __global__ void __launch_bounds__(256) dwconv3x3_bf16x8_kernel(const __nv_bfloat
   *reinterpret_cast<uint4 *>(y + ((size_t)b * C + c) * H * W + (size_t)h * W + w0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+
+// Per-head Gram matrix and squared norms of the MDTA self-attention (Attention.forward, arch/SIDECVSR_our.py:1545-1576):
+//   G[b][hd][i][j] = sum_p q[b][8 hd + i][p] k[b][8 hd + j][p],   nq[b][c] = sum_p q[b][c][p]^2,   nk likewise,
+// q = channels [0, 64) and k = channels [64, 128) of the depthwise-convolved qkv tensor [B][Ctot][HW].  With them the whole attention is a
+// 64 x 64 matrix per sample (softmax(G / (|q| |k|) T) folded with project_out), applied to v as one batched GEMM: q and k are read ONCE
+// (the ATen chain reads / writes them ~10 times: two norms, two divisions, fp32 copies, a K = H*W skinny GEMM).
+// A CTA reduces a pixel range; partial sums [B][parts][640] = 512 Gram entries + 64 + 64 are added by the caller in fixed order.
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int kN = 4;
+  static __device__ __forceinline__ void load(const float *p, float *o) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *o) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+
+constexpr int kGramLd = 68;
+
+template <typename T>
+__global__ void __launch_bounds__(256) mdta_gram_kernel(const T *__restrict__ qk, float *__restrict__ partial, int Ctot, int HW,
+                                                        int px_per_part, int vec_ok) {
+  __shared__ __align__(16) float tile[128 * kGramLd];     // [128 channels][64 pixels]
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  const int p_begin = part * px_per_part, p_end = min(HW, p_begin + px_per_part);
+  const T *src = qk + (size_t)b * Ctot * HW;
+  // thread -> Gram entries e = tid and tid + 256: head = e / 64, i = (e / 8) % 8, j = e % 8
+  const int e0 = tid, e1 = tid + 256;
+  const float *q0 = tile + ((e0 >> 6) * 8 + ((e0 >> 3) & 7)) * kGramLd, *k0 = tile + (64 + (e0 >> 6) * 8 + (e0 & 7)) * kGramLd;
+  const float *q1 = tile + ((e1 >> 6) * 8 + ((e1 >> 3) & 7)) * kGramLd, *k1 = tile + (64 + (e1 >> 6) * 8 + (e1 & 7)) * kGramLd;
+  float g0 = 0.f, g1 = 0.f, nn = 0.f;
+  constexpr int kN = Vec<T>::kN, kPerRow = 64 / kN, kIters = 128 * kPerRow / 256;
+  for (int p0 = p_begin; p0 < p_end; p0 += 64) {
+    const int npx = min(64, p_end - p0);
+    __syncthreads();
+    if (vec_ok) {      // all of a thread's vector loads are issued before the first store
+      float r[kIters][kN];
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int e = tid + it * 256, c = e / kPerRow, q = (e % kPerRow) * kN;
+        if (q < npx) Vec<T>::load(src + (size_t)c * HW + p0 + q, r[it]);
+        else
+#pragma unroll
+          for (int i = 0; i < kN; ++i) r[it][i] = 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int e = tid + it * 256, c = e / kPerRow, q = (e % kPerRow) * kN;
+#pragma unroll
+        for (int i = 0; i < kN; i += 4) *reinterpret_cast<float4 *>(tile + c * kGramLd + q + i) = make_float4(r[it][i], r[it][i + 1], r[it][i + 2], r[it][i + 3]);
+      }
+    } else {
+      for (int e = tid; e < 128 * 64; e += 256) {
+        const int c = e >> 6, q = e & 63;
+        tile[c * kGramLd + q] = q < npx ? ldf(src + (size_t)c * HW + p0 + q) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < 64; q += 4) {
+      const float4 a = *reinterpret_cast<const float4 *>(q0 + q), c = *reinterpret_cast<const float4 *>(k0 + q);
+      const float4 d = *reinterpret_cast<const float4 *>(q1 + q), f = *reinterpret_cast<const float4 *>(k1 + q);
+      g0 += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+      g1 += d.x * f.x + d.y * f.y + d.z * f.z + d.w * f.w;
+    }
+    if (tid < 128) {
+      const float *row = tile + tid * kGramLd;
+#pragma unroll 4
+      for (int q = 0; q < 64; q += 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(row + q);
+        nn += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      }
+    }
+  }
+  float *out = partial + ((size_t)b * parts + part) * 640;
+  out[e0] = g0;
+  out[e1] = g1;
+  if (tid < 128) out[512 + tid] = nn;
+}
+
 }  // namespace feat
 }  // namespace cdfo
 
@@ -133,4 +221,23 @@ extern "C" int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B,
     feat::dwconv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)x, w, (__nv_bfloat16 *)y, C, H, W);
   else return fail(CDFO_ERR_UNSUPPORTED, "cdfo_dwconv3x3_fwd: dtype must be fp32 or bf16");
   return check_launch("cdfo_dwconv3x3_fwd");
+}
+
+extern "C" int cdfo_mdta_gram_fwd(const void *qk, float *partial, int B, int Ctot, int H, int W, int parts, int dtype, void *stream) {
+  CDFO_REQUIRE(qk && partial, CDFO_ERR_NULL, "cdfo_mdta_gram_fwd: NULL pointer");
+  CDFO_REQUIRE(B > 0 && B <= 65535 && Ctot >= 128 && H > 0 && W > 0 && parts > 0, CDFO_ERR_SHAPE, "cdfo_mdta_gram_fwd: bad shape");
+  const int HW = H * W;
+  int per = ceil_div(ceil_div(HW, parts), 64) * 64;          // pixel ranges are multiples of the 64-pixel tile
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(parts, B);
+  if (dtype == CDFO_F32) {
+    const int vec = HW % 4 == 0 && ((uintptr_t)qk & 15) == 0;
+    feat::mdta_gram_kernel<float><<<grid, 256, 0, s>>>((const float *)qk, partial, Ctot, HW, per, vec);
+  } else if (dtype == CDFO_BF16) {
+    const int vec = HW % 8 == 0 && ((uintptr_t)qk & 15) == 0;
+    feat::mdta_gram_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)qk, partial, Ctot, HW, per, vec);
+  } else {
+    return fail(CDFO_ERR_UNSUPPORTED, "cdfo_mdta_gram_fwd: dtype must be fp32 or bf16");
+  }
+  return check_launch("cdfo_mdta_gram_fwd");
 }

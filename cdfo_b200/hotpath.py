@@ -369,3 +369,17 @@ def dwconv3x3(x, weight):
     _lib.call("cdfo_dwconv3x3_fwd", _lib.ptr(x), _lib.ptr(_f32(weight).reshape(C, 9)), _lib.ptr(y), B, C, H, W, _lib.dtype_code(x),
               _lib.stream_ptr(x.device))
     return y
+
+
+@torch.no_grad()
+def mdta_gram(qkv, parts=64):
+    """Per-head Gram q k^T over H*W and the squared norms of the rows of q and k (8 heads x 8 channels) of the depthwise-convolved
+    qkv tensor [B, 192, H, W] (arch:1545-1576): (G [B, 8, 8, 8], |q|^2 [B, 64], |k|^2 [B, 64]) fp32, q and k read once."""
+    B, C, H, W = qkv.shape
+    if C < 128 or not qkv.is_contiguous():
+        raise _lib.CdfoError("mdta_gram: contiguous [B, >=128, H, W] tensor expected")
+    parts = max(1, min(parts, (H * W + 63) // 64))
+    partial = torch.empty((B, parts, 640), dtype=torch.float32, device=qkv.device)
+    _lib.call("cdfo_mdta_gram_fwd", _lib.ptr(qkv), _lib.ptr(partial), B, C, H, W, parts, _lib.dtype_code(qkv), _lib.stream_ptr(qkv.device))
+    s = partial.sum(1)
+    return s[:, :512].view(B, 8, 8, 8), s[:, 512:576], s[:, 576:640]

@@ -79,6 +79,15 @@ class _SelfMDTA(_Holder):
             qkv = hotpath.dwconv3x3(qkv, self.qkv_dwconv.weight)
         else:
             qkv = self.qkv_dwconv(qkv)
+        if qkv.is_cuda and qkv.dtype in (torch.float32, torch.bfloat16) and c == 64 and self.num_heads == 8 and qkv.is_contiguous():
+            # the attention is one 64 x 64 matrix per sample: softmax(G / (|q| |k|) T) folded with project_out, applied to v as a batched GEMM
+            G, nq, nk = hotpath.mdta_gram(qkv)
+            nq = nq.sqrt().clamp_min(1e-12).view(b, 8, 8, 1)          # F.normalize: x / max(|x|, eps)
+            nk = nk.sqrt().clamp_min(1e-12).view(b, 8, 1, 8)
+            attn = (G / (nq * nk) * self.temperature.float().view(1, 8, 1, 1)).softmax(dim=-1)
+            M = torch.einsum("ohi,bhij->bohj", self.project_out.weight.float().view(64, 8, 8), attn).reshape(b, 64, 64)
+            v = qkv[:, 128:].reshape(b, 64, h * w)
+            return torch.bmm(M.to(v.dtype), v).view(b, 64, h, w)
         q, k, v = qkv.chunk(3, dim=1)
         sh = (b, self.num_heads, c // self.num_heads, h * w)
         q = F.normalize(q.reshape(sh).float(), dim=-1)

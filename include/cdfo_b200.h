@@ -251,6 +251,10 @@ int cdfo_layernorm_c_fwd(const void *x, const float *gamma, const float *beta, v
                          int dtype, void *stream);
 /* depthwise 3x3, stride 1, padding 1, no bias (qkv_dwconv, arch:1545-1576): w [C,1,3,3] fp32. */
 int cdfo_dwconv3x3_fwd(const void *x, const float *w, void *y, int B, int C, int H, int W, int dtype, void *stream);
+/* Per-head Gram matrix and squared norms of the MDTA self-attention (Attention.forward, arch:1545-1576; 8 heads x 8 channels):
+ * qk [B,Ctot,H,W] (dtype fp32 / bf16) with q = channels [0,64), k = [64,128);  partial [B,parts,640] fp32 = per pixel range the 512
+ * entries G[hd][i][j] = sum_p q[8hd+i] k[8hd+j], then sum_p q[c]^2 (64) and sum_p k[c]^2 (64): the caller adds the parts in order. */
+int cdfo_mdta_gram_fwd(const void *qk, float *partial, int B, int Ctot, int H, int W, int parts, int dtype, void *stream);
 /* ---- 3x3 convolutions on a CTA PAIR (csrc/conv3x3_pair_sm100.cu): tcgen05.mma cta_group::2, M = 256 pixels over the two SMs of a
  * TPC, each CTA holding the weights of HALF the output channels resident in shared memory.  Supported: Cout = 64 with Cin in
  * {64, 128, 192, 256} (the trunk's 256 -> 64, conv_expand_fea_r, the 64 -> 64 layers) and 64 -> 256 (the trunk's body.0,
