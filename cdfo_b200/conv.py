@@ -167,6 +167,12 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
         _lib.call("cdfo_conv3x3_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(None),
                   _lib.ptr(y), B, Cin, Cout, H, W, int(act), 1, _lib.stream_ptr(x8.device))
         return y
+    if (config.conv_pair and out_nchw and ks == 3 and not pixel_shuffle and resid8 is None
+            and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)):
+        y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x8.device)
+        _lib.call("cdfo_conv3x3_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(None),
+                  _lib.ptr(y), B, Cin, Cout, H, W, int(act), 2, _lib.stream_ptr(x8.device))
+        return y
     if config.conv_pair and pair_ok:
         y = torch.empty((B, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=x8.device)
         _lib.call("cdfo_conv3x3_pair_sm100_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(resid8),

@@ -40,7 +40,7 @@ struct Params {
   int B, Cin, H, W, act;
   int tiles_x, tiles_y, m_tiles;
   int tma_wide;         // 1: the tensor map merges the pixel and channel axes (a halo row = 80 contiguous elements = one 160-byte request)
-  int y_planes;         // 1: y is stored as its four parity planes [B][2 NH / 8][row parity][column parity][H/2][W/2][8] (H, W even) --
+  int y_planes;         // 2: y is NCHW fp32 [B][2 NH][H][W].  1: y is stored as its four parity planes [B][2 NH / 8][row parity][column parity][H/2][W/2][8] (H, W even) --
                         // the layout from which the 4x4 / stride-2 convolution (conv4x4s2_pair_sm100.cu) loads dense TMA boxes
 };
 
@@ -190,7 +190,7 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       const bool live = valid && h < p.H && w < p.W;
       const size_t pix = (size_t)h * p.W + w;
       // parity planes: pixel (h, w) -> plane (h & 1, w & 1), position (h / 2, w / 2); a chunk still spans H * W pixels
-      const size_t opix = p.y_planes ? (size_t)((h & 1) * 2 + (w & 1)) * (HW >> 2) + (size_t)(h >> 1) * (p.W >> 1) + (w >> 1) : pix;
+      const size_t opix = p.y_planes == 1 ? (size_t)((h & 1) * 2 + (w & 1)) * (HW >> 2) + (size_t)(h >> 1) * (p.W >> 1) + (w >> 1) : pix;
       ptx::mbar_wait(BAR(8 + acc), acc_phase);
       ptx::tc_fence_after();
       // the two warps of a TMEM lane quarter take alternate 16-column chunks; 16 channels = two c8 chunks of 16 bytes per pixel
@@ -227,6 +227,12 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
               v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
             }
           }
+        }
+        if (p.y_planes == 2) {               // NCHW fp32 (consumers that still read fp32 planes: the MDTA statistics kernel)
+          float *yf = reinterpret_cast<float *>(p.y) + ((size_t)b * kN + c0) * HW + pix;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) yf[(size_t)i * HW] = v[i];
+          continue;
         }
         uint4 *y = p.y + ((size_t)b * (kN / 8) + c0 / 8) * HW + opix;
         y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
@@ -323,7 +329,7 @@ extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, co
 extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
                                                   int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv3x3_pair_sm100_fwd: NULL pointer");
-  CDFO_REQUIRE(y_planes == 0 || (y_planes == 1 && H % 2 == 0 && W % 2 == 0), CDFO_ERR_SHAPE,
+  CDFO_REQUIRE(y_planes == 0 || y_planes == 2 || (y_planes == 1 && H % 2 == 0 && W % 2 == 0), CDFO_ERR_SHAPE,
                "cdfo_conv3x3_pair_sm100_planes_fwd: the parity-plane output needs an even size (got %d x %d)", H, W);
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_conv3x3_pair_sm100_fwd: bad shape");
   CDFO_REQUIRE(cdfo_conv3x3_pair_sm100_supported(Cout, Cin), CDFO_ERR_UNSUPPORTED, "cdfo_conv3x3_pair_sm100_fwd: unsupported channels %d -> %d", Cin, Cout);

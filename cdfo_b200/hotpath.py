@@ -372,7 +372,7 @@ def dwconv3x3(x, weight):
 
 
 @torch.no_grad()
-def mdta_gram(qkv, parts=64):
+def mdta_gram(qkv, parts=256):
     """Per-head Gram q k^T over H*W and the squared norms of the rows of q and k (8 heads x 8 channels) of the depthwise-convolved
     qkv tensor [B, 192, H, W] (arch:1545-1576): (G [B, 8, 8, 8], |q|^2 [B, 64], |k|^2 [B, 64]) fp32, q and k read once."""
     B, C, H, W = qkv.shape

@@ -200,3 +200,21 @@ def test_conv1x1_sm100(cuda_dev, B, Cin, Cout, H, W):
     err = (y - ref).abs().max().item()
     print("conv1x1 %s: max err %.3g (max|ref| %.3g)" % ((B, Cin, Cout, H, W), err, ref.abs().max().item()))
     assert err <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 128, 64, 33, 21), (1, 64, 256, 24, 40), (3, 64, 64, 64, 64)])
+def test_conv3x3_pair_nchw_output_equals_single_sm(cuda_dev, B, Cin, Cout, H, W):
+    """NCHW fp32 output of the CTA-pair convolution (conv_expand_fea_r feeds the MDTA statistics kernel in fp32) = the single-SM
+    kernel's, bit for bit (same fp32 accumulation order)."""
+    from cdfo_b200 import config, conv
+    g = torch.Generator().manual_seed(B * Cin + H)
+    x8 = conv.to_c8(torch.randn(B, Cin, H, W, generator=g).to(cuda_dev))
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(cuda_dev)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(cuda_dev)
+    y_pair = conv.conv3x3(x8, w, b, conv.ACT_LRELU, out_nchw=True)
+    config.conv_pair = False
+    try:
+        y_one = conv.conv3x3(x8, w, b, conv.ACT_LRELU, out_nchw=True)
+    finally:
+        config.conv_pair = True
+    assert y_pair.dtype == torch.float32 and torch.equal(y_pair, y_one)
