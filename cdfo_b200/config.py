@@ -20,9 +20,10 @@ conv_fold_half = os.environ.get("CDFO_CONV_FOLD_HALF", "1") != "0"
 
 # With conv_fold_half: True = the 2x-resolution intermediate of that branch is written by the 64 -> 256 convolution as its four parity
 # planes ([B, C/8, 2, 2, H, W, 8]), so every stride-2 phase window of the folded convolution is a dense TMA box; False = plain c8,
-# loaded with elementStrides = 2.  Measured (tools/bench_conv.py): no gain for the folded convolution once its streamed weights arrive
-# as 512-byte TMA rows (212 us either way at 2 x 544x960), and the producer's scattered stores cost 5 % -- kept as an option, off.
-conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "0") != "0"
+# loaded with elementStrides = 2 (every 16-byte pixel chunk drags a 32-byte L2 sector: 1.85 GB instead of 1.16 GB of L2 -> SM traffic per
+# launch at 2 x 544x960).  Measured (tools/bench_conv.py) once the MMA issuer stopped being the bottleneck: 193.6 -> 153.8 us for the
+# folded convolution against +16 us for the producer's scattered stores.
+conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "1") != "0"
 
 # Offset / mask head of MVDualAttAlignment: True = both evaluations of conv_offset[-1] in one launch (the first one stays in the
 # epilogue's registers, cdfo_mv_offset_head_dual_sm100_fwd); False = two launches with the intermediate fields in HBM.

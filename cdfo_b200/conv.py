@@ -159,7 +159,9 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
     b = None if bias is None else bias.detach().contiguous().float()
     if resid8 is not None and (resid8.shape != (B, Cout // 8, H, W, 8) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
         raise _lib.CdfoError("conv3x3: residual must be a contiguous bf16 c8 tensor of the output shape")
-    pair_ok = ks == 3 and not pixel_shuffle and not out_nchw and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)
+    # 64 -> 64 has one K block per tile: the single-SM kernel is faster there (795 vs 621 TFLOP/s); parity_planes forces the pair kernel
+    pair_shape = _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin) and (parity_planes or not (Cin == 64 and Cout == 64))
+    pair_ok = ks == 3 and not pixel_shuffle and not out_nchw and pair_shape
     if parity_planes:
         if not pair_ok or resid8 is not None or H % 2 or W % 2:
             raise _lib.CdfoError("conv3x3: parity_planes needs a CTA-pair shape (3x3, %d -> %d), an even size and no residual" % (Cin, Cout))
@@ -167,8 +169,7 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
         _lib.call("cdfo_conv3x3_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(None),
                   _lib.ptr(y), B, Cin, Cout, H, W, int(act), 1, _lib.stream_ptr(x8.device))
         return y
-    if (config.conv_pair and out_nchw and ks == 3 and not pixel_shuffle and resid8 is None
-            and _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin)):
+    if config.conv_pair and out_nchw and ks == 3 and not pixel_shuffle and resid8 is None and pair_shape:
         y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x8.device)
         _lib.call("cdfo_conv3x3_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(None),
                   _lib.ptr(y), B, Cin, Cout, H, W, int(act), 2, _lib.stream_ptr(x8.device))

@@ -142,16 +142,19 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           ptx::mbar_wait(BAR(stage), phase);
           ptx::tc_fence_after();
           if (lane == 0) {
-            const uint32_t a0 = ptx::smem_u32(asmem) + stage * kABytes;
-#pragma unroll 1
+            // descriptors of (tap 0, K step 0) once per stage; every MMA then adds compile-time constants to the low words
+            const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(asmem) + stage * kABytes, kPlane, kSbo);
+            const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(wsm) + kb * kPiece, kNH * 16, 128);
+            const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32), b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t b_tap_step = (uint32_t)(KB * kPiece) >> 4;
+            const uint32_t tmem_d = tmem_base + acc * kAccCols;
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a0 + ((tap / 3) * kHaloW + (tap % 3)) * 16;
-              const uint32_t b_tap = ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kPlane, kPlane, kSbo);
-                const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (kNH * 16), kNH * 16, 128);
-                umma_f16_2sm(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
+                const uint32_t a_lo = a_lo0 + ((((tap / 3) * kHaloW + (tap % 3)) * 16 + j * 2 * kPlane) >> 4);
+                const uint32_t b_lo = b_lo0 + tap * b_tap_step + ((j * 2 * (kNH * 16)) >> 4);
+                umma_f16_2sm_w(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, (tap | j) != 0 ? 1u : (uint32_t)(kb != 0));
               }
             }
             umma_commit_pair(BAR(4 + stage));

@@ -179,15 +179,19 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t a0 = ptx::smem_u32(asmem) + stage * stage_stride;
-#pragma unroll 1
+          // descriptors once per stage; every MMA adds constants to the low words (at N <= 64 the issuing thread is the critical path)
+          const uint64_t ad0 = ptx::make_smem_desc(a0, G::kPlane, G::kSbo);
+          const uint64_t bd0 = ptx::make_smem_desc(p.stream_w ? a0 + kABytes : ptx::smem_u32(wsm) + kb * kPiece, NT * 16, 128);
+          const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32), b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+          const uint32_t b_tap_step = (uint32_t)((p.stream_w ? 1 : KB) * kPiece) >> 4;
+          const uint32_t tmem_d = tmem_base + acc * kAccCols;
+#pragma unroll
           for (int tap = 0; tap < kTaps; ++tap) {
-            const uint32_t a_tap = a0 + ((tap / KS) * G::kHaloW + (tap % KS)) * 16;
-            const uint32_t b_tap = p.stream_w ? a0 + kABytes + tap * kPiece : ptx::smem_u32(wsm) + (tap * KB + kb) * kPiece;
 #pragma unroll
             for (int j = 0; j < KBLK / 16; ++j) {
-              const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * G::kPlane, G::kPlane, G::kSbo);
-              const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (NT * 16), NT * 16, 128);
-              ptx::umma_f16(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
+              const uint32_t a_lo = a_lo0 + ((((tap / KS) * G::kHaloW + (tap % KS)) * 16 + j * 2 * G::kPlane) >> 4);
+              const uint32_t b_lo = b_lo0 + tap * b_tap_step + ((j * 2 * (NT * 16)) >> 4);
+              ptx::umma_f16_w(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, (tap | j) != 0 ? 1u : (uint32_t)(kb != 0));
             }
           }
           ptx::umma_commit(BAR(4 + stage));

@@ -145,19 +145,21 @@ conv4x4s2_pair_sm100_kernel(const __grid_constant__ CUtensorMap xmap, const __gr
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t a0 = stage0 + stage * kStageBytes, b0 = a0 + kAStage;
-#pragma unroll 1
+            // descriptors once per stage; every MMA adds compile-time constants to the low words (the issuing thread is the critical path)
+            const uint64_t ad0 = ptx::make_smem_desc(a0, kPlane, kSbo), bd0 = ptx::make_smem_desc(b0, kNH * 16, 128);
+            const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32), b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t tmem_d = tmem_base + acc * kAccCols;
+#pragma unroll
             for (int tap = 0; tap < 16; ++tap) {
               // tap (ui, vi), u = ui - 1: parity a = u & 1, window row offset m' = (u + a) / 2 (same for columns)
               const int ui = tap >> 2, vi = tap & 3;
               const int pa = (ui + 1) & 1, pb = (vi + 1) & 1;
               const int mr = (ui - 1 + pa) >> 1, mc = (vi - 1 + pb) >> 1;
-              const uint32_t a_tap = a0 + (pa * 2 + pb) * kPhaseStride + (mr * kPW + mc) * 16;
-              const uint32_t b_tap = b0 + tap * kTapBytes;
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint64_t ad = ptx::make_smem_desc(a_tap + j * 2 * kPlane, kPlane, kSbo);
-                const uint64_t bd = ptx::make_smem_desc(b_tap + j * 2 * (kNH * 16), kNH * 16, 128);
-                umma_f16_2sm(tmem_base + acc * kAccCols, ad, bd, idesc, (kb | tap | j) != 0);
+                const uint32_t a_lo = a_lo0 + (((pa * 2 + pb) * kPhaseStride + (mr * kPW + mc) * 16 + j * 2 * kPlane) >> 4);
+                const uint32_t b_lo = b_lo0 + ((tap * kTapBytes + j * 2 * (kNH * 16)) >> 4);
+                umma_f16_2sm_w(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, (tap | j) != 0 ? 1u : (uint32_t)(kb != 0));
               }
             }
             umma_commit_pair(BAR(4 + stage));

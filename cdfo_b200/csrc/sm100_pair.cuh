@@ -39,6 +39,22 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
       : "memory");
 }
+// Same with the shared-memory descriptors passed as (lo, hi) words.  The issuing thread is the kernel's critical path at N = 64 (an
+// MMA retires every ~32 clocks): with the descriptors rebuilt per MMA it spent ~16 uniform-datapath instructions per MMA and the
+// tensor pipe sat at 30 %.  lo holds the 14-bit start address (>> 4) and the leading-dimension offset, hi the stride offset and the
+// version bit: advancing the operand is ONE 32-bit add of a compile-time constant.
+__device__ __forceinline__ void umma_f16_2sm_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
 // arrive (count 1) on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   const uint16_t mask = 3;
