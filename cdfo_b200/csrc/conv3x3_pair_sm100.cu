@@ -141,7 +141,7 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(BAR(stage), phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {       // one elected lane: no per-thread waterfall around the uniform-operand MMAs
             // descriptors of (tap 0, K step 0) once per stage; every MMA then adds compile-time constants to the low words
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(asmem) + stage * kABytes, kPlane, kSbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(wsm) + kb * kPiece, kNH * 16, 128);

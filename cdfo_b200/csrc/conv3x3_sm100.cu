@@ -177,7 +177,7 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
       for (int kb = 0; kb < KB; ++kb) {
         ptx::mbar_wait(BAR(stage), phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {       // one elected lane: no per-thread waterfall around the uniform-operand MMAs
           const uint32_t a0 = ptx::smem_u32(asmem) + stage * stage_stride;
           // descriptors once per stage; every MMA adds constants to the low words (at N <= 64 the issuing thread is the critical path)
           const uint64_t ad0 = ptx::make_smem_desc(a0, G::kPlane, G::kSbo);

@@ -143,7 +143,7 @@ conv4x4s2_pair_sm100_kernel(const __grid_constant__ CUtensorMap xmap, const __gr
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(BAR(stage), phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {       // one elected lane: no per-thread waterfall around the uniform-operand MMAs
             const uint32_t a0 = stage0 + stage * kStageBytes, b0 = a0 + kAStage;
             // descriptors once per stage; every MMA adds compile-time constants to the low words (the issuing thread is the critical path)
             const uint64_t ad0 = ptx::make_smem_desc(a0, kPlane, kSbo), bd0 = ptx::make_smem_desc(b0, kNH * 16, 128);

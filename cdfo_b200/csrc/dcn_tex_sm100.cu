@@ -182,7 +182,7 @@ dcn_tex_sm100_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         for (int tap = 0; tap < 9; ++tap) {
           ptx::mbar_wait(BAR(stage), phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint32_t a0 = tmem_base + kAColBase + stage * kAColsPerStage;   // A operand of this tap lives in TMEM
             const uint32_t b0 = ptx::smem_u32(wsm) + tap * kTapWBytes;
 #pragma unroll

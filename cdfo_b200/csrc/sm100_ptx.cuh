@@ -115,6 +115,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// true in exactly one lane of a converged warp (elect.sync): unlike `lane == 0` the compiler knows the guarded region is executed by ONE
+// thread, so uniform-operand instructions (tcgen05.mma, tcgen05.commit) need no per-thread waterfall loop around them
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Same with the descriptors as (lo, hi) words (see sm100_pair.cuh: one 32-bit add per MMA advances an operand).
 __device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                            uint32_t accumulate) {
