@@ -150,9 +150,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line of the contract
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to STDOUT: send its log to stderr, stdout is the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert cdfo_b200._lib.lib().cdfo_device_ok(local) == 1, "not an sm_100 device"
 
