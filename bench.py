@@ -294,7 +294,9 @@ def run_ours(args):
                     "%d px per launch; this build moves 1408 B/px (fp16 x 128, packed fp16x4 fields 1152 staged by TMA, bf16 y 128 "
                     "written straight into tsa_fusion's stacked input); traffic = dram bytes per px of the ncu --set full capture "
                     "(profiles/r01_dcn_tex_tma_fields_ncu.md) scaled to this launch; the binding resource is the L1TEX data stage "
-                    "(texture wavefronts alone put the floor at frac 0.68), see DESIGN.md 3.1" % px,
+                    "(texture wavefronts alone put the floor at frac 0.68), see DESIGN.md 3.1; that stage runs at the SM clock, so inside "
+                    "this power-capped step (see clocks.sm_mhz) the kernel is slower than timed alone at full clock "
+                    "(tools/bench_dcn.py: 278 us for 6 calls = frac 0.48)" % px,
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
