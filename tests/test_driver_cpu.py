@@ -99,3 +99,26 @@ def test_conversion_oracles():
     assert y.shape == (3, 4) and y[0, 3] == 1.0 and y[1:].sum() == 0 and y[0, 1] == np.float32(1) / np.float32(255)
     sr = np.array([[-0.5, 0.0, 0.999, 1.0, 7.0, 0.5]], np.float32)
     assert R.sr_to_u8(sr, 1).tolist() == [[0, 0, 254, 255, 255, 127]]               # truncation, not rounding
+
+
+def test_feature_ring_window_order_and_wraparound():
+    """model.FeatureRing (host logic, runs on CPU tensors): after k pushes the window is the last N frames in temporal order,
+    contiguous, with the centre frame and the two neighbour runs as views, for more pushes than there are slots."""
+    import torch
+    from cdfo_b200.model import FeatureRing
+    B, N, C, H, W = 2, 7, 3, 4, 5
+    frames = [torch.full((B, C, H, W), float(t)) + torch.arange(B).view(B, 1, 1, 1) * 0.5 for t in range(N + 11)]
+    l1 = torch.stack(frames[:N], 1).reshape(B * N, C, H, W)            # the reference's b-major [B*N, C, H, W]
+    ring = FeatureRing(l1, B, N)
+    handle = ring.handle()
+    for t in range(N, N + 11):
+        win = ring.window()
+        assert win.is_contiguous() and tuple(win.shape) == (N, B, C, H, W)
+        for n in range(N):
+            assert torch.equal(win[n], frames[t - N + n])
+        assert handle._cdfo_ring[1] == ring.serial
+        ring.push(frames[t])
+        assert handle._cdfo_ring[1] != ring.serial                        # the old handle is stale now
+        handle = ring.handle()
+        assert handle.data_ptr() == ring.window().data_ptr() and tuple(handle.shape) == (N * B, C, H, W)
+    assert torch.equal(ring.window()[N - 1], frames[N + 10])
