@@ -34,8 +34,6 @@ METRIC = "HR frames/sec, 1080p x4 LD-QP37"
 UNIT = "frames/s"
 LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
 ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
-# dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture (profiles/r01_dcn_tex_tma_fields_ncu.md), per LR pixel
-NCU_TRAFFIC_BYTES_PER_PX = (1.005385e9 + 95.661e6) / (6 * 272 * 480)
 
 
 def peaks():
@@ -81,59 +79,86 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_fps(sample_hw, steps, warmup, variant="O2"):
-    """Oracle port of the reference forward on the host cores: fps of steady-state frames on an LR crop of
-    `sample_hw`, scaled to the full 272x480 frame by the pixel ratio."""
+def cpu_reference_frames(hw, steps, warmup, budget_s, variant="O2"):
+    """The reference's algorithm (oracle/torch_ref.py: fp32 torch CPU ops + torchvision's CPU deform_conv2d, 0-diff against the real
+    reference at this very configuration, tests/golden/model_c3_golden.npz `port_err`) on the host cores: FULL steady-state frames
+    of one sequence at LR size `hw` -- nothing is cropped or extrapolated.  One untimed first frame builds the L1 cache, then up to
+    `warmup` untimed and `steps` timed cached frames, stopping early once `budget_s` seconds are spent (at least one timed frame).
+    Returns (list of seconds per timed frame, warm-ups done, cores)."""
     import torch
     from cdfo_b200 import synthetic
     from oracle import priors_ref, torch_ref
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    H, W = sample_hw
+    H, W = hw
     from cdfo_b200.model import CVSR_V8
     tmpl = CVSR_V8(alignment="mv_dcn" if variant == "O2" else "dual_att").state_dict()
     sd = synthetic.seeded_state_dict(tmpl, seed=4)
     clip = synthetic.make_clip(1, H, W, 1)
     mvs = torch.from_numpy(priors_ref.mv2mvs_model_layout(clip["mv_l0"][0].numpy()))
     noise = synthetic.gumbel_uniforms(4, 0, 0, 1, H, W)
+    t_start = time.perf_counter()
+    times, warm_done = [], 0
     with torch.no_grad():
         _, l1 = torch_ref.cvsr_v8_forward(sd, clip["x"], mvs, clip["pms"], clip["rms"], clip["ufs"], None, noise, variant)
-        times = []
-        for it in range(warmup + steps):
+        first = time.perf_counter() - t_start
+        est = first
+        while len(times) < steps:
+            spent = time.perf_counter() - t_start
+            timed = warm_done >= warmup or spent + 2.0 * est > budget_s     # out of budget for more warm-up: time this one
+            if times and spent + est > budget_s:
+                break
             t0 = time.perf_counter()
             _, l1 = torch_ref.cvsr_v8_forward(sd, clip["x"], mvs, clip["pms"], clip["rms"], clip["ufs"], l1, noise, variant)
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    scale = (H * W) / float(LR_H * LR_W)
-    return scale / sec, cores, sec
+            est = time.perf_counter() - t0
+            if timed:
+                times.append(est)
+            else:
+                warm_done += 1
+    return times, warm_done, cores, first
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    fps, cores, sec = cpu_reference_fps((136, 240), steps, warmup)
-    sample = ("oracle port (oracle/torch_ref.py, fp32, torch CPU ops + torchvision deform_conv2d) of the same "
-              "steady-state forward on a 136x240 LR crop (1/4 of the 272x480 frame): %.2f s per frame, fps scaled by "
-              "1/4; %d timed steps" % (sec, steps))
+    H, W = args.lr_h, args.lr_w
+    times, warm_done, cores, first = cpu_reference_frames((H, W), max(1, args.steps), max(0, args.warmup), args.cpu_budget_s, args.variant)
+    sec = sum(times) / len(times)
+    fps = 1.0 / sec
+    capped = len(times) < args.steps or warm_done < args.warmup
+    sample = ("oracle port (oracle/torch_ref.py, fp32, torch CPU ops + torchvision deform_conv2d; equals the real reference to 0 diff at "
+              "this configuration) of the steady-state forward on FULL %dx%d LR frames of one sequence: %d timed frame(s) after %d "
+              "warm-up(s) (+ one cache-building first frame, %.1f s), %.2f s per frame (min %.2f, max %.2f)%s"
+              % (H, W, len(times), warm_done, first, sec, min(times), max(times),
+                 "; --steps %d / --warmup %d were cut by the %d s time cap (--cpu-budget-s)" % (args.steps, args.warmup, args.cpu_budget_s) if capped else ""))
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps * args.gpus, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup, "time_capped": capped,
+        "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CVSR_V8+MVDualAttAlignment (O2), 7x(480x270->272 rows) LR -> 1920x1080 HR, LD priors, "
-                               "steady state (cached L1_fea)", "host": "CPU"},
+        "config": {"workload": "CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, LD priors, "
+                               "steady state (cached L1_fea)" % args.variant, "lr": [H, W], "host": "CPU",
+                   "step": "one HR frame of one sequence (the CPU path has no batch to amortise; ours steps %d sequences at once)" % args.seqs},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": fps * args.gpus, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if args.gpus > 1:
-        line["config"]["note"] = "CPU arm runs on rank 0 only; value = one host's fps x n_gpus is NOT claimed: see cpu_baseline"
-        line["value"] = fps
-        line["e2e"]["value"] = fps
+        line["config"]["note"] = "the CPU arm runs on rank 0's host only: value is ONE host, not multiplied by n_gpus"
     print(json.dumps(line), flush=True)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per LR pixel of the roofline kernel, read from the newest per-round capture summary
+    profiles/r??_roofline_kernel_traffic.json (written by tools/ncu_traffic.py from an `ncu --set full` .ncu-rep).  No constant in
+    this file: a missing summary fails loudly."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r??_roofline_kernel_traffic.json")))
+    if not files:
+        raise SystemExit("bench.py: no profiles/r??_roofline_kernel_traffic.json (run tools/ncu_traffic.py on this round's ncu capture)")
+    d = json.load(open(files[-1]))
+    return d, os.path.relpath(files[-1], ROOT)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -278,6 +303,7 @@ def run_ours(args):
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
+        traffic, traffic_src = ncu_traffic()
         durs = [a.elapsed_time(b) * 1e-3 for a, b, _, _ in dcn_log]           # seconds per launch
         px = dcn_log[0][2] if dcn_log else 0
         per_px = ALGO_BYTES_PER_PX_BF16
@@ -287,7 +313,7 @@ def run_ours(args):
                  if cdfo_b200.config.dcn_gather == "tex" else "dcn_sm100_kernel (tcgen05 implicit-GEMM DCNv2, LDG gather)")
         roof = {
             "kernel": kname, "bound": "hbm",
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_PX * px if NCU_TRAFFIC_BYTES_PER_PX else None,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic["dram_bytes_per_px"] * px, "traffic_source": traffic_src,
             "peak_source": peak_src, "avg_launch_us": avg * 1e6, "launches_timed": len(durs),
             "algorithmic_bytes_per_launch": per_px * px,
             "note": "algorithmic bytes = SURVEY 8d's 1120 B per LR pixel and neighbour call (x 128 + offset 576 + mask 288 + y 128) x "
@@ -300,10 +326,12 @@ def run_ours(args):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            fps_cpu, cores, sec = cpu_reference_fps((72, 120), 1, 0, args.variant)
-            cpu = {"value": fps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle port (oracle/torch_ref.py, fp32 torch CPU) of one steady-state frame on a 72x120 LR "
-                             "crop (1/15 of 272x480): %.2f s, fps scaled by the pixel ratio" % sec}
+            times, warm_done, cores, first = cpu_reference_frames((H, W), 3, 1, args.cpu_baseline_budget_s, args.variant)
+            med = sorted(times)[len(times) // 2]
+            cpu = {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle port (oracle/torch_ref.py, fp32 torch CPU) of the steady-state forward on FULL %dx%d LR frames of ONE "
+                             "sequence: median of %d timed frame(s) after %d warm-up(s) (+ one cache-building first frame, %.1f s): %.2f s "
+                             "per frame, nothing cropped or scaled" % (H, W, len(times), warm_done, first, med)}
         value = total_frames / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -335,6 +363,8 @@ def main():
     ap.add_argument("--lr-h", type=int, default=LR_H)
     ap.add_argument("--lr-w", type=int, default=LR_W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=int, default=200, help="--impl reference: wall-clock cap of the CPU run (full frames; steps / warm-ups beyond it are dropped and the line says so)")
+    ap.add_argument("--cpu-baseline-budget-s", type=int, default=80, help="cap of the in-arm cpu_baseline leg (full frames, rank 0, N = 1)")
     ap.add_argument("--graph", type=int, default=0, help="1: replay the steady-state step as a CUDA graph (+1.7 %); 0 (default): eager "
                     "launches, which is what lets the DCN kernel be timed live with CUDA events inside the timed region")
     args = ap.parse_args()

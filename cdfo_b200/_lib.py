@@ -5,6 +5,7 @@ missing, or a call returns a non-zero status, this raises.
 """
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -86,3 +87,26 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             # the reference raises NotImplementedError for CPU tensors (deform_conv.py:46-47,136-137)
             raise NotImplementedError("cdfo_b200 ops are CUDA-only (got a %s tensor)" % t.device)
+
+
+class TensorCache:
+    """Derived tensors (packed / permuted weights) keyed by the SOURCE tensor object: an entry is valid only while that very object is
+    alive (weak reference identity, never id() alone -- CPython reuses freed addresses) with the same storage address, device and
+    in-place version; entries of collected tensors are dropped by the weak reference's callback, so nothing outlives its model."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, t, build, kind=None):
+        key = (id(t), kind)
+        sig = (t.data_ptr(), str(t.device), t._version, t.dtype)
+        hit = self._d.get(key)
+        if hit is not None and hit[0]() is t and hit[1] == sig:
+            return hit[2]
+        val = build()
+        d = self._d
+        self._d[key] = (weakref.ref(t, lambda _r, k=key: d.pop(k, None)), sig, val)
+        return val
+
+    def __len__(self):
+        return len(self._d)

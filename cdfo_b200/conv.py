@@ -1,12 +1,10 @@
 """Host side of the tcgen05 3x3 convolution (cdfo_conv3x3_sm100_fwd) and of the c8 layout adapters."""
-import weakref
-
 import torch
 
 from . import _lib, config
 
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-_wcache = {}
+_wcache = _lib.TensorCache()
 
 
 @torch.no_grad()
@@ -36,10 +34,10 @@ def from_c8(x8: torch.Tensor) -> torch.Tensor:
 @torch.no_grad()
 def pack_weight(weight: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, k, k] (k = 1 or 3) -> packed bf16 B operand (cached per parameter / version)."""
-    key = id(weight)
-    hit = _wcache.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        return hit[2]
+    return _wcache.get(weight, lambda: _pack_weight(weight))
+
+
+def _pack_weight(weight):
     Cout, Cin, ks = weight.shape[:3]
     if ks not in (1, 3) or weight.shape[3] != ks:
         raise _lib.CdfoError("conv_sm100: kernel size 1 or 3 expected, got %s" % (tuple(weight.shape[2:]),))
@@ -49,20 +47,19 @@ def pack_weight(weight: torch.Tensor) -> torch.Tensor:
     w = weight.detach().contiguous().float()
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
     _lib.call("cdfo_conv_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, int(ks), _lib.stream_ptr(w.device))
-    _wcache[key] = (weakref.ref(weight), weight._version, out)
     return out
 
 
-_wcache_pair = {}
+_wcache_pair = _lib.TensorCache()
 
 
 @torch.no_grad()
 def pack_weight_pair(weight: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> the CTA-pair kernel's B operand [2 halves][9][Cin/8][Cout/2][8] bf16 (cached per parameter / version)."""
-    key = id(weight)
-    hit = _wcache_pair.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        return hit[2]
+    return _wcache_pair.get(weight, lambda: _pack_weight_pair(weight))
+
+
+def _pack_weight_pair(weight):
     Cout, Cin = weight.shape[:2]
     nbytes = _lib.lib().cdfo_conv3x3_pair_sm100_weight_bytes(Cout, Cin)
     if nbytes == 0:
@@ -70,11 +67,10 @@ def pack_weight_pair(weight: torch.Tensor) -> torch.Tensor:
     w = weight.detach().contiguous().float()
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
     _lib.call("cdfo_conv3x3_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cout, Cin, _lib.stream_ptr(w.device))
-    _wcache_pair[key] = (weakref.ref(weight), weight._version, out)
     return out
 
 
-_wcache_4x4 = {}
+_wcache_4x4 = _lib.TensorCache()
 
 
 @torch.no_grad()
@@ -95,15 +91,12 @@ def conv3x3_then_half(x8, weight, bias=None, resid8=None):
         raise _lib.CdfoError("conv3x3_then_half: unsupported shape %s on %s" % (tuple(weight.shape), tuple(x8.shape)))
     if x8.dtype != torch.bfloat16 or not x8.is_contiguous():
         raise _lib.CdfoError("conv3x3_then_half: input must be a contiguous bf16 c8 tensor")
-    key = id(weight)
-    hit = _wcache_4x4.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        wpk = hit[2]
-    else:
+    def pack():
         w = weight.detach().contiguous().float()
-        wpk = torch.empty(_lib.lib().cdfo_conv4x4s2_pair_sm100_weight_bytes(Cin) // 2, dtype=torch.bfloat16, device=w.device)
-        _lib.call("cdfo_conv4x4s2_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(wpk), Cin, _lib.stream_ptr(w.device))
-        _wcache_4x4[key] = (weakref.ref(weight), weight._version, wpk)
+        out = torch.empty(_lib.lib().cdfo_conv4x4s2_pair_sm100_weight_bytes(Cin) // 2, dtype=torch.bfloat16, device=w.device)
+        _lib.call("cdfo_conv4x4s2_pair_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), Cin, _lib.stream_ptr(w.device))
+        return out
+    wpk = _wcache_4x4.get(weight, pack)
     y = torch.empty((B, Cout // 8, Hi // 2, Wi // 2, 8), dtype=torch.bfloat16, device=x8.device)
     if resid8 is not None and (tuple(resid8.shape) != tuple(y.shape) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
         raise _lib.CdfoError("conv3x3_then_half: residual must be a contiguous bf16 c8 tensor of the output shape")
@@ -113,20 +106,14 @@ def conv3x3_then_half(x8, weight, bias=None, resid8=None):
     return y
 
 
-_derived = {}
+_derived = _lib.TensorCache()
 
 
 @torch.no_grad()
 def derived(param, kind, fn):
     """fn(param) cached per (parameter, version, kind): weights re-laid-out for a kernel (PixelShuffle channel
     order, padded output channels, composed 1x1 o 3x3 ...).  The result then has its own pack_weight entry."""
-    key = (id(param), kind)
-    hit = _derived.get(key)
-    if hit is not None and hit[0]() is param and hit[1] == param._version:
-        return hit[2]
-    out = fn(param.detach())
-    _derived[key] = (weakref.ref(param), param._version, out)
-    return out
+    return _derived.get(param, lambda: fn(param.detach()), kind)
 
 
 def centre_tap(w):

@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "cdfo_common.cuh"
 #include "sm100_ptx.cuh"
@@ -429,22 +430,34 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 static bool g_no_tma_fields = false;   // cdfo_dcn_tex_sm100_set_fields_path: A/B switch for tools/bench_dcn.py
 
-// ---- texture objects over caller-owned linear memory, cached by (device, pointer, shape) ----
-struct TexEntry { int dev; const void *ptr; int rows, Wpt; cudaTextureObject_t tex; unsigned long long stamp; };
+// ---- texture objects over caller-owned linear memory, cached by (device, pointer, rows, W, pitch) ----
+// A handle is a descriptor only (it owns no memory), but it may be baked into a captured CUDA graph or be in use by kernels still
+// queued on any stream, so it is never destroyed behind the caller's back: handles created while the launching stream is being
+// captured are pinned for the life of the process, and the cache only evicts (oldest unpinned entry first) once it holds
+// kTexCacheMax descriptors, and then only after cudaDeviceSynchronize() -- never while a capture is in progress, in which case
+// the cache simply grows.
+struct TexEntry { int dev; const void *ptr; int rows, W, Wpt; cudaTextureObject_t tex; unsigned long long stamp; bool pinned; };
 static std::mutex g_mu;
-static TexEntry g_cache[64];
-static int g_cache_n = 0;
+static std::vector<TexEntry> g_cache;
 static unsigned long long g_stamp = 0;
+constexpr size_t kTexCacheMax = 1024;
 
-static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaTextureObject_t *out) {
+static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaStream_t stream, cudaTextureObject_t *out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) {
+    cudaGetLastError();
+    cap = cudaStreamCaptureStatusNone;
+  }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   std::lock_guard<std::mutex> lock(g_mu);
-  for (int i = 0; i < g_cache_n; ++i)
-    if (g_cache[i].dev == dev && g_cache[i].ptr == ptr && g_cache[i].rows == rows && g_cache[i].Wpt == Wpt) {
-      g_cache[i].stamp = ++g_stamp;
-      *out = g_cache[i].tex;
+  for (TexEntry &t : g_cache)
+    if (t.dev == dev && t.ptr == ptr && t.rows == rows && t.W == W && t.Wpt == Wpt) {
+      t.stamp = ++g_stamp;
+      t.pinned = t.pinned || capturing;
+      *out = t.tex;
       return cudaSuccess;
     }
   cudaResourceDesc rd = {};
@@ -462,16 +475,16 @@ static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaTe
   cudaTextureObject_t t = 0;
   e = cudaCreateTextureObject(&t, &rd, &td, nullptr);
   if (e != cudaSuccess) return e;
-  int slot = g_cache_n;
-  if (g_cache_n < 64) {
-    ++g_cache_n;
-  } else {   // evict the least recently used descriptor (it only describes memory, it owns none)
-    slot = 0;
-    for (int i = 1; i < 64; ++i)
-      if (g_cache[i].stamp < g_cache[slot].stamp) slot = i;
-    cudaDestroyTextureObject(g_cache[slot].tex);
+  if (g_cache.size() >= kTexCacheMax && !capturing) {
+    size_t victim = g_cache.size();
+    for (size_t i = 0; i < g_cache.size(); ++i)
+      if (!g_cache[i].pinned && (victim == g_cache.size() || g_cache[i].stamp < g_cache[victim].stamp)) victim = i;
+    if (victim != g_cache.size() && cudaDeviceSynchronize() == cudaSuccess) {   // nothing queued can still sample through it
+      cudaDestroyTextureObject(g_cache[victim].tex);
+      g_cache.erase(g_cache.begin() + (long)victim);
+    }
   }
-  g_cache[slot] = TexEntry{dev, ptr, rows, Wpt, t, ++g_stamp};
+  g_cache.push_back(TexEntry{dev, ptr, rows, W, Wpt, t, ++g_stamp, capturing});
   *out = t;
   return cudaSuccess;
 }
@@ -548,7 +561,7 @@ static int dcn_tex_run(const void *x_q4t, const void *fields, const float *mv, c
                (long long)p.x_batch * 16 * (H + 3));
   const int Wpt = cdfo_q4t_pitch(W);
   {
-    cudaError_t e = dtex::get_texture(x_q4t, p.x_batch * 16 * (H + 3), W, Wpt, &p.tex);
+    cudaError_t e = dtex::get_texture(x_q4t, p.x_batch * 16 * (H + 3), W, Wpt, (cudaStream_t)stream, &p.tex);
     if (e != cudaSuccess) return fail(CDFO_ERR_CUDA, "cdfo_dcn_tex_sm100_fwd: cudaCreateTextureObject: %s", cudaGetErrorString(e));
   }
   p.fields = (const uint2 *)fields; p.mv = mv; p.wpk = (const uint8_t *)wpk; p.bias = bias; p.y = y;

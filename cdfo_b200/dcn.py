@@ -104,13 +104,28 @@ def deform_conv2d(input, offset, weight, bias=None, stride=(1, 1), padding=(0, 0
         raise RuntimeError("the shape of the offset tensor at dimension 1 is not valid. It should be a multiple of "
                            "2 * weight.size[2] * weight.size[3].")
     oh, ow = _out_hw((H, W), (kh, kw), (sh, sw), (ph, pw), (dh, dw))
+    # shape errors as torchvision raises them (torchvision/csrc/ops/cuda/deform_conv2d_kernel.cu checks)
+    if groups == 0 or C != Ck * groups or Co % groups:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (C, Ck * max(groups, 1)))
+    if offset.shape[1] != dg * 2 * kh * kw or C % dg:
+        raise RuntimeError("offset.shape[1] is not valid: got: %d expected: %d" % (offset.shape[1], dg * 2 * kh * kw))
+    if tuple(offset.shape) != (B, dg * 2 * kh * kw, oh, ow):
+        raise RuntimeError("offset output dims: (%d, %d) - computed output dims: (%d, %d)" % (offset.shape[2], offset.shape[3], oh, ow))
+    if mask is not None and tuple(mask.shape) != (B, dg * kh * kw, oh, ow):
+        raise RuntimeError("mask.shape is not valid: got %s expected %s" % (tuple(mask.shape), (B, dg * kh * kw, oh, ow)))
+    if bias is not None and tuple(bias.shape) != (Co,):
+        raise RuntimeError("invalid bias shape: got: %s expected: (%d,)" % (tuple(bias.shape), Co))
     x = input.contiguous()
+    # one element width for every pointer of the C ABI (cdfo_dcn_fwd takes a single dtype code): under autocast x may be fp16 / bf16
+    # while offsets and weights are still fp32 -- cast them to x's dtype like torchvision's autocast wrapper does
+    cast = lambda t: None if t is None else t.to(x.dtype).contiguous()  # noqa: E731
+    offset, mask, weight, bias = cast(offset), cast(mask), cast(weight), cast(bias)
     if config.tensor_core and dcn_sm100.supported(x, weight, (sh, sw), (ph, pw), (dh, dw), groups, dg, mask):
         return _tensor_core_modulated(x, offset, mask, weight, bias, dg)
     y = x.new_empty((B, Co, oh, ow))
-    _lib.call("cdfo_dcn_fwd", 
-        _lib.ptr(x), _lib.ptr(offset.contiguous()), _lib.ptr(None if mask is None else mask.contiguous()),
-        _lib.ptr(weight.contiguous()), _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(y),
+    _lib.call("cdfo_dcn_fwd",
+        _lib.ptr(x), _lib.ptr(offset), _lib.ptr(mask),
+        _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y),
         B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, groups, dg, _lib.dtype_code(x), _lib.stream_ptr(x.device))
     return y
 

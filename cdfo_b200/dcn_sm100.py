@@ -1,12 +1,11 @@
 """Host side of the tcgen05 DCN kernel (cdfo_dcn_sm100_fwd): operand packing, weight cache, launch."""
 import ctypes
-import weakref
 
 import torch
 
 from . import _lib
 
-_wcache = {}  # id(weight) -> (weakref, version, packed)
+_wcache = _lib.TensorCache()
 
 # When a list, every dcn_sm100() launch appends (start_event, end_event, pixels) recorded on the launching
 # stream: bench.py reads the kernel's live duration from these for its roofline line.
@@ -23,14 +22,13 @@ def supported(x, weight, stride, padding, dilation, groups, deformable_groups, m
 @torch.no_grad()
 def pack_weight(weight: torch.Tensor) -> torch.Tensor:
     """[64,64,3,3] -> bf16 B operand [9, 8, 64, 8]; cached per parameter tensor / version counter."""
-    key = id(weight)
-    hit = _wcache.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        return hit[2]
+    return _wcache.get(weight, lambda: _pack_weight(weight))
+
+
+def _pack_weight(weight):
     w = weight.detach().contiguous().float()
     out = torch.empty((9, 8, 64, 8), dtype=torch.bfloat16, device=w.device)
     _lib.call("cdfo_dcn_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
-    _wcache[key] = (weakref.ref(weight), weight._version, out)
     return out
 
 
@@ -93,20 +91,19 @@ def _launch(x_q4p, offset, mask, wpk, bias, mv, out_c8, num_ctas, B, H, W, dg, x
 
 
 # ------------------------------------------------------------------------------------------ texture-unit gather (v3)
-_wcache16 = {}
+_wcache16 = _lib.TensorCache()
 
 
 @torch.no_grad()
 def pack_weight_f16(weight: torch.Tensor) -> torch.Tensor:
     """[64,64,3,3] -> fp16 B operand [9, 8, 64, 8] of cdfo_dcn_tex_sm100_fwd; cached per parameter / version."""
-    key = id(weight)
-    hit = _wcache16.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
-        return hit[2]
+    return _wcache16.get(weight, lambda: _pack_weight_f16(weight))
+
+
+def _pack_weight_f16(weight):
     w = weight.detach().contiguous().float()
     out = torch.empty((9, 8, 64, 8), dtype=torch.float16, device=w.device)
     _lib.call("cdfo_dcn_tex_sm100_pack_weight", _lib.ptr(w), _lib.ptr(out), _lib.stream_ptr(w.device))
-    _wcache16[key] = (weakref.ref(weight), weight._version, out)
     return out
 
 

@@ -194,10 +194,9 @@ class FrameDriver:
             raise ValueError("FrameDriver.run: frame width must be a multiple of 8 (got %d)" % W)
         seq_ids = list(range(S)) if seq_ids is None else list(seq_ids)
         with_gt = all(q.gt is not None for q in seqs)
+        # int32 staging if any sequence carries int32 MVs; int8 fields are widened by the staging copy itself (the caller's
+        # Sequence objects are never modified)
         mv_dtype = torch.int32 if any(q.mvl0.dtype == np.int32 for q in seqs) else torch.int8
-        if mv_dtype == torch.int32:
-            for q in seqs:
-                q.mvl0 = q.mvl0.astype(np.int32)
         dev, H = self.device, padded_rows(h)
         main = torch.cuda.current_stream(dev)
         slots = [_Staging(S, h, H, W, mv_dtype, with_gt, dev) for _ in range(2)]
@@ -221,52 +220,54 @@ class FrameDriver:
         l1, pending = None, None
         ring_before = self.model.feature_ring
         self.model.feature_ring = not self.use_graph      # eager steps keep the window's L1 features in a ring (model.FeatureRing)
-        for i in range(T):
-            slot = slots[i % 2]
-            if i + 1 < T:                               # stage step i+1 while step i computes
-                nxt = slots[(i + 1) % 2]
-                if nxt.used:
-                    nxt.ready.synchronize()             # its previous H2D finished: the pinned buffers may be rewritten
-                self._fill(nxt, seqs, new_frame_of_step(i + 1, T), i + 1, h)
-                self._upload(nxt)
-            main.wait_event(slot.ready)
-            if i > 0:
-                new = {"x": metrics.planes_to_unit(slot.dev["lr"], H), "pms": metrics.planes_to_unit(slot.dev["pm"], H),
-                       "rms": metrics.planes_to_unit(slot.dev["res"], H), "ufs": metrics.planes_to_unit(slot.dev["unflt"], H)}
-                for k in win:
-                    win[k] = torch.cat([win[k][:, 1:], new[k].view(S, 1, 1, H, W)], 1)
-            mvs = torch.cat([priors.mv2mvs(slot.dev["mv"][s]) for s in range(S)], 0)
-            priors.modify_mv_for_end_frames(i, mvs, T)
-            noise = noise_for(self.seed, seq_ids, i, H, W, dev)
-            if l1 is None:
-                sr, l1 = self.model(win["x"], None, mvs, win["pms"], win["rms"], win["ufs"], None, noise=noise)
-            elif self.use_graph:
-                if self._graphed is None or self._graphed.static_in[0].shape != win["x"].shape:
-                    self._graphed = GraphedStep(self.model, win["x"], mvs, win["pms"], win["rms"], win["ufs"], l1, noise)
-                sr, l1 = self._graphed(win["x"], mvs, win["pms"], win["rms"], win["ufs"], l1, noise)
-            else:
-                sr, l1 = self.model(win["x"], None, mvs, win["pms"], win["rms"], win["ufs"], l1, noise=noise)
-            o = i % 2
-            if i >= 2 and sink is not None:
-                main.wait_event(out_done[o])                      # the D2H of step i-2 has left this buffer
-            metrics.sr_to_u8(sr.reshape(S, 4 * H, 4 * W), 4 * h, out=out_u8[o])
-            if with_gt:
-                metrics.psnr_ssim(out_u8[o], slot.dev["gt"], self.crop_border, accum=sums)
-            slot.consumed.record(main)
-            out_ready[o].record(main)
-            if sink is not None:
-                cs = self.copy_stream
-                cs.wait_event(out_ready[o])
-                with torch.cuda.stream(cs):
-                    out_host[o].copy_(out_u8[o], non_blocking=True)
-                    out_done[o].record(cs)
-                if pending is not None:                 # deliver the previous frame while this one computes
-                    self._deliver(sink, pending, out_host, out_done)
-                pending = (i, o, S)
-        if sink is not None and pending is not None:
-            self._deliver(sink, pending, out_host, out_done)
-        torch.cuda.current_stream(dev).synchronize()
-        self.model.feature_ring = ring_before
+        try:
+            for i in range(T):
+                slot = slots[i % 2]
+                if i + 1 < T:                               # stage step i+1 while step i computes
+                    nxt = slots[(i + 1) % 2]
+                    if nxt.used:
+                        nxt.ready.synchronize()             # its previous H2D finished: the pinned buffers may be rewritten
+                    self._fill(nxt, seqs, new_frame_of_step(i + 1, T), i + 1, h)
+                    self._upload(nxt)
+                main.wait_event(slot.ready)
+                if i > 0:
+                    new = {"x": metrics.planes_to_unit(slot.dev["lr"], H), "pms": metrics.planes_to_unit(slot.dev["pm"], H),
+                           "rms": metrics.planes_to_unit(slot.dev["res"], H), "ufs": metrics.planes_to_unit(slot.dev["unflt"], H)}
+                    for k in win:
+                        win[k] = torch.cat([win[k][:, 1:], new[k].view(S, 1, 1, H, W)], 1)
+                mvs = torch.cat([priors.mv2mvs(slot.dev["mv"][s]) for s in range(S)], 0)
+                priors.modify_mv_for_end_frames(i, mvs, T)
+                noise = noise_for(self.seed, seq_ids, i, H, W, dev)
+                if l1 is None:
+                    sr, l1 = self.model(win["x"], None, mvs, win["pms"], win["rms"], win["ufs"], None, noise=noise)
+                elif self.use_graph:
+                    if self._graphed is None or self._graphed.static_in[0].shape != win["x"].shape:
+                        self._graphed = GraphedStep(self.model, win["x"], mvs, win["pms"], win["rms"], win["ufs"], l1, noise)
+                    sr, l1 = self._graphed(win["x"], mvs, win["pms"], win["rms"], win["ufs"], l1, noise)
+                else:
+                    sr, l1 = self.model(win["x"], None, mvs, win["pms"], win["rms"], win["ufs"], l1, noise=noise)
+                o = i % 2
+                if i >= 2 and sink is not None:
+                    main.wait_event(out_done[o])                      # the D2H of step i-2 has left this buffer
+                metrics.sr_to_u8(sr.reshape(S, 4 * H, 4 * W), 4 * h, out=out_u8[o])
+                if with_gt:
+                    metrics.psnr_ssim(out_u8[o], slot.dev["gt"], self.crop_border, accum=sums)
+                slot.consumed.record(main)
+                out_ready[o].record(main)
+                if sink is not None:
+                    cs = self.copy_stream
+                    cs.wait_event(out_ready[o])
+                    with torch.cuda.stream(cs):
+                        out_host[o].copy_(out_u8[o], non_blocking=True)
+                        out_done[o].record(cs)
+                    if pending is not None:                 # deliver the previous frame while this one computes
+                        self._deliver(sink, pending, out_host, out_done)
+                    pending = (i, o, S)
+            if sink is not None and pending is not None:
+                self._deliver(sink, pending, out_host, out_done)
+            torch.cuda.current_stream(dev).synchronize()
+        finally:
+            self.model.feature_ring = ring_before       # also on an exception mid-sequence: later plain callers must not get ring handles
         res = {"frames": T, "sums": sums, "psnr": None, "ssim": None}
         if with_gt:
             host = sums.cpu()

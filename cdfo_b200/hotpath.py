@@ -20,6 +20,31 @@ def _c(mod, x, **kw):
     return F.conv2d(x, mod.weight, mod.bias, **kw)
 
 
+def _pkey(*params):
+    """Identity of a set of parameters for a derived-tensor cache: storage address, device and in-place version of each.  The cache
+    itself hangs on the OWNING MODULE (never on id(): CPython reuses the addresses of freed objects, and every parameter of a
+    freshly loaded checkpoint has the same _version), so it dies with the model and cannot be hit by another one."""
+    return tuple((p.data_ptr(), str(p.device), p._version, p.dtype) for p in params)
+
+
+def _module_cache(mod, slot, key, build):
+    """mod.__dict__['_cdfo_derived'][slot] = (key, value); rebuilt when the key (see _pkey) changes -- load_state_dict, .to(device),
+    optimizer steps.  A write through `.data` that keeps address and version is invisible: call clear_derived(model) after one."""
+    store = mod.__dict__.setdefault("_cdfo_derived", {})
+    hit = store.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = build()
+    store[slot] = (key, val)
+    return val
+
+
+def clear_derived(model):
+    """Drop every derived tensor (composed trunk weights, permuted head weights, LRA tables) cached on the modules of `model`."""
+    for m in model.modules():
+        m.__dict__.pop("_cdfo_derived", None)
+
+
 # ------------------------------------------------------------------------------------------ MDTA (A4 / A5 shared)
 def _f32(t):
     return t.detach().contiguous().float()
@@ -80,24 +105,19 @@ def _expand_batch(x, B):
     return x if x.size(0) == B else x.repeat(B // x.size(0), 1, 1, 1)
 
 
-_head_cache = {}
-
-
 def _head_weights(c2, dg):
     """conv_offset[-1] with its output channels permuted into (dy, dx, m) triples in the order k' = tap*dg + g (reference
     channels 2k, 2k+1, dg*18 + k with k = g*9 + tap: the chunk/cat of arch:3341-3345), packed for the tcgen05 conv."""
-    key = id(c2.weight)
-    hit = _head_cache.get(key)
-    if hit is not None and hit[0] == (c2.weight._version, c2.bias._version):
-        return hit[1], hit[2]
-    kp = torch.arange(dg * 9, device=c2.weight.device)
-    k = (kp % dg) * 9 + kp // dg
-    perm = torch.stack([2 * k, 2 * k + 1, dg * 18 + k], dim=1).reshape(-1)
-    w = c2.weight.detach().index_select(0, perm).contiguous()
-    wpk = conv.pack_weight(w)
-    bias = c2.bias.detach().index_select(0, perm).contiguous().float()
-    _head_cache[key] = ((c2.weight._version, c2.bias._version), wpk, bias, w)
-    return wpk, bias
+    def build():
+        kp = torch.arange(dg * 9, device=c2.weight.device)
+        k = (kp % dg) * 9 + kp // dg
+        perm = torch.stack([2 * k, 2 * k + 1, dg * 18 + k], dim=1).reshape(-1)
+        w = c2.weight.detach().index_select(0, perm).contiguous()
+        wpk = conv.pack_weight(w)
+        bias = c2.bias.detach().index_select(0, perm).contiguous().float()
+        return wpk, bias, w          # w keeps conv.pack_weight's weak reference alive
+    out = _module_cache(c2, "head_%d" % dg, _pkey(c2.weight, c2.bias), build)
+    return out[0], out[1]
 
 
 @torch.no_grad()
@@ -146,29 +166,22 @@ def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow, stack=None, group
 
 
 # ------------------------------------------------------------------------------------------ A8
-_lra_tables = {}
-
-
 def _lra_tap_tables(mod):
-    """kw[9], kh[9], K1[64], R[64,64] of csrc/lra.cu from directW1_conv / directH1_conv (cached per weight version)."""
-    key = (id(mod.directW1_conv.weight), mod.directW1_conv.weight._version, mod.directH1_conv.weight._version,
-           mod.directW1_conv.bias._version, mod.directH1_conv.bias._version)
-    hit = _lra_tables.get(id(mod))
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    kw = mod.directW1_conv.weight.detach().reshape(9).double()
-    kh = mod.directH1_conv.weight.detach().reshape(9).double()
-    c = torch.arange(64, device=kw.device)
-    tix = c.view(64, 1) - c.view(1, 64) + 4                 # tix[c_star][c] = tap index of a bump centred at c_star
-    tapm = torch.where((tix >= 0) & (tix <= 8), kw[tix.clamp(0, 8)], torch.zeros((), dtype=kw.dtype, device=kw.device))
-    k1 = tapm.sum(dim=1)                                     # K1[c_star]
-    r = tapm @ tapm.t()                                      # R[c1][c2]
-    tab = torch.cat([kw, kh, k1, r.reshape(-1)]).float().contiguous()
-    # the two scalar biases are read back ONCE per weight version (a .item() per call would be a host sync per step and
-    # would make the step impossible to capture in a CUDA graph)
-    out = (tab, float(mod.directW1_conv.bias), float(mod.directH1_conv.bias))
-    _lra_tables[id(mod)] = (key, out)
-    return out
+    """kw[9], kh[9], K1[64], R[64,64] of csrc/lra.cu from directW1_conv / directH1_conv (cached on the module per weight version)."""
+    def build():
+        kw = mod.directW1_conv.weight.detach().reshape(9).double()
+        kh = mod.directH1_conv.weight.detach().reshape(9).double()
+        c = torch.arange(64, device=kw.device)
+        tix = c.view(64, 1) - c.view(1, 64) + 4                 # tix[c_star][c] = tap index of a bump centred at c_star
+        tapm = torch.where((tix >= 0) & (tix <= 8), kw[tix.clamp(0, 8)], torch.zeros((), dtype=kw.dtype, device=kw.device))
+        k1 = tapm.sum(dim=1)                                     # K1[c_star]
+        r = tapm @ tapm.t()                                      # R[c1][c2]
+        tab = torch.cat([kw, kh, k1, r.reshape(-1)]).float().contiguous()
+        # the two scalar biases are read back ONCE per weight version (a .item() per call would be a host sync per step and
+        # would make the step impossible to capture in a CUDA graph)
+        return tab, float(mod.directW1_conv.bias.detach()), float(mod.directH1_conv.bias.detach())
+    return _module_cache(mod, "lra_tables", _pkey(mod.directW1_conv.weight, mod.directH1_conv.weight, mod.directW1_conv.bias,
+                                                   mod.directH1_conv.bias), build)
 
 
 def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
@@ -291,22 +304,15 @@ def _compose_1x1_after_3x3(w1, b1, w3, b3):
 
 
 def _block_weights(blk):
-    """Per cross-scale block: the 1x1 convs that FOLLOW a body, composed into the body's second 3x3."""
-    b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
+    """Per cross-scale block: the 1x1 convs that FOLLOW a body, composed into the body's second 3x3 (cached on the block)."""
+    b2 = blk.body._modules["2"]
     dn, up = blk.down._modules["0"], blk.up._modules["0"]
-    key = (id(blk), b0.weight._version, b2.weight._version, dn.weight._version, up.weight._version,
-           b2.bias._version, dn.bias._version, up.bias._version)
-    hit = _trunk_cache.get(id(blk))
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    wu2, bu2 = _compose_1x1_after_3x3(up.weight.detach(), up.bias.detach(), b2.weight.detach(), b2.bias.detach())
-    wd2, bd2 = _compose_1x1_after_3x3(dn.weight.detach(), dn.bias.detach(), b2.weight.detach(), b2.bias.detach())
-    out = {"up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
-    _trunk_cache[id(blk)] = (key, out)
-    return out
 
-
-_trunk_cache = {}
+    def build():
+        wu2, bu2 = _compose_1x1_after_3x3(up.weight.detach(), up.bias.detach(), b2.weight.detach(), b2.bias.detach())
+        wd2, bd2 = _compose_1x1_after_3x3(dn.weight.detach(), dn.bias.detach(), b2.weight.detach(), b2.bias.detach())
+        return {"up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
+    return _module_cache(blk, "composed", _pkey(b2.weight, b2.bias, dn.weight, dn.bias, up.weight, up.bias), build)
 
 
 @torch.no_grad()

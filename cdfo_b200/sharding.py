@@ -4,8 +4,8 @@ Every output frame depends only on its own 7-frame window of LR frames + priors 
 features depend only on that frame (arch/SIDECVSR_our.py:4417-4419), so the work list of (sequence, frame) items is
 partitioned statically: one process per GPU, weights replicated, no collective on the data path.  The only collective
 is the end-of-job gather of the metric sums (the reference computes PSNR/SSIM per sequence on the host,
-metric/psnr_ssim.py:446-484): one all_reduce(SUM) of an [n_seq, 3] fp64 tensor (sum of squared error, sum of SSIM,
-frame count), NCCL on the GPU box, gloo in the CPU tests.
+metric/psnr_ssim.py:446-484): one all_reduce(SUM) of an [n_seq, 3] fp64 tensor (sum of per-frame PSNR, sum of per-frame
+SSIM, frame count -- what metrics.psnr_ssim(accum=) accumulates), NCCL on the GPU box, gloo in the CPU tests.
 
 Nothing here touches CUDA: the functions are plain host logic and are tested with world_size-2 gloo groups.
 """
@@ -51,7 +51,7 @@ def noise_key(seed, sequence, frame, neighbour):
 
 def gather_metrics(local, group=None):
     """Sum of the per-rank [n_seq, 3] fp64 metric sums over all ranks (in place; identity without a process group).
-    Rows a rank does not own must be zero.  Returns (psnr_from_sse helper inputs) the reduced tensor."""
+    Rows a rank does not own must be zero.  Returns the reduced tensor (see mean_metrics_per_sequence)."""
     if local.dtype != torch.float64 or local.dim() != 2 or local.size(1) != 3:
         raise ValueError("gather_metrics: expected an [n_seq, 3] float64 tensor")
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -59,8 +59,9 @@ def gather_metrics(local, group=None):
     return local
 
 
-def psnr_per_sequence(sums, pixels_per_frame, peak=255.0):
-    """PSNR of each sequence from the reduced sums, averaged per frame like cal_psnr_ssim (metric/psnr_ssim.py:477-481)
-    when every frame has the same size: column 0 = sum over frames of per-frame MSE * pixels, column 2 = frame count."""
-    mse = sums[:, 0] / (sums[:, 2].clamp_min(1.0) * float(pixels_per_frame))
-    return 10.0 * torch.log10(peak * peak / mse.clamp_min(1e-20))
+def mean_metrics_per_sequence(sums):
+    """(mean PSNR [dB], mean SSIM) of each sequence from the reduced [n_seq, 3] sums = (sum of per-frame PSNR, sum of per-frame
+    SSIM, frames) that metrics.psnr_ssim(accum=) / FrameDriver.run accumulate: the per-sequence average of per-frame values, which is
+    what the reference's cal_psnr_ssim reports (metric/psnr_ssim.py:477-481)."""
+    n = sums[:, 2].clamp_min(1.0)
+    return sums[:, 0] / n, sums[:, 1] / n

@@ -96,6 +96,31 @@ def test_full_model_vs_reference_golden(cuda_dev, variant, lowp):
         assert err <= TOL_ABS and dpsnr <= TOL_PSNR
 
 
+def test_full_model_benchmarked_config_c3_vs_reference_golden(cuda_dev):
+    """bench.py's exact step against the REAL reference (tests/golden/model_c3_golden.npz, oracle/make_golden_c3.py): BASELINE.json
+    configs[2] = 7 x 272x480 LR -> 1088x1920, DCN alignment (O2), B = 2 sequences, lowp = bf16, feature ring on, the six noise
+    tensors handed over as one neighbour-major batch, texture-gather DCN -- a first frame and a second frame through the ring."""
+    import cdfo_b200
+    g = G.load("model_c3_golden.npz")
+    (c0, m0, n0), (c1, m1, n1) = G.c3_frames()
+    assert cdfo_b200.config.dcn_gather == "tex" and cdfo_b200.config.head_dual
+    m = _model("O2", cuda_dev, torch.bfloat16)
+    m.feature_ring = True
+    c0, c1 = _dev(c0, cuda_dev), _dev(c1, cuda_dev)
+    sr0, l1 = m(c0["x"], None, m0.to(cuda_dev), c0["pms"], c0["rms"], c0["ufs"], None, noise=torch.cat(n0, 0).to(cuda_dev))
+    assert getattr(l1, "_cdfo_ring", None) is not None
+    sr1, _ = m(c1["x"], None, m1.to(cuda_dev), c1["pms"], c1["rms"], c1["ufs"], l1, noise=torch.cat(n1, 0).to(cuda_dev))
+    for i, sr in enumerate((sr0, sr1)):
+        ref16 = g["sr%d" % i]
+        out = sr.float().cpu().numpy()
+        err = np.abs(out - ref16.astype(np.float32)).max()          # includes <= 2.5e-4 of fp16 storage of the golden
+        target = G.c3_target(ref16, i)
+        dpsnr = np.abs(G.psnr_per_sequence(np.clip(out, 0, 1), target) - g["psnr%d" % i])
+        print("CVSR_V8 O2 c3 272x480 B=2 bf16 ring %s frame: max abs err %.3g, dPSNR per sequence %s dB (reference PSNR %s)"
+              % (("first", "cached")[i], err, np.round(dpsnr, 5), np.round(g["psnr%d" % i], 3)))
+        assert err <= TOL_ABS and dpsnr.max() <= TOL_PSNR
+
+
 def test_full_model_ragged_size_vs_oracle(cuda_dev):
     """A size with a ragged last DCN tile (W = 40, not a multiple of 32), B = 2, against the torch oracle."""
     from cdfo_b200 import synthetic

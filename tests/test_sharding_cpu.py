@@ -50,10 +50,11 @@ def test_noise_is_keyed_by_work_item():
 
 
 def _fake_frame_metrics(seq, frame):
-    """Stand-in for (sum of squared error, SSIM, 1) of one output frame: a deterministic function of the work item."""
+    """Stand-in for (PSNR dB, SSIM, 1) of one output frame -- the triple metrics.psnr_ssim(accum=) adds per frame: a deterministic
+    function of the work item."""
     g = torch.Generator().manual_seed(1000 * seq + frame)
     err = torch.randn(16, 16, generator=g, dtype=torch.float64)
-    return torch.tensor([float((err * err).sum()), float(err.abs().mean()), 1.0], dtype=torch.float64)
+    return torch.tensor([float(30.0 + (err * err).mean()), float(err.abs().mean()), 1.0], dtype=torch.float64)
 
 
 def _worker(rank, world, port, n_seq, n_frames, out):
@@ -89,8 +90,8 @@ def test_metric_gather_world2_gloo(tmp_path):
         for f in range(n_frames):
             ref[s] += _fake_frame_metrics(s, f)
     assert torch.equal(total, ref)
-    psnr = sharding.psnr_per_sequence(total, 16 * 16)
-    assert psnr.shape == (n_seq,) and torch.isfinite(psnr).all()
+    psnr, ssim = sharding.mean_metrics_per_sequence(total)
+    assert psnr.shape == (n_seq,) and torch.allclose(psnr, ref[:, 0] / n_frames) and torch.allclose(ssim, ref[:, 1] / n_frames)
 
 
 def test_gather_metrics_without_group_is_identity():

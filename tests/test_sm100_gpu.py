@@ -215,3 +215,86 @@ def test_dcn_tex_tma_fields_equals_ldg_fields(cuda_dev, B, H, W):
     finally:
         lib.cdfo_dcn_tex_sm100_set_fields_path(1)
     assert torch.equal(y_tma, y_ldg) and torch.equal(y8_tma, y8_ldg)
+
+
+@pytest.mark.parametrize("xB,H,W", [(1, 40, 40), (4, 272, 40)])
+def test_dcn_tex_footprint_probe_vs_oracle(cuda_dev, xB, H, W):
+    """Effective sampling footprint of the BENCHMARKED kernel (dcn_tex_sm100_kernel: the texture unit receives the fp32
+    coordinate base + (residual + mv), arch/SIDECVSR_our.py:3347 + deform_conv_cuda_kernel.cu:614-617, and filters with 8-bit
+    fractional weights) against the exact fp32 oracle, measured with probe images instead of inferred:
+
+      * every group's 4 channels are (local row ramp, local column ramp, one-hot anchor rows, one-hot anchor columns) -- anchors
+        every 40 pixels -- and the weight is a per-tap identity, so output channel 4g+c of launch `tap` IS the blended probe value
+        of sample (pixel, g, tap): ramps -> effective coordinate, one-hot -> the bilinear weight on the anchor row / column;
+      * every sample is steered into [a-1, a+1) around its cell's anchor a (residuals up to +-23 px: fp16 ulp 1/64), onto exact
+        integers, integers -+ 2^-17 / 2^-11 / 2^-9 (per-pixel MV perturbations the fp16 residual cannot absorb), k/128 positions
+        and random fractions;
+      * (4, 272, 40) is the benchmarked geometry: the texture folds (sample, quad plane, row) into its row axis, so sample 3 of
+        x_batch = 4 at 272 rows samples at row coordinates up to 17 600, where fp32 keeps 9-10 fractional bits.
+
+    Reports (and bounds) how many samples put weight on a row / column the exact footprint does not touch, the largest such weight,
+    and the largest weight / effective-coordinate error."""
+    from cdfo_b200 import dcn_sm100 as S
+    dg = 16
+    g = torch.Generator().manual_seed(12 + H)
+    rows = torch.arange(H).float().view(1, 1, H, 1).expand(1, 1, H, W)
+    cols = torch.arange(W).float().view(1, 1, 1, W).expand(1, 1, H, W)
+    anc_r, anc_c = 40.0 * torch.floor(rows / 40.0) + 20.0, 40.0 * torch.floor(cols / 40.0) + 20.0
+    ramp_r = torch.where((rows - anc_r).abs() <= 2, (rows - anc_r) * 0.5, torch.zeros(()))   # exact in fp16; linear on the footprint rows
+    ramp_c = torch.where((cols - anc_c).abs() <= 2, (cols - anc_c) * 0.5, torch.zeros(()))
+    quad = torch.cat([ramp_r, ramp_c, (rows == anc_r).float(), (cols == anc_c).float()], 1)    # [1, 4, H, W]
+    x = quad.repeat(1, dg, 1, 1).contiguous()
+    # target position of sample (pixel, group, tap): a_r - 1 + u, a_c - 1 + v with u, v in [0, 2) drawn from the hard cases
+    n = dg * 9 * H * W
+    kind = torch.randint(0, 6, (2, n), generator=g)
+    base_int = torch.randint(0, 2, (2, n), generator=g).float()
+    frac = torch.rand(2, n, generator=g)
+    u = torch.where(kind <= 1, base_int, base_int + frac)                                      # 0, 1: exact integer (+ the MV delta)
+    u = torch.where(kind == 2, base_int + 2.0 ** -11, u)                                       # 2: just above (near pixels only)
+    u = torch.where(kind == 3, base_int + torch.randint(0, 128, (2, n), generator=g).float() / 128.0, u)   # 3: k/128 (MV grid)
+    u = torch.where(kind == 4, base_int + 1.0 - 2.0 ** -9, u)                                  # 4: half a filter step below
+    u = u.clamp(0.0, 2.0 - 2.0 ** -10).view(2, dg, 9, H, W)
+    taps_i = torch.arange(9).view(1, 9, 1, 1) // 3
+    taps_j = torch.arange(9).view(1, 9, 1, 1) % 3
+    base_y = (rows[0] - 1).view(1, 1, H, W) + taps_i                                           # h*1 - 1 + i   (.cu:607-608,614)
+    base_x = (cols[0] - 1).view(1, 1, H, W) + taps_j
+    # MV prior on a k/64 grid (mv2mvs produces k/128; /64 keeps integer targets exactly representable as fp16 residuals up to 32 px)
+    # plus a per-pixel perturbation the fp16 residual cannot absorb: integer targets become integer + delta at EVERY pixel
+    mv_grid = torch.randint(-96, 96, (1, 2, H, W), generator=g).float() / 64.0
+    deltas = torch.tensor([0.0, -2.0 ** -11, 2.0 ** -11, -2.0 ** -9, -2.0 ** -17, 2.0 ** -17])
+    mv = mv_grid + deltas[torch.randint(0, 6, (1, 2, H, W), generator=g)]
+    off_y = ((anc_r[0] - 1 + u[0]) - base_y - mv_grid[0, 1]).half().float()                    # what the fields can hold (fp16)
+    off_x = ((anc_c[0] - 1 + u[1]) - base_x - mv_grid[0, 0]).half().float()
+    assert float(off_y.abs().max()) <= 24 and float(off_x.abs().max()) <= 24
+    offset = torch.stack([off_y, off_x], 2).reshape(1, dg * 18, H, W).contiguous()             # channel 2*(g*9+tap) + {0: dy, 1: dx}
+    mask = torch.ones(1, dg * 9, H, W)
+    full = offset + mv.flip(1).repeat(1, dg * 9, 1, 1)                                          # residual + flow in fp32 (arch:3347)
+    d = lambda t: t.to(cuda_dev)
+    rep = lambda t: t.repeat(xB, 1, 1, 1)                                                       # xB identical samples; the last one is compared
+    xq, fields, mvd = S.pack_q4t(d(rep(x))), d(S.pack_fields(rep(offset), rep(mask), dg)), d(rep(mv))
+    n_idx = 0
+    worst_w = worst_only = worst_coord = 0.0
+    eye = torch.eye(64)
+    for tap in range(9):
+        wt = torch.zeros(64, 64, 3, 3)
+        wt[:, :, tap // 3, tap % 3] = eye
+        ref = O.dcn_forward(x.numpy(), full.numpy(), mask.numpy(), wt.numpy(), None, 1, 1, 1, 1, dg)
+        y = S.dcn_tex(xq, fields, S.pack_weight_f16(d(wt)), None, mv=mvd)[xB - 1].cpu().numpy()
+        yq, rq = y.reshape(dg, 4, H, W), ref.reshape(dg, 4, H, W)
+        # ramps: effective coordinate relative to the anchor in pixels (ramp slope 0.5)
+        worst_coord = max(worst_coord, float(np.abs(yq[:, :2] - rq[:, :2]).max()) * 2.0)
+        # one-hot row / column: weight on the anchor row / column; exact weights come from the oracle run itself
+        worst_w = max(worst_w, float(np.abs(yq[:, 2:] - rq[:, 2:]).max()))
+        # the texture footprint puts weight on a row / column the exact one does not touch = its floor index differs
+        mism = (yq[:, 2:] > 0) & ~(rq[:, 2:] > 0)
+        n_idx += int(mism.sum())
+        if mism.any():
+            worst_only = max(worst_only, float(yq[:, 2:][mism].max()))
+    print("tex footprint probe xB=%d %dx%d: %d samples x 2 axes; rows / columns touched by the texture footprint only: %d (largest weight "
+          "there %.3g); max |weight error| %.3g (filter step 2^-8 = %.3g); max |effective coordinate error| %.3g px"
+          % (xB, H, W, n, n_idx, worst_only, worst_w, 2.0 ** -8, worst_coord))
+    # the hardware quantises the fractional position to 8 bits (1.8 fixed point): weights and effective coordinates within one
+    # filter step (+ fp16 rounding of the A operand, + the fp32 resolution of the folded row coordinate, 2^-10 at 16 384 rows); a
+    # row / column the exact footprint does not touch never gets more than that
+    bound = 2.0 ** -8 + 2.0 ** -10 + (2.0 ** -10 if xB * 16 * (H + 3) > 8192 else 0.0)
+    assert worst_w <= bound and worst_only <= bound and worst_coord <= bound
