@@ -36,6 +36,12 @@ LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
 ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
 
 
+def workload(args):
+    """config.workload: identical in both arms (ours and --impl reference) -- BASELINE.json configs[2]."""
+    return ("CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, %s priors, steady state (cached L1_fea)"
+            % (args.variant, args.priors))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -137,8 +143,7 @@ def run_reference(args):
         "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup, "time_capped": capped,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, LD priors, "
-                               "steady state (cached L1_fea)" % args.variant, "lr": [H, W], "host": "CPU",
+        "config": {"workload": workload(args), "lr": [H, W], "host": "CPU",
                    "step": "one HR frame of one sequence (the CPU path has no batch to amortise; ours steps %d sequences at once)" % args.seqs},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -337,9 +342,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CVSR_V8+MVDualAttAlignment (%s), 7x(480x270->272 rows) LR -> 1920x1080 HR, %s priors, "
-                                   "steady state (cached L1_fea), %d sequences per GPU per step" % (args.variant, args.priors, S),
-                       "lr": [H, W], "seqs_per_gpu": S, "cuda_graph": bool(args.graph), "parallelism": "sequence-sharded x%d, no data-path collective" % world,
+            "config": {"workload": workload(args), "lr": [H, W], "seqs_per_gpu": S, "cuda_graph": bool(args.graph), "parallelism": "sequence-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (per step > 1 GB of offsets/masks/activations; %d rotating windows)" % len(pool),
                        "stages": "alignment / attention / fusion / trunk (CTA-pair tcgen05 convs) / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16 + own LayerNorm / depthwise kernels"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -363,7 +366,7 @@ def main():
     ap.add_argument("--lr-h", type=int, default=LR_H)
     ap.add_argument("--lr-w", type=int, default=LR_W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=int, default=200, help="--impl reference: wall-clock cap of the CPU run (full frames; steps / warm-ups beyond it are dropped and the line says so)")
+    ap.add_argument("--cpu-budget-s", type=int, default=400, help="--impl reference: wall-clock cap of the CPU run (full frames; steps / warm-ups beyond it are dropped and the line says so)")
     ap.add_argument("--cpu-baseline-budget-s", type=int, default=80, help="cap of the in-arm cpu_baseline leg (full frames, rank 0, N = 1)")
     ap.add_argument("--graph", type=int, default=0, help="1: replay the steady-state step as a CUDA graph (+1.7 %); 0 (default): eager "
                     "launches, which is what lets the DCN kernel be timed live with CUDA events inside the timed region")

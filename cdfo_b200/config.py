@@ -28,3 +28,7 @@ conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "1") != "0"
 # Offset / mask head of MVDualAttAlignment: True = both evaluations of conv_offset[-1] in one launch (the first one stays in the
 # epilogue's registers, cdfo_mv_offset_head_dual_sm100_fwd); False = two launches with the intermediate fields in HBM.
 head_dual = os.environ.get("CDFO_HEAD_DUAL", "1") != "0"
+
+# MVDualAttAlignment (dg = 16, texture gather): True = conv_offset[-1] on both hidden maps + tanh / sigmoid + MV prior + DCN as ONE kernel
+# (cdfo_mv_head_dcn_fused_sm100_fwd: the offset / mask fields never reach HBM); False = dual head launch -> fields in HBM -> DCN kernel.
+fused_head_dcn = os.environ.get("CDFO_FUSED_HEAD_DCN", "1") != "0"

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "cdfo_common.cuh"
+#include "mv_head_math.cuh"
 #include "sm100_ptx.cuh"
 
 namespace cdfo {
@@ -243,31 +244,17 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
                 float v[48];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  v[i] = __uint_as_float(r0[i]) + bias_s[c0 + i];
-                  v[16 + i] = __uint_as_float(r1[i]) + bias_s[c0 + 16 + i];
-                  v[32 + i] = __uint_as_float(r2[i]) + bias_s[c0 + 32 + i];
+                  v[i] = __fadd_rn(__uint_as_float(r0[i]), bias_s[c0 + i]);
+                  v[16 + i] = __fadd_rn(__uint_as_float(r1[i]), bias_s[c0 + 16 + i]);
+                  v[32 + i] = __fadd_rn(__uint_as_float(r2[i]), bias_s[c0 + 32 + i]);
                 }
                 const int k0 = (n0 + c0) / 3;
                 const size_t base16 = (((size_t)b * 9 + k0 / 16) * 8 * HW + pix) * 2;   // dg == 16: pair plane 0 of this tap
                 uint2 outv[16];
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                  float dy, dx, m = v[3 * t + 2];
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(dy) : "f"(v[3 * t]));
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(dx) : "f"(v[3 * t + 1]));
-                  dy *= p.mag;
-                  dx *= p.mag;
-                  if (ev == 1) {
-                    const float2 pd = __half22float2(*reinterpret_cast<const __half2 *>(&stash[ci][t].x));
-                    const float pm = __low2float(*reinterpret_cast<const __half2 *>(&stash[ci][t].y));
-                    dy += pd.x;                                       // offset_1 + offset_2 (arch:3347)
-                    dx += pd.y;
-                    m = __fdividef(1.f, 1.f + __expf(-(pm + m)));     // sigmoid(mask_1 + mask_2) (arch:3350)
-                  }
-                  const __half2 h0 = __floats2half2_rn(dy, dx), h1 = __floats2half2_rn(m, 0.f);
-                  const uint2 o = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                  if (ev == 0) stash[ci][t] = o;
-                  else outv[t] = o;
+                for (int t = 0; t < 16; ++t) {   // offset_1 + offset_2, sigmoid(mask_1 + mask_2): arch:3347,3350 (mv_head_math.cuh)
+                  if (ev == 0) stash[ci][t] = head::first(v[3 * t], v[3 * t + 1], v[3 * t + 2], p.mag);
+                  else outv[t] = head::second(stash[ci][t], v[3 * t], v[3 * t + 1], v[3 * t + 2], p.mag);
                 }
                 if (ev == 1) {
                   uint2 *y = reinterpret_cast<uint2 *>(p.y);
@@ -334,9 +321,9 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
             float v[48];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              v[i] = __uint_as_float(r0[i]) + bias_s[c0 + i];
-              v[16 + i] = __uint_as_float(r1[i]) + bias_s[c0 + 16 + i];
-              v[32 + i] = __uint_as_float(r2[i]) + bias_s[c0 + 32 + i];
+              v[i] = __fadd_rn(__uint_as_float(r0[i]), bias_s[c0 + i]);
+              v[16 + i] = __fadd_rn(__uint_as_float(r1[i]), bias_s[c0 + 16 + i]);
+              v[32 + i] = __fadd_rn(__uint_as_float(r2[i]), bias_s[c0 + 32 + i]);
             }
             // fields layout [B][9 taps][dg/gp][H*W][gp] (gp = 2 for dg == 16, else 1): triple k' = tap * dg + g.  The 16
             // consecutive triples of one thread are the 16 groups of one tap when dg == 16: 8 pair planes, 16 bytes each,
@@ -362,22 +349,9 @@ conv3x3_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Conv3x3Para
               }
             }
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              float dy, dx, m = v[3 * t + 2];
-              asm("tanh.approx.f32 %0, %1;" : "=f"(dy) : "f"(v[3 * t]));
-              asm("tanh.approx.f32 %0, %1;" : "=f"(dx) : "f"(v[3 * t + 1]));
-              dy *= p.mag;
-              dx *= p.mag;
-              if (p.epi == 2) {
-                const float2 pd = __half22float2(*reinterpret_cast<const __half2 *>(&prior[t].x));
-                const float pm = __low2float(*reinterpret_cast<const __half2 *>(&prior[t].y));
-                dy += pd.x;                                       // offset_1 + offset_2 (arch:3347)
-                dx += pd.y;
-                m = __fdividef(1.f, 1.f + __expf(-(pm + m)));     // sigmoid(mask_1 + mask_2) (arch:3350)
-              }
-              const __half2 h0 = __floats2half2_rn(dy, dx), h1 = __floats2half2_rn(m, 0.f);
-              outv[t] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-            }
+            for (int t = 0; t < 16; ++t)     // offset_1 + offset_2, sigmoid(mask_1 + mask_2): arch:3347,3350 (mv_head_math.cuh)
+              outv[t] = p.epi == 2 ? head::second(prior[t], v[3 * t], v[3 * t + 1], v[3 * t + 2], p.mag)
+                                   : head::first(v[3 * t], v[3 * t + 1], v[3 * t + 2], p.mag);
             uint2 *y = reinterpret_cast<uint2 *>(p.y);
             if (vec) {
 #pragma unroll

@@ -490,6 +490,11 @@ static cudaError_t get_texture(const void *ptr, int rows, int W, int Wpt, cudaSt
 }
 
 }  // namespace dtex
+
+// shared with csrc/mv_dcn_fused_sm100.cu
+cudaError_t dcn_tex_get_texture(const void *ptr, int rows, int W, int Wpt, cudaStream_t stream, cudaTextureObject_t *out) {
+  return dtex::get_texture(ptr, rows, W, Wpt, stream, out);
+}
 }  // namespace cdfo
 
 using namespace cdfo;

@@ -209,3 +209,68 @@ def unpack_fields(fields):
     off = f[..., :2].permute(0, 2, 5, 1, 6, 3, 4).reshape(B, dg * 18, H, W).contiguous()   # [B, pair, gp, 9, 2, H, W]
     msk = f[..., 2].permute(0, 2, 5, 1, 3, 4).reshape(B, dg * 9, H, W).contiguous()
     return off, msk
+
+
+# ------------------------------------------------------------------------------------------ fused head + DCN (csrc/mv_dcn_fused_sm100.cu)
+def fused_head_permutation(dg, device):
+    """Output-channel order of conv_offset[-1] the fused kernel expects: n' = T*144 + qs*36 + tl*12 + gi*3 + c  <-  reference channel
+    (2k, 2k+1, dg*18 + k)[c] with k = g*9 + tap, tap = 3T + tl, g = 4 qs + gi (the chunk / cat of arch:3341-3345)."""
+    if dg != 16:
+        raise _lib.CdfoError("fused head + DCN: 16 deformable groups only")
+    n = torch.arange(432, device=device)
+    T, r = n // 144, n % 144
+    qs, r = r // 36, r % 36
+    tl, r = r // 12, r % 12
+    gi, c = r // 3, r % 3
+    k = (4 * qs + gi) * 9 + 3 * T + tl
+    return torch.where(c == 2, dg * 18 + k, 2 * k + c)
+
+
+@torch.no_grad()
+def mv_head_dcn_fused(z8, head_wpk, head_bias, magnitude, x_q4t, mv, wpk16, bias=None, out_c8=False, stack=None, group_chunk=None,
+                      fields_out=None, num_ctas=0):
+    """z8 [2B, 8, H, W, 8] bf16 hidden maps (sample b and b + B); x_q4t [xB, 16, H+3, Wpt, 4] fp16; mv [B, 2, H, W] fp32 or None.
+    Returns [B, 64, H, W] fp32, [B, 8, H, W, 8] bf16 (out_c8), or None when writing into `stack` ([n_seq, chunks, H, W, 8] bf16,
+    group-major batch like dcn_tex_stacked).  fields_out: optional fp16 [B, 9, 8, H, W, 2, 4] debug tap of the fields."""
+    B2, c8, H, W, e = z8.shape
+    if z8.dtype != torch.bfloat16 or not z8.is_contiguous() or c8 != 8 or e != 8 or B2 % 2:
+        raise _lib.CdfoError("mv_head_dcn_fused: z8 must be a contiguous bf16 [2B, 8, H, W, 8] tensor")
+    B, xB = B2 // 2, x_q4t.size(0)
+    if x_q4t.size(2) != H + 3 or x_q4t.size(3) != _lib.lib().cdfo_q4t_pitch(W) or x_q4t.dtype != torch.float16 or not x_q4t.is_contiguous():
+        raise _lib.CdfoError("mv_head_dcn_fused: x_q4t does not match the %dx%d hidden maps (use pack_q4t)" % (H, W))
+    if B % xB:
+        raise _lib.CdfoError("mv_head_dcn_fused: batch %d is not a multiple of the x batch %d" % (B, xB))
+    if head_bias.dtype != torch.float32 or head_bias.numel() != 432 or not head_bias.is_contiguous():
+        raise _lib.CdfoError("mv_head_dcn_fused: head bias must be 432 contiguous fp32 values")
+    mv = None if mv is None else mv.contiguous().float()
+    bias = None if bias is None else bias.detach().contiguous().float()
+    dev = z8.device
+    ev = None
+    if event_log is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    if stack is not None:
+        n_seq, chunks = stack.size(0), stack.size(1)
+        if stack.dtype != torch.bfloat16 or not stack.is_contiguous() or tuple(stack.shape[2:]) != (H, W, 8) or B % n_seq or \
+                len(group_chunk) != B // n_seq:
+            raise _lib.CdfoError("mv_head_dcn_fused: stack mismatch")
+        grp = (ctypes.c_int * len(group_chunk))(*[int(g) for g in group_chunk])
+        _lib.call("cdfo_mv_head_dcn_fused_sm100_stacked_fwd", _lib.ptr(z8), _lib.ptr(head_wpk), _lib.ptr(head_bias),
+                  ctypes.c_float(float(magnitude)), _lib.ptr(x_q4t), _lib.ptr(mv), _lib.ptr(wpk16), _lib.ptr(bias), _lib.ptr(stack),
+                  int(n_seq), len(group_chunk), int(chunks), grp, H, W, int(xB), _lib.stream_ptr(dev))
+        y = None
+    else:
+        if out_c8:
+            y = torch.empty((B, 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+        else:
+            y = torch.empty((B, 64, H, W), dtype=torch.float32, device=dev)
+        if fields_out is not None and (fields_out.dtype != torch.float16 or not fields_out.is_contiguous() or
+                                       tuple(fields_out.shape) != fields_shape(B, 16, H, W)):
+            raise _lib.CdfoError("mv_head_dcn_fused: fields_out must be a contiguous fp16 %s tensor" % (fields_shape(B, 16, H, W),))
+        _lib.call("cdfo_mv_head_dcn_fused_sm100_fwd", _lib.ptr(z8), _lib.ptr(head_wpk), _lib.ptr(head_bias),
+                  ctypes.c_float(float(magnitude)), _lib.ptr(x_q4t), _lib.ptr(mv), _lib.ptr(wpk16), _lib.ptr(bias), _lib.ptr(y),
+                  _lib.ptr(fields_out), B, H, W, 1 if out_c8 else 0, int(xB), int(num_ctas), _lib.stream_ptr(dev))
+    if ev is not None:
+        ev[1].record()
+        event_log.append((ev[0], ev[1], B * H * W, "fused"))
+    return y

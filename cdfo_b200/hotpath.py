@@ -120,6 +120,23 @@ def _head_weights(c2, dg):
     return out[0], out[1]
 
 
+def _head_weights_fused(c2, dg):
+    """conv_offset[-1] permuted and packed for the fused head + DCN kernel (dcn_sm100.fused_head_permutation)."""
+    def build():
+        perm = dcn_sm100.fused_head_permutation(dg, c2.weight.device)
+        w = c2.weight.detach().index_select(0, perm).contiguous()
+        return conv.pack_weight(w), c2.bias.detach().index_select(0, perm).contiguous().float(), w
+    out = _module_cache(c2, "head_fused_%d" % dg, _pkey(c2.weight, c2.bias), build)
+    return out[0], out[1]
+
+
+@torch.no_grad()
+def mv_hidden_maps(mod, x, extra_feat, pred_feat, flow):
+    """lrelu(conv_offset[0](o_k)) of the two MDTA outputs (arch:3304-3340, first layer of conv_offset): c8 bf16 [2B, 8, H, W, 8]."""
+    c0 = mod.conv_offset._modules["0"]
+    return conv.conv3x3(dual_mdta(mod, x, extra_feat, pred_feat, flow, mode=0), c0.weight, c0.bias, conv.ACT_LRELU)
+
+
 @torch.no_grad()
 def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     """Learned offset residual and mask of MVDualAttAlignment WITHOUT the MV prior (arch:3339-3350 minus the
@@ -128,7 +145,7 @@ def mv_offset_fields(mod, x, extra_feat, pred_feat, flow):
     Both conv_offset layers run in the tcgen05 convolution kernel; tanh / sum / sigmoid are its epilogue."""
     B = extra_feat.size(0)
     c0, c2 = mod.conv_offset._modules["0"], mod.conv_offset._modules["2"]
-    z = conv.conv3x3(dual_mdta(mod, x, extra_feat, pred_feat, flow, mode=0), c0.weight, c0.bias, conv.ACT_LRELU)   # [2B, 8, H, W, 8]
+    z = mv_hidden_maps(mod, x, extra_feat, pred_feat, flow)   # [2B, 8, H, W, 8]
     H, W = z.shape[2:4]
     dg = mod.deformable_groups
     wpk, bias = _head_weights(c2, dg)
@@ -155,6 +172,12 @@ def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow, stack=None, group
     `x` may hold fewer samples than the other arguments (sample b uses x[b % x.size(0)]): the model's six
     neighbour calls share the centre-frame feature (arch:4456).  With `stack` ([n_seq, chunks, H, W, 8] bf16) the DCN
     epilogue writes group g of the group-major batch into chunks [group_chunk[g], +8) of it and None is returned."""
+    if config.dcn_gather == "tex" and config.fused_head_dcn and mod.deformable_groups == 16:
+        # ONE kernel from the hidden maps to the aligned feature: the offset / mask fields stay on the SM
+        z = mv_hidden_maps(mod, x, extra_feat, pred_feat, flow)
+        hw, hb = _head_weights_fused(mod.conv_offset._modules["2"], 16)
+        return dcn_sm100.mv_head_dcn_fused(z, hw, hb, mod.max_residue_magnitude, dcn_sm100.pack_q4t(x), flow,
+                                           dcn_sm100.pack_weight_f16(mod.weight), mod.bias, stack=stack, group_chunk=group_chunk)
     fields = mv_offset_fields(mod, x, extra_feat, pred_feat, flow)
     if config.dcn_gather == "tex":
         if stack is not None:

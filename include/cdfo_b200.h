@@ -144,6 +144,24 @@ int cdfo_dcn_tex_sm100_stacked_fwd(const void *x_q4t, const void *fields, const 
                                    void *y_stack, int n_seq, int n_groups, int stack_chunks, const int *group_chunk, int H,
                                    int W, int dg, int x_batch, void *stream);
 int cdfo_dcn_tex_sm100_pack_weight(const float *w, void *wpk, void *stream);
+/* ---- A5 + A6 fused: conv_offset[-1] on both hidden maps, tanh / sum / sigmoid, + MV prior, DCN -- ONE kernel
+ * (csrc/mv_dcn_fused_sm100.cu; arch/SIDECVSR_our.py:3339-3352).  The offset / mask fields never reach HBM.  dg = 16 only.
+ *   z_c8      [2 B, 8, H, W, 8] bf16: hidden maps lrelu(conv_offset[0](.)) of the two MDTA outputs, sample b and b + B
+ *   head_wpk  cdfo_conv_sm100_pack_weight(432, 64, 3) of conv_offset[-1].weight with its output channels permuted to
+ *             n' = T*144 + qs*36 + tl*12 + gi*3 + c  <-  tap = 3 T + tl, group g = 4 qs + gi, c = (dy, dx, m), i.e. reference
+ *             channels (2 k, 2 k + 1, 288 + k) with k = g * 9 + tap;  head_bias [432] fp32 permuted the same way
+ *   magnitude max_residue_magnitude (10);  x_q4t / mv / dcn_wpk / dcn_bias / y / out_mode / x_batch / num_ctas: as
+ *             cdfo_dcn_tex_sm100_fwd
+ *   fields_out NULL, or [B, 9, 8, H, W, 2] x fp16x4: debug tap of the fields the kernel computed (same layout and, by
+ *             construction, the same bits as cdfo_mv_offset_head_dual_sm100_fwd writes) */
+int cdfo_mv_head_dcn_fused_sm100_fwd(const void *z_c8, const void *head_wpk, const float *head_bias, float magnitude,
+                                     const void *x_q4t, const float *mv, const void *dcn_wpk, const float *dcn_bias, void *y,
+                                     void *fields_out, int B, int H, int W, int out_mode, int x_batch, int num_ctas, void *stream);
+/* Same, writing into the stacked input of tsa_fusion like cdfo_dcn_tex_sm100_stacked_fwd. */
+int cdfo_mv_head_dcn_fused_sm100_stacked_fwd(const void *z_c8, const void *head_wpk, const float *head_bias, float magnitude,
+                                             const void *x_q4t, const float *mv, const void *dcn_wpk, const float *dcn_bias,
+                                             void *y_stack, int n_seq, int n_groups, int stack_chunks, const int *group_chunk,
+                                             int H, int W, int x_batch, void *stream);
 /* NCHW fp32 -> [B, C/4, H+3, Wpt, 4] fp16 (saturated to +-65504), zero border 1 before / 2 after, zero pitch padding. */
 int cdfo_pack_q4t(const float *x_nchw, void *x_q4t, int B, int C, int H, int W, void *stream);
 int cdfo_q4t_pitch(int W);
