@@ -8,6 +8,7 @@ import torch
 from cdfo_b200 import synthetic
 from oracle import priors_ref
 from oracle.make_golden import frame_inputs, module_inputs, priors_cases  # noqa: F401  (no reference import inside)
+from oracle.make_golden_dsta import dsta_inputs  # noqa: F401
 from oracle.make_golden_c3 import c3_frames, c3_target, psnr as psnr_per_sequence  # noqa: F401  (same: seeds -> inputs only)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")

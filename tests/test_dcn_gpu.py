@@ -163,3 +163,36 @@ def test_pack_module_zero_init_is_plain_conv(cuda_dev):
     y = m(x)
     ref = 0.5 * torch.nn.functional.conv2d(x.cpu(), m.weight.cpu(), None, 1, 1) + m.bias.cpu().view(1, -1, 1, 1)
     assert (y.cpu() - ref).abs().max().item() < 1e-4
+
+
+def test_torchvision_override_routes_cuda_calls_here(cuda_dev):
+    """torch.library CUDA-key override of torchvision::deform_conv2d (SURVEY 8b): the reference's call sites
+    (arch/SIDECVSR_our.py:3164,3260,3352,3733) reach this library with zero changes to arch.py."""
+    import torchvision
+    import cdfo_b200
+    from cdfo_b200 import torchvision_override as tvo
+    case = (2, 8, 9, 11, 6, 3, 1, 1, 1, 2, 4, True, True)
+    x, offset, mask, wt, b = _rand_case(case, seed=21)
+    ref = O.dcn_forward(x.numpy(), offset.numpy(), mask.numpy(), wt.numpy(), b.numpy(), 1, 1, 1, 2, 4)
+    ref_v1 = O.dcn_forward(x.numpy(), offset.numpy(), None, wt.numpy(), None, 1, 1, 1, 2, 4)
+    d = lambda t: t.to(cuda_dev)
+    tvo.install()
+    try:
+        n0 = cdfo_b200._lib.launch_count
+        y = torchvision.ops.deform_conv2d(d(x), d(offset), d(wt), d(b), 1, 1, 1, d(mask))
+        y1 = torchvision.ops.deform_conv2d(d(x), d(offset), d(wt), None, 1, 1, 1, None)
+        assert cdfo_b200._lib.launch_count >= n0 + 2, "the override was not dispatched to"
+        # hot shape -> the tensor-core kernel, through the same operator
+        xh, oh_, mh, wh, bh = _rand_case((1, 64, 12, 16, 64, 3, 1, 1, 1, 1, 16, True, True), seed=22)
+        cdfo_b200.config.tensor_core = True          # (the file's fixture pins the fp32 kernel; restored by it afterwards)
+        yh = torchvision.ops.deform_conv2d(d(xh), d(oh_), d(wh), d(bh), 1, 1, 1, d(mh))
+        cdfo_b200.config.tensor_core = False
+        refh = O.dcn_forward(xh.numpy(), oh_.numpy(), mh.numpy(), wh.numpy(), bh.numpy(), 1, 1, 1, 1, 16)
+    finally:
+        tvo.uninstall()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    assert np.abs(y1.cpu().numpy() - ref_v1).max() <= 2e-5 * max(1.0, np.abs(ref_v1).max())
+    assert np.abs(yh.cpu().numpy() - refh).max() <= 1e-2 * np.abs(refh).max()
+    n1 = cdfo_b200._lib.launch_count
+    torchvision.ops.deform_conv2d(d(x), d(offset), d(wt), d(b), 1, 1, 1, d(mask))      # uninstalled: torchvision's own kernel again
+    assert cdfo_b200._lib.launch_count == n1

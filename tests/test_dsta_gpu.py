@@ -2,6 +2,9 @@
 import pytest
 import torch
 
+import numpy as np
+
+import golden_util as G
 from oracle import torch_ref
 
 pytestmark = pytest.mark.gpu
@@ -33,3 +36,21 @@ def test_dsta_matches_oracle_and_keeps_names(cuda_dev):
     assert err <= 2e-4
     with pytest.raises(NotImplementedError):
         cdfo_b200.DSTA(64)(x)
+
+
+def test_dsta_vs_reference_golden(cuda_dev):
+    """A11 against the REAL reference: tests/golden/dsta_golden.npz is the output of ops/attentionlayer.py's own forward."""
+    import cdfo_b200
+    g = G.load("dsta_golden.npz")
+    m = cdfo_b200.DSTA(64)
+    sd, x = G.dsta_inputs(m.state_dict())
+    m.load_state_dict(sd, strict=True)                     # the reference's parameter names / shapes
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        got = m.to(cuda_dev)(x.to(cuda_dev)).cpu().numpy()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    err = np.abs(got - g["out"]).max()
+    print("DSTA vs reference golden: max err %.3g (max|ref| %.3g)" % (err, np.abs(g["out"]).max()))
+    assert err <= 2e-4
