@@ -33,7 +33,9 @@ sys.path.insert(0, ROOT)
 METRIC = "HR frames/sec, 1080p x4 LD-QP37"
 UNIT = "frames/s"
 LR_H, LR_W = 272, 480            # 270 rows + 2 zero rows (test_LD_37.py:24-26)
-ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)
+ALGO_BYTES_PER_PX_BF16 = 1120    # x 128 + offset 576 + mask 288 + y 128 (2-byte I/O)  [DCN-only kernel]
+FUSED_FLOP_PER_PX = 2 * 497664 + 73728   # last head conv x 2 + offset assembly + DCN, fused
+FUSED_BYTES_PER_PX = 516                 # 2 hidden maps 256 + x 128 + flow 4 + y 128
 
 
 def workload(args):
@@ -311,24 +313,44 @@ def run_ours(args):
         traffic, traffic_src = ncu_traffic()
         durs = [a.elapsed_time(b) * 1e-3 for a, b, _, _ in dcn_log]           # seconds per launch
         px = dcn_log[0][2] if dcn_log else 0
-        per_px = ALGO_BYTES_PER_PX_BF16
+        fused = bool(dcn_log) and dcn_log[0][3] == "fused"
+        if ("fused" in traffic["kernel"]) != fused:      # a capture of another kernel says nothing about this one
+            raise SystemExit("bench.py: %s holds the traffic of %s, not of the kernel this run reports; capture it (tools/ncu_traffic.py)"
+                             % (traffic_src, traffic["kernel"]))
         avg = sum(durs) / max(1, len(durs))
-        achieved = per_px * px / avg / 1e9 if durs else 0.0
-        kname = ("dcn_tex_sm100_kernel (tcgen05 implicit-GEMM DCNv2 64->64 3x3 dg=16, texture-unit gather)"
-                 if cdfo_b200.config.dcn_gather == "tex" else "dcn_sm100_kernel (tcgen05 implicit-GEMM DCNv2, LDG gather)")
-        roof = {
-            "kernel": kname, "bound": "hbm",
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic["dram_bytes_per_px"] * px, "traffic_source": traffic_src,
-            "peak_source": peak_src, "avg_launch_us": avg * 1e6, "launches_timed": len(durs),
-            "algorithmic_bytes_per_launch": per_px * px,
-            "note": "algorithmic bytes = SURVEY 8d's 1120 B per LR pixel and neighbour call (x 128 + offset 576 + mask 288 + y 128) x "
-                    "%d px per launch; this build moves 1408 B/px (fp16 x 128, packed fp16x4 fields 1152 staged by TMA, bf16 y 128 "
-                    "written straight into tsa_fusion's stacked input); traffic = dram bytes per px of the ncu --set full capture "
-                    "(profiles/r01_dcn_tex_tma_fields_ncu.md) scaled to this launch; the binding resource is the L1TEX data stage "
-                    "(texture wavefronts alone put the floor at frac 0.68), see DESIGN.md 3.1; that stage runs at the SM clock, so inside "
-                    "this power-capped step (see clocks.sm_mhz) the kernel is slower than timed alone at full clock "
-                    "(tools/bench_dcn.py: 278 us for 6 calls = frac 0.48)" % px,
-        }
+        if fused:
+            # the fused head + DCN alignment kernel: tensor-bound (1 069 056 FLOP and 516 B per LR pixel and call)
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak_tf = float(pk.get("bf16_tflops_sustained", 1400.0))
+            achieved = FUSED_FLOP_PER_PX * px / avg / 1e12 if durs else 0.0
+            roof = {
+                "kernel": "mv_head_dcn_fused_sm100_kernel (conv_offset[-1] on both hidden maps 64->432 3x3 bf16 tcgen05 + tanh/sigmoid + MV prior "
+                          "+ texture-gather DCNv2 64->64 3x3 dg=16 fp16 tcgen05 TS-form; offset/mask fields never in HBM)",
+                "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": traffic["dram_bytes_per_px"] * px, "traffic_source": traffic_src,
+                "peak_source": ("measured cuBLAS bf16, sustained figure for a kernel timed inside a long step (MEASURED_PEAKS.json); burst %.1f"
+                                % pk["bf16_tflops"]) if pk else "fallback sustained figure (B200_PROFILING.md)",
+                "frac_of_burst_peak": achieved / float(pk["bf16_tflops"]) if pk else None,
+                "avg_launch_us": avg * 1e6, "launches_timed": len(durs), "algorithmic_flops_per_launch": FUSED_FLOP_PER_PX * px,
+                "algorithmic_bytes_per_launch": FUSED_BYTES_PER_PX * px,
+                "hbm_frac_of_same_launch": FUSED_BYTES_PER_PX * px / avg / 1e9 / hbm_peak if durs else None,
+                "note": "algorithmic work = SURVEY 8d row 3: 2 x 497 664 (two evaluations of the 64->432 3x3 head) + 73 728 (DCN) FLOP and 516 B "
+                        "(2 hidden maps 256 + x 128 + flow 4 + y 128) per LR pixel and neighbour call x %d px per launch; traffic = dram bytes per "
+                        "px of this round's ncu --set full capture scaled to this launch; DESIGN.md 3.1" % px,
+            }
+        else:
+            per_px = ALGO_BYTES_PER_PX_BF16
+            achieved = per_px * px / avg / 1e9 if durs else 0.0
+            kname = ("dcn_tex_sm100_kernel (tcgen05 implicit-GEMM DCNv2 64->64 3x3 dg=16, texture-unit gather)"
+                     if cdfo_b200.config.dcn_gather == "tex" else "dcn_sm100_kernel (tcgen05 implicit-GEMM DCNv2, LDG gather)")
+            roof = {
+                "kernel": kname, "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic["dram_bytes_per_px"] * px,
+                "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_us": avg * 1e6, "launches_timed": len(durs),
+                "algorithmic_bytes_per_launch": per_px * px,
+                "note": "two-kernel path (CDFO_FUSED_HEAD_DCN=0): algorithmic bytes = SURVEY 8d's 1120 B per LR pixel and neighbour call (x 128 + "
+                        "offset 576 + mask 288 + y 128) x %d px per launch; the binding resource is the L1TEX data stage, DESIGN.md 3.1" % px,
+            }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             times, warm_done, cores, first = cpu_reference_frames((H, W), 3, 1, args.cpu_baseline_budget_s, args.variant)

@@ -108,3 +108,52 @@ def seeded_state_dict(template, seed=4):
             t = std * torch.randn(shape, generator=g)
         sd[key] = t.to(template[key].dtype)
     return sd
+
+
+class SyntheticSequences:
+    """Lazy list of `n` synthetic coded sequences in the reference's on-disk data contract (driver.Sequence: uint8 LR / partition /
+    unfiltered planes, integer residual maps, int8 MV fields [T, h, W, 3], uint8 ground truth at x4), each a pure function of its
+    sequence id -- a rank generates only the sequences it owns, and every sharding sees identical data (BASELINE.json configs[3]:
+    64 independent 1080p x4 sequences)."""
+
+    def __init__(self, n, frames=16, h=270, w=480, seed=0, with_gt=True):
+        self.n, self.frames, self.h, self.w, self.seed, self.with_gt = int(n), int(frames), int(h), int(w), int(seed), bool(with_gt)
+        self._cache = {}
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sid):
+        import numpy as np
+        from .driver import Sequence
+        if not 0 <= sid < self.n:
+            raise IndexError(sid)
+        if sid in self._cache:
+            return self._cache[sid]
+        T, h, w = self.frames, self.h, self.w
+        rng = np.random.default_rng(900000 + 7919 * self.seed + sid)
+        # a slowly drifting smooth image: low-resolution noise upsampled x8, shifted by one pixel per frame
+        base = rng.integers(0, 256, (h // 8 + 3, w // 8 + 3 + T)).astype(np.float32)
+        big = np.kron(base, np.ones((8, 8), np.float32))
+        k = np.ones(9, np.float32) / 9.0
+        big = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, big)
+        big = np.apply_along_axis(lambda c: np.convolve(c, k, mode="same"), 0, big)
+        lr = np.stack([big[8:8 + h, 8 + t:8 + t + w] for t in range(T)])
+        lr = np.clip(np.round(lr + rng.normal(0, 2.0, lr.shape)), 0, 255).astype(np.uint8)
+        unflt = np.clip(lr.astype(np.int16) + rng.integers(-4, 5, lr.shape), 0, 255).astype(np.uint8)
+        hb, wb = -(-h // 16), -(-w // 16)
+        pm = np.kron(rng.integers(0, 256, (T, hb, wb)).astype(np.uint8), np.ones((1, 16, 16), np.uint8))[:, :h, :w]
+        keep = np.kron((rng.random((T, -(-h // 8), -(-w // 8))) >= 0.7).astype(np.int16), np.ones((1, 8, 8), np.int16))[:, :h, :w]
+        res = (np.clip(np.round(rng.normal(0, 6.0, (T, h, w))), -128, 127).astype(np.int16) * keep).astype(np.int16)
+        blk = rng.integers(-64, 64, (T, -(-h // 8), -(-w // 8), 2))
+        rd = -np.array([1, 2, 4])[rng.integers(0, 3, (T, -(-h // 8), -(-w // 8), 1))]
+        mv = np.kron(np.concatenate([blk, rd], -1), np.ones((1, 8, 8, 1), np.int64))[:, :h, :w].astype(np.int8)
+        gt = None
+        if self.with_gt:
+            up = np.kron(lr, np.ones((1, 4, 4), np.uint8)).astype(np.int16)
+            gt = np.clip(up + rng.integers(-3, 4, up.shape), 0, 255).astype(np.uint8)
+        q = Sequence(lr, pm, res, unflt, mv, gt, name="synthetic_%03d" % sid)
+        if len(self._cache) > 8:
+            self._cache.clear()
+        self._cache[sid] = q
+        return q

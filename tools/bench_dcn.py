@@ -90,6 +90,24 @@ def main():
                 lambda: torchvision.ops.deform_conv2d(x, offset, wt, bias, 1, 1, 1, mask), 5, 1)
         except Exception as e:  # noqa: BLE001
             res["torchvision_cuda_fp32_us"] = "unavailable: %s" % e
+        # the reference's OWN CUDA op (ops/dcn/src/*, built by baseline/build_ref_dcn.py into baseline/_ref/): the same-box figure to beat
+        import glob
+        import importlib.util
+        so = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "deform_conv_cuda*.so")))
+        if so:
+            spec = importlib.util.spec_from_file_location("deform_conv_cuda", so[0])
+            ref = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref)
+
+            def ref_call(xx, oo, mm, ww, bb):
+                out = xx.new_empty((B, 64, H, W))
+                ref.modulated_deform_conv_cuda_forward(xx, ww, bb, xx.new_empty(0), oo, mm, out, xx.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+                return out
+            res["reference_ext_cuda_fp32_us"] = timeit(lambda: ref_call(x, offset, mask, wt, bias), 5, 1)
+            res["reference_ext_cuda_fp16_us"] = timeit(lambda: ref_call(x.half(), off16, m16, wt.half(), bias.half()), 5, 1)
+            res["reference_ext_vs_exact_maxdiff"] = float((ref_call(x, offset, mask, wt, bias) - yb).abs().max())
+        else:
+            res["reference_ext_cuda_fp32_us"] = "baseline/_ref not built"
     print(json.dumps(res))
 
 
