@@ -375,6 +375,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config c4 (and c5 at scale)
+def run_c4(args):
+    """BASELINE.json configs[3] literally: `--c4-seqs` (64) independent 1080p x4 sequences of `--c4-frames` (16) frames each through the
+    public pipeline cdfo_b200.driver.run_sharded -- sliding 7-frame window with clipped ends (test_LD_37.py:13-16), MV decode +
+    end-of-sequence fix-ups on the device (:83-105, :209-234), uint8 planes H2D from pinned staging, uint8 SR frames D2H, on-GPU PSNR / SSIM
+    (metric/psnr_ssim.py:278-399) and ONE NCCL all_reduce of the real [n_seq, 3] metric sums at the end.  The job is fixed, the ranks
+    split it (contiguous blocks of sequences): STRONG scaling.  Everything -- first frames included -- is inside the timed region; the
+    sequences sit decoded in host memory when it starts (a rank generates only the ones it owns)."""
+    import torch
+    import torch.distributed as dist
+    import cdfo_b200
+    from cdfo_b200 import driver, sharding, synthetic
+    from cdfo_b200.model import CVSR_V8
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    model = CVSR_V8(alignment="mv_dcn" if args.variant == "O2" else "dual_att")
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=4), strict=True)
+    model = model.to(dev).eval()
+    model.lowp = torch.bfloat16
+    n, T, S = args.c4_seqs, args.c4_frames, args.seqs
+    lazy = synthetic.SyntheticSequences(n, frames=T, h=270, w=480, seed=0, with_gt=True)
+    own = sharding.sequence_shard(n, world, rank)
+    t0 = time.perf_counter()
+    held = {k: lazy[k] for k in own}
+
+    class Owned:                      # run_sharded indexes only the sequences this rank owns
+        def __len__(self):
+            return n
+
+        def __getitem__(self, k):
+            return held[k]
+    gen_s = time.perf_counter() - t0
+    # untimed warm-up on a short clip of the same shape (module load, allocator, cuDNN heuristics)
+    warm = synthetic.SyntheticSequences(S, frames=8, h=270, w=480, seed=1, with_gt=True)
+    driver.FrameDriver(model, seed=7).run([warm[k] for k in range(S)], sink=lambda s, i, img: None)
+    delivered = [0]
+
+    def sink(sid, i, img):
+        delivered[0] += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    res = driver.run_sharded(model, Owned(), batch=S, seed=0, sink=sink)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - w0
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0].item()), float(t[1].item()) * 1e-3
+    assert delivered[0] == len(own) * T, (delivered[0], len(own), T)
+    frames = sum(res["frames"])
+    assert frames == n * T, (frames, n, T)
+    if rank == 0:
+        per_frame_h2d = 3 * 270 * 480 + 2 * 270 * 480 + 272 * 480 * 3 + 1080 * 1920     # uint8 lr/pm/unflt, int16 res, int8 mv, uint8 gt
+        line = {
+            "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": T, "warmup": 1,
+            "ms_per_step": ms / T, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "c4: %d independent 1080p x4 sequences x %d frames (7x(480x270->272 rows) LR -> 1920x1080 HR, LD priors) "
+                                   "through driver.run_sharded: sliding window with clipped ends, MV end fix-ups, on-GPU PSNR/SSIM, NCCL gather of "
+                                   "the metric sums" % (n, T), "variant": args.variant, "seqs_per_batch": S,
+                       "parallelism": "sequence-sharded x%d (contiguous blocks), no data-path collective" % world,
+                       "l2": "inputs larger than L2", "timed_region": "whole job incl. every sequence's first (7-frame) window, H2D, D2H, metrics, all_reduce",
+                       "host_generation_s_untimed": gen_s, "wall_s": wall},
+            "e2e": {"value": frames / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": per_frame_h2d * S, "d2h_bytes_per_step": 1080 * 1920 * S},
+            "gpu_launches": cdfo_b200._lib.launch_count, "psnr": res["psnr"], "ssim": res["ssim"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,6 +472,10 @@ def main():
     ap.add_argument("--priors", default="LD", choices=["LD", "RA"], help="LD (configs c3/c4) or RA = bidirectional (l0, l1) MV pairs (config c5)")
     ap.add_argument("--lr-h", type=int, default=LR_H)
     ap.add_argument("--lr-w", type=int, default=LR_W)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 (default): steady-state step of resident windows (BASELINE configs[2]); "
+                    "c4: 64 whole sequences through driver.run_sharded (configs[3], strong scaling)")
+    ap.add_argument("--c4-seqs", type=int, default=64)
+    ap.add_argument("--c4-frames", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=int, default=400, help="--impl reference: wall-clock cap of the CPU run (full frames; steps / warm-ups beyond it are dropped and the line says so)")
     ap.add_argument("--cpu-baseline-budget-s", type=int, default=80, help="cap of the in-arm cpu_baseline leg (full frames, rank 0, N = 1)")
@@ -395,6 +484,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -32,3 +32,9 @@ head_dual = os.environ.get("CDFO_HEAD_DUAL", "1") != "0"
 # MVDualAttAlignment (dg = 16, texture gather): True = conv_offset[-1] on both hidden maps + tanh / sigmoid + MV prior + DCN as ONE kernel
 # (cdfo_mv_head_dcn_fused_sm100_fwd: the offset / mask fields never reach HBM); False = dual head launch -> fields in HBM -> DCN kernel.
 fused_head_dcn = os.environ.get("CDFO_FUSED_HEAD_DCN", "1") != "0"
+
+# Feature extraction (conv_first / conv_second + PAItransformerSA_2) when model.lowp is bf16: True = this repo's kernels on c8 bf16
+# (cdfo_b200/features.py: tcgen05 convolutions + csrc/features_c8.cu, no cuDNN / cuBLAS / ATen launch, bit-identical reruns);
+# False = round 1's path (cuDNN bf16 convolutions under autocast + own LayerNorm / depthwise / Gram kernels).  model.lowp = None
+# always takes the fp32 cuDNN path (a debugging reference, not the benchmarked configuration).
+features_c8 = os.environ.get("CDFO_FEATURES_C8", "1") != "0"

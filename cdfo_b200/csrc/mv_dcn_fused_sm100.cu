@@ -22,7 +22,9 @@
 // and the producers drain Y (+ bias) to c8 bf16 / NCHW fp32 one triple into the next tile.
 // TMEM (512 columns): head accumulators [0,144) and [160,304), DCN accumulator [320,384), A ring [384,512).
 // Shared memory (218 KB): DCN weights 72 KB (resident), 2 x 2 hidden-map halos 90 KB, head weight ring 54 KB, biases, barriers.
+// 18 warps: MMA issuer, one TMA pump thread (weight pieces + halos, non-blocking probes), 16 producers.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cdfo_common.cuh"
@@ -44,8 +46,8 @@ constexpr int kNT = 144;                                // head output channels 
 constexpr int kPiece = kNT * 64 * 2;                    // head weights of one (triple, head tap): 18432 B
 constexpr int kWStages = 3, kAStages = 4;
 constexpr int kDcnWBytes = 9 * 64 * 64 * 2, kTapWBytes = 64 * 64 * 2, kBLbo = 64 * 16;
-constexpr int kWarps = 19, kThreads = kWarps * 32;      // warp 0 MMA issuer, 1 weight TMA, 2 hidden-map TMA, 3..18 producers
-constexpr int kProdWarp0 = 3, kProdThreads = 16 * 32;
+constexpr int kWarps = 18, kThreads = kWarps * 32;      // warp 0 MMA issuer, 1 TMA pump (weights + hidden maps), 2..17 producers
+constexpr int kProdWarp0 = 2, kProdThreads = 16 * 32;   // (576 threads: 112 registers per thread, no spills in the producers)
 constexpr int kColH0 = 0, kColH1 = 160, kColD = 320, kColA = 384, kAColsPerStage = 32, kTmemCols = 512;
 
 constexpr int kOffZ = kDcnWBytes;                       // 73728
@@ -75,6 +77,7 @@ struct Params {
   int B, H, W, out_mode, x_batch;
   int y_nb, y_cs, y_grp[8];  // c8 placement, as in dcn_tex_sm100.cu
   int tiles_x, tiles_per_img, num_tiles;
+  int poll_ns;               // back-off between failed probes of the producers' long waits (0: none)
 };
 
 struct TileCoord { int b, h0, w0; };
@@ -108,6 +111,16 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
+
+// Long waits of the producer warps (a head GEMM or a DCN tap away): probe, then sleep -- every probe of an mbarrier is a wavefront in
+// the L1TEX data stage, the resource this kernel saturates (ncu: tensor-core operand reads 45 % + texture 34 % + LSU 19 %).
+__device__ __forceinline__ void wait_backoff(uint32_t bar, uint32_t parity, int ns) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap ztm) {
@@ -159,18 +172,18 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
   if (warp == 0) {
     // ======================================= MMA issuer =======================================
     const uint32_t idesc_h = ptx::make_idesc_bf16(128, kNT), idesc_d = make_idesc_f16(128, 64);
-    ptx::mbar_wait(BAR(kBarDcnW), 0);
+    ptx::mbar_wait_parked(BAR(kBarDcnW), 0);
     int wst = 0, wph = 0, ast = 0, aph = 0;
     uint32_t q = 0;                        // triples issued by this CTA so far (3 per tile)
     auto issue_dcn = [&](uint32_t qq) {    // the three DCN taps of triple qq: A operand from the TMEM ring, weights resident
       const int T = (int)(qq % 3u);
       if (T == 0) {                        // first tap of a tile overwrites the accumulator: the previous tile must be drained
-        ptx::mbar_wait(BAR(kBarDEmpty), ((qq / 3u) & 1u) ^ 1u);
+        ptx::mbar_wait_parked(BAR(kBarDEmpty), ((qq / 3u) & 1u) ^ 1u);
         ptx::tc_fence_after();
       }
       for (int tl = 0; tl < 3; ++tl) {
         const int tap = T * 3 + tl;
-        ptx::mbar_wait(BAR(kBarAFull + ast), aph);
+        ptx::mbar_wait_parked(BAR(kBarAFull + ast), aph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a0 = tmem_base + kColA + ast * kAColsPerStage;
@@ -189,13 +202,13 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
     };
     for (int it = 0; it < my_tiles; ++it) {
       const int zb = it & 1;
-      ptx::mbar_wait(BAR(kBarZFull + zb), (it >> 1) & 1);
+      ptx::mbar_wait_parked(BAR(kBarZFull + zb), (it >> 1) & 1);
       ptx::tc_fence_after();
       for (int T = 0; T < 3; ++T) {
-        ptx::mbar_wait(BAR(kBarHEmpty), (q & 1u) ^ 1u);      // the producers hold the previous triple's accumulators in registers
+        ptx::mbar_wait_parked(BAR(kBarHEmpty), (q & 1u) ^ 1u);      // the producers hold the previous triple's accumulators in registers
         ptx::tc_fence_after();
         for (int ht = 0; ht < 9; ++ht) {
-          ptx::mbar_wait(BAR(kBarWFull + wst), wph);
+          ptx::mbar_wait_parked(BAR(kBarWFull + wst), wph);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t za = s_z + zb * 2 * kZBytes + ((ht / 3) * kHaloW + (ht % 3)) * 16;
@@ -224,33 +237,41 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
     }
     if (q > 0) issue_dcn(q - 1);
   } else if (warp == 1) {
-    // ======================================= weights: DCN (once), head pieces (ring) =======================================
+    // ======================================= TMA pump: DCN weights (once), head weight pieces (ring), hidden-map halos =======================================
+    // One thread feeds both queues with non-blocking probes, so that a full weight ring never delays a halo load or vice versa.
     if (lane == 0) {
+      ptx::prefetch_tmap(&ztm);
       ptx::mbar_arrive_expect_tx(BAR(kBarDcnW), kDcnWBytes);
       for (int t = 0; t < 9; ++t) ptx::bulk_g2s(s_dw + t * kTapWBytes, p.dw + t * kTapWBytes, kTapWBytes, BAR(kBarDcnW));
-      int wst = 0, wph = 0;
-      for (int it = 0; it < my_tiles; ++it)
-        for (int piece = 0; piece < 27; ++piece) {         // (triple, head tap) in issue order: [3][9] pieces, contiguous in HBM
-          ptx::mbar_wait(BAR(kBarWEmpty + wst), wph ^ 1);
+      int wst = 0, wph = 0, piece = 0, pit = 0, zit = 0;
+      uint32_t idle = 0;
+      while (pit < my_tiles || zit < my_tiles) {
+        bool progress = false;
+        if (zit < my_tiles && ptx::mbar_test_wait(BAR(kBarZEmpty + (zit & 1)), ((zit >> 1) & 1) ^ 1)) {
+          const int zb = zit & 1;
+          const TileCoord tc = tile_coord(p, blockIdx.x + zit * gridDim.x);
+          ptx::mbar_arrive_expect_tx(BAR(kBarZFull + zb), 2 * kZBytes);
+          // box = (10 px x 8 ch, 18 rows, 8 chunks): lands as [chunk][18][10][8] = the canonical K-major operand; out-of-frame
+          // rows / columns arrive as zeros = the convolution's zero padding
+          ptx::tma_load_5d(s_z + zb * 2 * kZBytes, &ztm, BAR(kBarZFull + zb), (tc.w0 - 1) * 8, tc.h0 - 1, 0, tc.b, 0);
+          ptx::tma_load_5d(s_z + zb * 2 * kZBytes + kZBytes, &ztm, BAR(kBarZFull + zb), (tc.w0 - 1) * 8, tc.h0 - 1, 0, tc.b + p.B, 0);
+          ++zit;
+          progress = true;
+        }
+        if (pit < my_tiles && ptx::mbar_test_wait(BAR(kBarWEmpty + wst), wph ^ 1)) {
+          // (triple, head tap) in issue order: [3][9] pieces, contiguous in HBM, the same 27 for every tile (L2-resident)
           ptx::mbar_arrive_expect_tx(BAR(kBarWFull + wst), kPiece);
           ptx::bulk_g2s(s_ring + wst * kPiece, p.hw + (size_t)piece * kPiece, kPiece, BAR(kBarWFull + wst));
           if (++wst == kWStages) { wst = 0; wph ^= 1; }
+          if (++piece == 27) { piece = 0; ++pit; }
+          progress = true;
         }
-    }
-    __syncwarp();
-  } else if (warp == 2) {
-    // ======================================= hidden-map halos (both evaluations), double buffered =======================================
-    if (lane == 0) {
-      ptx::prefetch_tmap(&ztm);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int zb = it & 1;
-        const TileCoord tc = tile_coord(p, blockIdx.x + it * gridDim.x);
-        ptx::mbar_wait(BAR(kBarZEmpty + zb), ((it >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(BAR(kBarZFull + zb), 2 * kZBytes);
-        // box = (10 px x 8 ch, 18 rows, 8 chunks): lands as [chunk][18][10][8] = the canonical K-major operand; out-of-frame
-        // rows / columns arrive as zeros = the convolution's zero padding
-        ptx::tma_load_5d(s_z + zb * 2 * kZBytes, &ztm, BAR(kBarZFull + zb), (tc.w0 - 1) * 8, tc.h0 - 1, 0, tc.b, 0);
-        ptx::tma_load_5d(s_z + zb * 2 * kZBytes + kZBytes, &ztm, BAR(kBarZFull + zb), (tc.w0 - 1) * 8, tc.h0 - 1, 0, tc.b + p.B, 0);
+        if (progress) {
+          idle = 0;
+        } else {
+          __nanosleep(250);
+          if (++idle > (1u << 28)) __trap();     // a protocol bug must fault, not hang
+        }
       }
     }
     __syncwarp();
@@ -270,7 +291,7 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
     auto epilogue = [&](int it) {                    // drain columns [16 qs, 16 qs + 16) of the DCN accumulator of tile `it`
       const TileCoord tc = tile_coord(p, blockIdx.x + it * gridDim.x);
       const int h = tc.h0 + ty, w = tc.w0 + tx;
-      ptx::mbar_wait(BAR(kBarDFull), it & 1);
+      wait_backoff(BAR(kBarDFull), it & 1, p.poll_ns);
       ptx::tc_fence_after();
       uint32_t r[16];
       tmem_ld16(lane_base + kColD + qs * 16, r);
@@ -312,7 +333,7 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
       for (int T = 0; T < 3; ++T) {
         // ---- this thread's 2 x 36 head outputs of triple T: columns qs * 36 + (tl * 12 + gi * 3 + {dy, dx, m})
         uint32_t a0[36], a1[36];
-        ptx::mbar_wait(BAR(kBarHFull), q & 1u);
+        wait_backoff(BAR(kBarHFull), q & 1u, p.poll_ns);
         ptx::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -322,7 +343,15 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(BAR(kBarHEmpty));             // the head GEMM of the next triple may overwrite both accumulators
-        const float *hb = hbias_s + T * kNT + qs * 36;
+        float hb[36];                                  // this thread's 36 biases: 9 broadcast LDS.128 (144-byte aligned rows)
+        {
+          const float4 *hb4 = reinterpret_cast<const float4 *>(hbias_s + T * kNT + qs * 36);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            const float4 v = hb4[c];
+            hb[4 * c] = v.x; hb[4 * c + 1] = v.y; hb[4 * c + 2] = v.z; hb[4 * c + 3] = v.w;
+          }
+        }
         uint2 fld[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
@@ -342,21 +371,22 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
             *reinterpret_cast<uint4 *>(dst + (size_t)P * 2) = make_uint4(fld[tl * 4 + 2].x, fld[tl * 4 + 2].y, fld[tl * 4 + 3].x, fld[tl * 4 + 3].y);
           }
         }
-        // ---- 12 texture fetches: reference order offset = residual + flow (arch:3347), then h_im = base + offset (.cu:614-615)
-        float4 tv[12];
+        // ---- texture fetches, two taps (8 fetches) in flight: reference order offset = residual + flow (arch:3347), then
+        //      h_im = base + offset (.cu:614-615); x mask -> fp16 A operand (row = TMEM lane, K elements 16 qs .. +15 = columns 8 qs .. +7)
         const float hbT = (float)(h - 1 + T);
-#pragma unroll
-        for (int tl = 0; tl < 3; ++tl) {
+        float4 tv[3][4];
+        auto fetch = [&](int tl) {
 #pragma unroll
           for (int gi = 0; gi < 4; ++gi) {
             const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&fld[tl * 4 + gi].x));
             const float h_im = __fadd_rn(hbT, __fadd_rn(d.x, mvy));
             const float w_t = __fadd_rn(wb0 + (float)tl, __fadd_rn(d.y, mvx));
             const float hc = fminf(fmaxf(h_im, -1.f), Hf);      // stay inside this quad's plane (+ zero border); NaN -> -1 -> 0
-            tv[tl * 4 + gi] = tex2D<float4>(tex, w_t, hc + (py + (float)(gi * plane_rows)));
+            tv[tl][gi] = tex2D<float4>(tex, w_t, hc + (py + (float)(gi * plane_rows)));
           }
-        }
-        // ---- x mask -> fp16 A operand of the three taps (row = TMEM lane, K elements 16 qs .. +15 = columns 8 qs .. +7)
+        };
+        fetch(0);
+        fetch(1);
 #pragma unroll
         for (int tl = 0; tl < 3; ++tl) {
           uint32_t o[8];
@@ -364,11 +394,12 @@ mv_head_dcn_fused_sm100_kernel(const __grid_constant__ Params p, const __grid_co
           for (int gi = 0; gi < 4; ++gi) {
             const uint32_t mm = __byte_perm(fld[tl * 4 + gi].y, 0, 0x1010);      // (m, m) fp16x2
             const __half2 m2 = *reinterpret_cast<const __half2 *>(&mm);
-            const float4 v = tv[tl * 4 + gi];
+            const float4 v = tv[tl][gi];
             o[gi * 2 + 0] = h2_as_u32(__hmul2(m2, __floats2half2_rn(v.x, v.y)));
             o[gi * 2 + 1] = h2_as_u32(__hmul2(m2, __floats2half2_rn(v.z, v.w)));
           }
-          ptx::mbar_wait(BAR(kBarAEmpty + ast), aph ^ 1);
+          if (tl == 0) fetch(2);                       // its latency hides under the pack / store of taps 0 and 1
+          wait_backoff(BAR(kBarAEmpty + ast), aph ^ 1, p.poll_ns);
           ptx::tc_fence_after();
           ptx::tmem_st8(lane_base + kColA + ast * kAColsPerStage + qs * 8, o);
           ptx::tmem_st_wait();
@@ -446,6 +477,10 @@ static int run(const void *z_c8, const void *head_wpk, const float *head_bias, f
   const long long nt = (long long)p.tiles_per_img * B;
   CDFO_REQUIRE(nt < (1ll << 31), CDFO_ERR_UNSUPPORTED, "cdfo_mv_head_dcn_fused_sm100_fwd: too many tiles");
   p.num_tiles = (int)nt;
+  {
+    static const int poll = getenv("CDFO_FUSED_POLL_NS") ? atoi(getenv("CDFO_FUSED_POLL_NS")) : 0;
+    p.poll_ns = poll;
+  }
   int grid = num_ctas > 0 ? num_ctas : kNumSMs;
   if (grid > p.num_tiles) grid = p.num_tiles;
   static bool attr_done = false;

@@ -53,6 +53,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same with a suspend-time hint: the warp is parked by the hardware until the phase completes or `ns` nanoseconds pass, instead of
+// re-polling shared memory every few cycles.  Each poll is a wavefront in the L1TEX data stage, which the tensor-core operand reads and
+// the texture fetches of a fused kernel need (ncu on mv_head_dcn_fused_sm100_kernel: 27 M polls = 13 % of that stage without the hint).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 20)) __trap();      // ~20 s: a protocol bug must fault, not hang
+  }
+}
+
 // ------------------------------------------------------------------ proxies / bulk copies
 // Generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / TMA reads).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

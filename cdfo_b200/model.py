@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import hotpath
+from . import config, hotpath
 
 _NB = (0, 1, 2, 4, 5, 6)
 
@@ -353,6 +353,9 @@ class CVSR_V8(nn.Module):
     # -- feature extraction of `n` frames ("next" row f2; cuDNN for now)
     def _features(self, x, pms):
         dt = self.lowp
+        if dt is torch.bfloat16 and config.features_c8 and x.is_cuda:
+            from . import conv, features
+            return conv.from_c8(features.feature_extraction_c8(self, x, pms))
         if dt is not None:
             with torch.autocast("cuda", dtype=dt):
                 l1 = _lrelu(self.conv_first(x))

@@ -320,6 +320,31 @@ int cdfo_psnr_ssim_u8(const uint8_t *res, const uint8_t *gt, int B, int H, int W
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
 
+/* ---- feature extraction on c8 bf16 (csrc/features_c8.cu; arch/SIDECVSR_our.py:1441-1475, :1643-1653) ----
+ * "c8" = [B, C/8, H, W, 8] bf16.  fp32 arithmetic, fixed reduction orders. */
+/* Conv2d(1, Co, 3, 1, 1) on x [B,1,H,W] fp32 (conv_first / conv_second, arch:4376-4377) -> y c8; lrelu != 0 applies LeakyReLU(0.1). */
+int cdfo_prior_conv_c8_fwd(const float *x, const float *w, const float *bias, void *y_c8, int B, int Co, int H, int W, int lrelu, void *stream);
+/* WithBias LayerNorm over the 64 channels of each pixel (arch:1169-1198). */
+int cdfo_layernorm_c8_fwd(const void *x_c8, const float *gamma, const float *beta, void *y_c8, int B, int H, int W, float eps, void *stream);
+/* Depthwise 3x3 / stride 1 / padding 1, no bias (qkv_dwconv, arch:1558): w [C, 9] fp32. */
+int cdfo_dwconv3x3_c8_fwd(const void *x_c8, const float *w, void *y_c8, int B, int C, int H, int W, void *stream);
+/* Per-head Gram q k^T over H*W + squared row norms of q (channels 0..63) and k (64..127) of qkv_c8 [B, C/8 >= 16, H, W, 8], 8 heads x 8
+ * channels: partial [B, parts, 640] fp32 = (G [8][8][8] | |q|^2 [64] | |k|^2 [64]) per pixel range. */
+int cdfo_mdta_gram_c8_fwd(const void *qkv_c8, float *partial, int B, int C, int H, int W, int parts, void *stream);
+/* M [B, 64, 64] = project_out . blockdiag(softmax(G / (|q| |k|) * temperature)) from the partial sums (arch:1567-1576). */
+int cdfo_mdta_fold_fwd(const float *partial, const float *temperature, const float *project_out, float *M, int B, int parts, void *stream);
+/* out1 = x1 + M v (v = channels [v_channel0, +64) of qkv_c8); out2 (optional) = out1 + x2. */
+int cdfo_mdta_apply_c8_fwd(const void *qkv_c8, int C, int v_channel0, const float *M, const void *x1_c8, const void *x2_c8, void *out1_c8,
+                           void *out2_c8, int B, int H, int W, void *stream);
+/* 16 -> 16 channels, 3x3, stride 2, padding 2, + LeakyReLU(0.1): convolution (transposed = 0, w [co][ci][3][3], Ho = (Hi + 1) / 2 + 1) or
+ * transposed convolution (transposed = 1, w [ci][co][3][3], Ho = 2 Hi - 3 or 2 Hi - 2 with output_padding 1) of the side branch
+ * (arch:1815-1832).  y_c8 has y_channels >= 16 channels; channels 0..15 are written. */
+int cdfo_conv16_c8_fwd(const void *x_c8, const float *w, const float *bias, void *y_c8, int B, int Hi, int Wi, int Ho, int Wo, int y_channels,
+                       int transposed, void *stream);
+/* SpatialAttention (arch:1883-1899) on a 16-channel c8 map: y = x * sigmoid(conv7x7([max_c x, mean_c x]) + bias); w [1][2][7][7];
+ * pooled_ws: B * H * W * 8 bytes of scratch. */
+int cdfo_spatial_gate_c8_fwd(const void *x_c8, const float *w, const float *bias, void *pooled_ws, void *y_c8, int B, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
