@@ -41,11 +41,13 @@ def lib():
         _lib.cdfo_psnr_ssim_workspace_bytes.restype = ctypes.c_size_t
         _lib.cdfo_conv3x3_pair_sm100_weight_bytes.restype = ctypes.c_size_t
         _lib.cdfo_conv4x4s2_pair_sm100_weight_bytes.restype = ctypes.c_size_t
+        _lib.cdfo_lra_mask_logits_workspace_bytes.restype = ctypes.c_size_t
     return _lib
 
 
 # number of CUDA kernels each C-ABI entry launches (for bench.py's gpu_launches claim)
-_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_mdta_fwd": 3, "cdfo_psnr_ssim_u8": 3}
+_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_lra_c8_fwd": 5, "cdfo_mdta_fwd": 3, "cdfo_psnr_ssim_u8": 3, "cdfo_lra_mask_logits_fwd": 2,
+             "cdfo_spatial_gate_c8_fwd": 2}
 launch_count = 0
 
 

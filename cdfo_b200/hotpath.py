@@ -207,6 +207,21 @@ def _lra_tap_tables(mod):
                                                    mod.directH1_conv.bias), build)
 
 
+@torch.no_grad()
+def mask_logits(mod, v):
+    """v_max [B, 64] = ReLU(conv_du_re2(mean ReLU(conv_du_re.2(v)))) (arch:2183-2186) from v = ReLU(conv_du_re.0(res)) [B, 64, H, W] fp32:
+    the stride-2 convolution on the tensor cores with ReLU + spatial sum in its epilogue, then the pooled 64 x 64 product (csrc/lra_mask_logits.cu)."""
+    B, C, H, W = v.shape
+    if C != 64:
+        raise _lib.CdfoError("mask_logits: 64 channels expected")
+    c2, c3 = mod.conv_du_re._modules["2"], mod.conv_du_re2._modules["0"]
+    ws = torch.empty(_lib.lib().cdfo_lra_mask_logits_workspace_bytes(B, H, W), dtype=torch.uint8, device=v.device)
+    vmax = torch.empty((B, 64), dtype=torch.float32, device=v.device)
+    _lib.call("cdfo_lra_mask_logits_fwd", _lib.ptr(_f32(v)), _lib.ptr(_f32(c2.weight)), _lib.ptr(_f32(c2.bias)), _lib.ptr(_f32(c3.weight).reshape(64, 64)),
+              _lib.ptr(_f32(c3.bias)), _lib.ptr(vmax), _lib.ptr(ws), B, H, W, _lib.stream_ptr(v.device))
+    return vmax
+
+
 def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
     """cdfo_pointwise_conv_fwd: tensor-core 1x1 convolution on NCHW fp32 (mode 0: x = in1 + in2; mode 1: pixel-major cat)."""
     B, K, H, W = in1.shape
@@ -230,9 +245,7 @@ def long_range_attention(mod, res, x, u, x2=None, out8=None, channel0=0):
     x2 = None if x2 is None else _f32(x2)
     du0 = mod.conv_du_re._modules["0"]
     v = _pointwise(res, None, du0.weight, du0.bias, act=1)
-    v = F.relu(_c(mod.conv_du_re._modules["2"], v, stride=2, padding=2))
-    v = v.mean(dim=(2, 3), keepdim=True)
-    vmax = F.relu(_c(mod.conv_du_re2._modules["0"], v)).reshape(B, C).contiguous()   # bilinear up of a 1x1 map = broadcast
+    vmax = mask_logits(mod, v)                                                          # bilinear up of a 1x1 map = broadcast
     qv = _pointwise(x, x2, mod.input_conv.weight, mod.input_conv.bias, act=0)
     nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)

@@ -320,6 +320,14 @@ int cdfo_psnr_ssim_u8(const uint8_t *res, const uint8_t *gt, int B, int H, int W
 /* tcgen05 plumbing self-test: D[128,64] fp32 = A[128,64] * B[64,64]^T (row-major bf16 inputs). */
 int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo, void *stream);
 
+/* ---- A8, mask logits after conv_du_re.0 (csrc/lra_mask_logits.cu; arch/SIDECVSR_our.py:2183-2186) ----
+ * v_max [B, 64] = ReLU(conv_du_re2(mean_hw ReLU(conv_du_re.2(v)))): v [B, 64, H, W] fp32 = ReLU(conv_du_re.0(res)); w2 [64,64,3,3] / b2 the
+ * stride-2 padding-2 convolution, w3 [64,64] / b3 the 1x1 on the pooled vector.  Tensor cores (TF32 mma.sync), the strided activation is
+ * never written; workspace: cdfo_lra_mask_logits_workspace_bytes(B, H, W) bytes of tile sums (fixed-order reduction). */
+size_t cdfo_lra_mask_logits_workspace_bytes(int B, int H, int W);
+int cdfo_lra_mask_logits_fwd(const float *v, const float *w2, const float *b2, const float *w3, const float *b3, float *vmax,
+                             void *workspace, int B, int H, int W, void *stream);
+
 /* ---- feature extraction on c8 bf16 (csrc/features_c8.cu; arch/SIDECVSR_our.py:1441-1475, :1643-1653) ----
  * "c8" = [B, C/8, H, W, 8] bf16.  fp32 arithmetic, fixed reduction orders. */
 /* Conv2d(1, Co, 3, 1, 1) on x [B,1,H,W] fp32 (conv_first / conv_second, arch:4376-4377) -> y c8; lrelu != 0 applies LeakyReLU(0.1). */

@@ -123,3 +123,23 @@ def test_lra_col_bf16_vs_tf32(cuda_dev):
     err = (out - ref).abs().max().item()
     print("LRA column pass bf16 vs tf32: max diff %.3g (max|out| %.3g)" % (err, ref.abs().max().item()))
     assert err <= 4e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 24, 40), (1, 30, 34), (3, 64, 72), (1, 272, 480)])
+def test_mask_logits_kernel_vs_torch(cuda_dev, B, H, W):
+    """csrc/lra_mask_logits.cu (stride-2 convolution on TF32 tensor cores + ReLU + mean + 1x1 + ReLU, arch:2183-2186) against fp32 torch."""
+    import torch.nn.functional as F
+    from cdfo_b200 import hotpath
+    from cdfo_b200.model import LLongRangAttention
+    torch.manual_seed(B * H + W)
+    mod = LLongRangAttention(64).to(cuda_dev)
+    v = torch.relu(torch.randn(B, 64, H, W) * 0.5)
+    c2, c3 = mod.conv_du_re._modules["2"], mod.conv_du_re2._modules["0"]
+    with torch.no_grad():
+        r = F.relu(F.conv2d(v.double(), c2.weight.detach().cpu().double(), c2.bias.detach().cpu().double(), stride=2, padding=2))
+        ref = F.relu(F.conv2d(r.mean(dim=(2, 3), keepdim=True), c3.weight.detach().cpu().double(), c3.bias.detach().cpu().double())).reshape(B, 64)
+    got = hotpath.mask_logits(mod, v.to(cuda_dev)).cpu().double()
+    err = (got - ref).abs().max().item()
+    print("mask logits %dx%dx%d: max err %.3g (max|ref| %.3g)" % (B, H, W, err, ref.abs().max().item()))
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(hotpath.mask_logits(mod, v.to(cuda_dev)).cpu().double(), got)      # fixed-order reduction

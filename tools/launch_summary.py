@@ -3,18 +3,22 @@ import collections
 import csv
 import sys
 
-OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::", "cpair::", "c4::")
+OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::", "cpair::", "c4::", "fdcn::", "fc8::", "lml::")
 
 
-def main(src, dst, title, note):
+def main(src, dst, title, note, marker=None, first=0, last=0):
+    """marker / first / last: keep only the launches from the `first`-th to just before the `last`-th launch (1-based) of the kernel whose
+    name contains `marker` -- e.g. the fused alignment kernel runs once per step, so (marker, 5, 7) = steps 5 and 6 of the process."""
     rows = list(csv.reader(open(src)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr = rows[hi]
     ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg, n = collections.OrderedDict(), 0
-    for r in rows[hi + 1:]:
-        if len(r) < len(hdr):
-            continue
+    body = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+    if marker:
+        hits = [i for i, r in enumerate(body) if marker in r[ik]]
+        body = body[hits[first - 1]:hits[last - 1]]
+    for r in body:
         v = float(r[iv].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[iu], 1.0)
         a = agg.setdefault(r[ik], [0.0, 0])
@@ -34,4 +38,7 @@ def main(src, dst, title, note):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4])
+    if len(sys.argv) > 5:
+        main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], int(sys.argv[6]), int(sys.argv[7]))
+    else:
+        main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4])
