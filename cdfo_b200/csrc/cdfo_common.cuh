@@ -49,6 +49,18 @@ __device__ __forceinline__ float warp_src_coord(int pos, float flow, int size) {
   return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));                 // ((g+1)/2)*(s-1)
 }
 
+// LLongRangAttention tap tables (csrc/lra.cu, csrc/lra_col_sm100.cu): device pointers, built on the host from directW1_conv / directH1_conv
+struct LraTables {
+  const float *kw;       // [9] taps along channels
+  const float *kh;       // [9] taps along H
+  const float *k1;       // [64]    K1[c]      = sum of in-range taps of a bump centred at channel c
+  const float *r;        // [64*64] R[c1][c2]  = sum_c kw[c1-c+4] kw[c2-c+4] over in-range c
+  float beta, bh;        // biases of directW1_conv / directH1_conv
+};
+// csrc/lra_col_sm100.cu: tcgen05 column pass; 1 = launched, 0 = shape outside its limits (caller falls back), < 0 = error
+int lra_col_sm100_launch(const float *vrow_t, const uint8_t *midx, const float *qsel, float *long_out, const LraTables &t, int B, int H, int W,
+                         cudaStream_t s);
+
 // csrc/pointwise.cu: tensor-core 1x1 convolution (see cdfo_pointwise_conv_fwd in include/cdfo_b200.h)
 int pointwise_conv(const float *in1, const float *in2, const float *w, const float *bias, const float *resid1, const float *resid2,
                    float *out, int B, int K, int Co, int HW, int act, int mode, cudaStream_t s, void *out_c8 = nullptr,

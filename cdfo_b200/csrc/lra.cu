@@ -19,14 +19,6 @@
 
 namespace cdfo {
 
-struct LraTables {       // device pointers, built on the host from directW1_conv / directH1_conv
-  const float *kw;       // [9] taps along channels
-  const float *kh;       // [9] taps along H
-  const float *k1;       // [64]    K1[c]      = sum of in-range taps of a bump centred at channel c
-  const float *r;        // [64*64] R[c1][c2]  = sum_c kw[c1-c+4] kw[c2-c+4] over in-range c
-  float beta, bh;        // biases of directW1_conv / directH1_conv
-};
-
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -732,13 +724,130 @@ __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__res
   });
 }
 
+// ---- tensor-core variant of the 8x8 window pass (the one cdfo_lra_fwd launches) ----
+// One CTA (4 warps) per window, a warp per 16 query tokens; S = q q^T and O = P V on warp-level mma.sync m16n8k16 bf16 (fp32 accumulate).
+// The window logits reach +-40 (dense 64-d dot products of unnormalised q), where one bf16 rounding of q would move the softmax weights by
+// percents, so q is split into bf16 hi + lo parts and the scores are the three-term product hi.hi + hi.lo + lo.hi (error ~2^-16 |q|^2, the
+// same order as the TF32 rounding of the other passes); P and V are single bf16 (the consumer rounds the result to bf16 anyway).  The
+// probabilities feed the second MMA straight from the score accumulators (C fragments of key tiles 2s, 2s+1 = A fragment of key step s),
+// V is held transposed.  Shared memory 27.6 KB per CTA: eight windows per SM hide each other's load phase.
+constexpr int kWinTcThreads = 128, kWinLd = 36;     // row stride in 32-bit words (72 bf16): 36 = 4 (mod 32), conflict-free fragment loads
+__global__ void __launch_bounds__(kWinTcThreads, 6) lra_win_tc_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
+                                                                      float *__restrict__ loc_out, int H, int W) {
+  __shared__ uint32_t Qh[64 * kWinLd], Ql[64 * kWinLd], Vt[64 * kWinLd];      // [token][channel pairs], [token][..], [channel][key pairs]
+  const int b = blockIdx.z, wy = blockIdx.y, wx = blockIdx.x;
+  const int HW = H * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  {
+    // thread = (token pair for V / token for Q, channel group): loads are 32-byte runs of 8 consecutive pixels per (channel, window row)
+    const int tok = tid & 63, half = tid >> 6;            // half 0: channels 0..31, half 1: 32..63
+    const int h = wy * 8 + (tok >> 3), w = wx * 8 + (tok & 7);
+    const size_t pix = (size_t)h * W + w;
+    const int cm = midx[(size_t)b * HW + pix];
+    const float *qp = qv + ((size_t)b * 128 + half * 32) * HW + pix;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const int c = half * 32 + 2 * k;
+      float q0 = __ldg(qp + (size_t)(2 * k) * HW), q1 = __ldg(qp + (size_t)(2 * k + 1) * HW);
+      if (cm == c) q0 = 0.f;                              // (1 - mask) * q, arch:2236-2239
+      if (cm == c + 1) q1 = 0.f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(q0), h1 = __float2bfloat16_rn(q1);
+      Qh[tok * kWinLd + (c >> 1)] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+      Ql[tok * kWinLd + (c >> 1)] = pack_bf16x2(q0 - __bfloat162float(h0), q1 - __bfloat162float(h1));
+      // V transposed: element (channel, key = tok) -- 16-bit stores, two tokens share a word
+      const float v0 = __ldg(qp + (size_t)(64 + 2 * k) * HW), v1 = __ldg(qp + (size_t)(64 + 2 * k + 1) * HW);
+      reinterpret_cast<__nv_bfloat16 *>(Vt)[(c * kWinLd) * 2 + tok] = __float2bfloat16_rn(v0);
+      reinterpret_cast<__nv_bfloat16 *>(Vt)[((c + 1) * kWinLd) * 2 + tok] = __float2bfloat16_rn(v1);
+    }
+  }
+  __syncthreads();
+  const int q0r = warp * 16;
+  uint32_t ah[4][4], al[4][4];                            // A fragments of this warp's 16 queries, hi and lo parts
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    ah[s][0] = Qh[(q0r + g) * kWinLd + 8 * s + tq];      ah[s][1] = Qh[(q0r + g + 8) * kWinLd + 8 * s + tq];
+    ah[s][2] = Qh[(q0r + g) * kWinLd + 8 * s + tq + 4];  ah[s][3] = Qh[(q0r + g + 8) * kWinLd + 8 * s + tq + 4];
+    al[s][0] = Ql[(q0r + g) * kWinLd + 8 * s + tq];      al[s][1] = Ql[(q0r + g + 8) * kWinLd + 8 * s + tq];
+    al[s][2] = Ql[(q0r + g) * kWinLd + 8 * s + tq + 4];  al[s][3] = Ql[(q0r + g + 8) * kWinLd + 8 * s + tq + 4];
+  }
+  float sc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc[n][i] = 0.f;
+    const uint32_t *kh_ = Qh + (8 * n + g) * kWinLd + tq, *kl_ = Ql + (8 * n + g) * kWinLd + tq;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const uint32_t bh0 = kh_[8 * s], bh1 = kh_[8 * s + 4];
+      mma_bf16(sc[n], al[s], bh0, bh1);                   // small terms first
+      mma_bf16(sc[n], ah[s], kl_[8 * s], kl_[8 * s + 4]);
+      mma_bf16(sc[n], ah[s], bh0, bh1);
+    }
+  }
+  float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+    mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    sc[n][0] = expf(sc[n][0] - mx[0]); sc[n][1] = expf(sc[n][1] - mx[0]);
+    sc[n][2] = expf(sc[n][2] - mx[1]); sc[n][3] = expf(sc[n][3] - mx[1]);
+    sum[0] += sc[n][0] + sc[n][1];
+    sum[1] += sc[n][2] + sc[n][3];
+  }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {        // 16 keys per step
+    const uint32_t ap[4] = {pack_bf16x2(sc[2 * s][0], sc[2 * s][1]), pack_bf16x2(sc[2 * s][2], sc[2 * s][3]),
+                            pack_bf16x2(sc[2 * s + 1][0], sc[2 * s + 1][1]), pack_bf16x2(sc[2 * s + 1][2], sc[2 * s + 1][3])};
+    const uint32_t *vr = Vt + g * kWinLd + 8 * s + tq;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) mma_bf16(o[n], ap, vr[8 * n * kWinLd], vr[8 * n * kWinLd + 4]);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+  }
+  const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+  const int t0 = q0r + g, t1 = t0 + 8;
+  float *d0 = loc_out + (((size_t)b * H + wy * 8 + (t0 >> 3)) * W + wx * 8 + (t0 & 7)) * 64 + 2 * tq;
+  float *d1 = loc_out + (((size_t)b * H + wy * 8 + (t1 >> 3)) * W + wx * 8 + (t1 & 7)) * 64 + 2 * tq;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    *reinterpret_cast<float2 *>(d0 + 8 * n) = make_float2(o[n][0] * inv0, o[n][1] * inv0);
+    *reinterpret_cast<float2 *>(d1 + 8 * n) = make_float2(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
 }  // namespace cdfo
 
 using namespace cdfo;
 
 static bool g_lra_col_tf32 = false;   // cdfo_lra_set_col_precision: A/B switch (tests, tools)
+static bool g_lra_col_tc = true;      // cdfo_lra_set_col_tcgen05: the tcgen05 column kernel (default) vs the warp-level mma.sync kernels
+static bool g_lra_win_tc = true;      // cdfo_lra_set_win_tensor_core: the bf16 split tensor-core window kernel (default) vs the fp32 SIMT one
 extern "C" int cdfo_lra_set_col_precision(int tf32) {
   g_lra_col_tf32 = tf32 != 0;
+  return CDFO_OK;
+}
+extern "C" int cdfo_lra_set_col_tcgen05(int on) {
+  g_lra_col_tc = on != 0;
+  return CDFO_OK;
+}
+extern "C" int cdfo_lra_set_win_tensor_core(int on) {
+  g_lra_win_tc = on != 0;
   return CDFO_OK;
 }
 
@@ -806,13 +915,20 @@ static int lra_run(const float *qv, const float *u, const float *vmax, const flo
     attr = true;
   }
   lra_row_kernel<<<dim3(H, B), kRowThreads, row_smem, s>>>(qv, midx, qsel, vrow_t, t, H, W);
-  if (g_lra_col_tf32) {
+  int col_done = 0;
+  if (!g_lra_col_tf32 && g_lra_col_tc) {     // csrc/lra_col_sm100.cu: whole score tile in tensor memory (H <= 448)
+    col_done = lra_col_sm100_launch(vrow_t, midx, qsel, long_out, t, B, H, W, s);
+    if (col_done < 0) return col_done;
+  }
+  if (col_done) {
+  } else if (g_lra_col_tf32) {
     lra_col_kernel<<<dim3(W, B), kColThreads, col_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
   } else {
     const size_t col16_smem = ((size_t)Hk * kQw + 64 * ((size_t)Hk / 2 + 4) + 2 * (size_t)(H + 8) + 16) * 4;
     lra_col_bf16_kernel<<<dim3(W, B), kColThreads, col16_smem, s>>>(vrow_t, midx, qsel, long_out, t, H, W);
   }
-  lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, win_smem, s>>>(qv, midx, loc_out, H, W);
+  if (g_lra_win_tc) lra_win_tc_kernel<<<dim3(W / 8, H / 8, B), kWinTcThreads, 0, s>>>(qv, midx, loc_out, H, W);
+  else lra_win_kernel<<<dim3(W / 8, H / 8, B), kWinThreads, win_smem, s>>>(qv, midx, loc_out, H, W);
   if (int rc = check_launch("cdfo_lra_fwd")) return rc;
   // fuse: 1x1 conv(128 -> 64) over cat[long, local] (pixel-major) + bias + x (+ x2): tensor-core pointwise kernel
   return pointwise_conv(long_out, loc_out, fuse_w, fuse_b, x, x2, out, B, 128, 64, HW, 0, 1, s, out_c8, out_channels, channel0);

@@ -248,6 +248,11 @@ int cdfo_lra_fwd(const float *qv, const float *u, const float *vmax, const float
  * half of the model's cat([fea, x_n]) (arch:4454), the input of conv_expand_fea_r; no fp32 copy of x_n exists. */
 /* Column pass operands: 0 (default) = bf16 mma.sync m16n8k16, 1 = TF32 m16n8k8 (the first-generation kernel; A/B switch). */
 int cdfo_lra_set_col_precision(int tf32);
+/* Column pass: 1 (default) = the tcgen05 kernel (csrc/lra_col_sm100.cu: score tile in tensor memory, bf16 operands; H <= 448), 0 = the
+ * warp-level mma.sync kernels of round 1.  A measurement / test switch. */
+int cdfo_lra_set_col_tcgen05(int on);
+/* 8x8 window pass: 1 (default) = tensor cores (bf16 hi/lo split scores, mma.sync), 0 = round 1's fp32 SIMT kernel. */
+int cdfo_lra_set_win_tensor_core(int on);
 int cdfo_lra_c8_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
                     float beta, float bh, const float *fuse_w, const float *fuse_b, void *out_c8, int out_channels, int channel0,
                     void *workspace, int B, int H, int W, void *stream);

@@ -108,10 +108,32 @@ def test_pointwise_conv_shapes(cuda_dev, K, Co, mode, H, W):
 
 
 def test_lra_col_bf16_vs_tf32(cuda_dev):
-    """The bf16 column pass (mma.sync m16n8k16, the default) against the TF32 one: same result to bf16-operand accuracy."""
+    """The bf16 mma.sync column pass against the TF32 one: same result to bf16-operand accuracy."""
     from cdfo_b200 import _lib
     B, H, W = 2, 72, 40          # H not a multiple of 64: masked keys in the last block; 5 query tiles over 9 warps
     res, x, u = _inputs(B, H, W, seed=3)
+    m = _model(cuda_dev)
+    res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
+    try:
+        _lib.call("cdfo_lra_set_col_tcgen05", 0)
+        _lib.call("cdfo_lra_set_col_precision", 1)
+        ref = m.RDAB(res, x, u)
+        _lib.call("cdfo_lra_set_col_precision", 0)
+        out = m.RDAB(res, x, u)
+    finally:
+        _lib.call("cdfo_lra_set_col_precision", 0)
+        _lib.call("cdfo_lra_set_col_tcgen05", 1)
+    err = (out - ref).abs().max().item()
+    print("LRA column pass bf16 vs tf32: max diff %.3g (max|out| %.3g)" % (err, ref.abs().max().item()))
+    assert err <= 4e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 72, 40), (1, 136, 24), (2, 272, 16), (1, 40, 8), (1, 264, 8)])
+def test_lra_col_tcgen05_vs_tf32(cuda_dev, B, H, W):
+    """The tcgen05 column pass (csrc/lra_col_sm100.cu: score tile in tensor memory, the default) against the TF32 mma.sync pass:
+    one / two / three 128-query tiles, one and two key chunks, H not a multiple of 16 * 8, rerun bit-identical."""
+    from cdfo_b200 import _lib
+    res, x, u = _inputs(B, H, W, seed=H + W)
     m = _model(cuda_dev)
     res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
     try:
@@ -121,8 +143,9 @@ def test_lra_col_bf16_vs_tf32(cuda_dev):
         _lib.call("cdfo_lra_set_col_precision", 0)
     out = m.RDAB(res, x, u)
     err = (out - ref).abs().max().item()
-    print("LRA column pass bf16 vs tf32: max diff %.3g (max|out| %.3g)" % (err, ref.abs().max().item()))
+    print("LRA column pass tcgen05 vs tf32 %dx%dx%d: max diff %.3g (max|out| %.3g)" % (B, H, W, err, ref.abs().max().item()))
     assert err <= 4e-3
+    assert torch.equal(m.RDAB(res, x, u), out)
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 24, 40), (1, 30, 34), (3, 64, 72), (1, 272, 480)])
@@ -143,3 +166,23 @@ def test_mask_logits_kernel_vs_torch(cuda_dev, B, H, W):
     print("mask logits %dx%dx%d: max err %.3g (max|ref| %.3g)" % (B, H, W, err, ref.abs().max().item()))
     assert err <= 2e-4 * max(1.0, ref.abs().max().item())
     assert torch.equal(hotpath.mask_logits(mod, v.to(cuda_dev)).cpu().double(), got)      # fixed-order reduction
+
+
+@pytest.mark.parametrize("B,H,W,scale", [(2, 24, 40, 0.5), (1, 64, 64, 1.5)])
+def test_lra_window_tensor_core_vs_fp32(cuda_dev, B, H, W, scale):
+    """The tensor-core window pass (bf16 hi/lo split scores, the default) against round 1's fp32 SIMT kernel, also with logits of
+    several tens (scale 1.5: |q|^2 ~ 100), where an unsplit bf16 product would be visibly wrong."""
+    from cdfo_b200 import _lib
+    res, x, u = _inputs(B, H, W, seed=7 * H + W)
+    x = x * scale / 0.5
+    m = _model(cuda_dev)
+    res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
+    try:
+        _lib.call("cdfo_lra_set_win_tensor_core", 0)
+        ref = m.RDAB(res, x, u)
+    finally:
+        _lib.call("cdfo_lra_set_win_tensor_core", 1)
+    out = m.RDAB(res, x, u)
+    err = (out - ref).abs().max().item()
+    print("LRA window pass tensor cores vs fp32 (x scale %.1f): max diff %.3g (max|out| %.3g)" % (scale, err, ref.abs().max().item()))
+    assert err <= 4e-3 * max(1.0, ref.abs().max().item())
