@@ -728,13 +728,13 @@ __global__ void __launch_bounds__(kWinThreads) lra_win_kernel(const float *__res
 // One CTA (4 warps) per window, a warp per 16 query tokens; S = q q^T and O = P V on warp-level mma.sync m16n8k16 bf16 (fp32 accumulate).
 // The window logits reach +-40 (dense 64-d dot products of unnormalised q), where one bf16 rounding of q would move the softmax weights by
 // percents, so q is split into bf16 hi + lo parts and the scores are the three-term product hi.hi + hi.lo + lo.hi (error ~2^-16 |q|^2, the
-// same order as the TF32 rounding of the other passes); P and V are single bf16 (the consumer rounds the result to bf16 anyway).  The
+// same order as the TF32 rounding of the other passes); P and V are split the same way (a peaked softmax copies a value row to the output).  The
 // probabilities feed the second MMA straight from the score accumulators (C fragments of key tiles 2s, 2s+1 = A fragment of key step s),
-// V is held transposed.  Shared memory 27.6 KB per CTA: eight windows per SM hide each other's load phase.
+// V is held transposed.  Shared memory 36.9 KB per CTA: six windows per SM hide each other's load phase.
 constexpr int kWinTcThreads = 128, kWinLd = 36;     // row stride in 32-bit words (72 bf16): 36 = 4 (mod 32), conflict-free fragment loads
 __global__ void __launch_bounds__(kWinTcThreads, 6) lra_win_tc_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
                                                                       float *__restrict__ loc_out, int H, int W) {
-  __shared__ uint32_t Qh[64 * kWinLd], Ql[64 * kWinLd], Vt[64 * kWinLd];      // [token][channel pairs], [token][..], [channel][key pairs]
+  __shared__ uint32_t Qh[64 * kWinLd], Ql[64 * kWinLd], Vt[64 * kWinLd], Vl[64 * kWinLd];   // [token][channel pairs] x 2, [channel][key pairs] x 2 (hi, lo)
   const int b = blockIdx.z, wy = blockIdx.y, wx = blockIdx.x;
   const int HW = H * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
@@ -756,8 +756,11 @@ __global__ void __launch_bounds__(kWinTcThreads, 6) lra_win_tc_kernel(const floa
       Ql[tok * kWinLd + (c >> 1)] = pack_bf16x2(q0 - __bfloat162float(h0), q1 - __bfloat162float(h1));
       // V transposed: element (channel, key = tok) -- 16-bit stores, two tokens share a word
       const float v0 = __ldg(qp + (size_t)(64 + 2 * k) * HW), v1 = __ldg(qp + (size_t)(64 + 2 * k + 1) * HW);
-      reinterpret_cast<__nv_bfloat16 *>(Vt)[(c * kWinLd) * 2 + tok] = __float2bfloat16_rn(v0);
-      reinterpret_cast<__nv_bfloat16 *>(Vt)[((c + 1) * kWinLd) * 2 + tok] = __float2bfloat16_rn(v1);
+      const __nv_bfloat16 vh0 = __float2bfloat16_rn(v0), vh1 = __float2bfloat16_rn(v1);
+      reinterpret_cast<__nv_bfloat16 *>(Vt)[(c * kWinLd) * 2 + tok] = vh0;
+      reinterpret_cast<__nv_bfloat16 *>(Vt)[((c + 1) * kWinLd) * 2 + tok] = vh1;
+      reinterpret_cast<__nv_bfloat16 *>(Vl)[(c * kWinLd) * 2 + tok] = __float2bfloat16_rn(v0 - __bfloat162float(vh0));
+      reinterpret_cast<__nv_bfloat16 *>(Vl)[((c + 1) * kWinLd) * 2 + tok] = __float2bfloat16_rn(v1 - __bfloat162float(vh1));
     }
   }
   __syncthreads();
@@ -809,11 +812,24 @@ __global__ void __launch_bounds__(kWinTcThreads, 6) lra_win_tc_kernel(const floa
     for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {        // 16 keys per step
-    const uint32_t ap[4] = {pack_bf16x2(sc[2 * s][0], sc[2 * s][1]), pack_bf16x2(sc[2 * s][2], sc[2 * s][3]),
-                            pack_bf16x2(sc[2 * s + 1][0], sc[2 * s + 1][1]), pack_bf16x2(sc[2 * s + 1][2], sc[2 * s + 1][3])};
-    const uint32_t *vr = Vt + g * kWinLd + 8 * s + tq;
+    // probabilities and values as bf16 hi + lo parts as well (P V = Ph Vh + Pl Vh + Ph Vl): a sharply peaked softmax copies one value
+    // row to the output, and a single bf16 rounding of it (2^-9 relative) would be the largest error of the whole module
+    uint32_t ap[4], apl[4];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) mma_bf16(o[n], ap, vr[8 * n * kWinLd], vr[8 * n * kWinLd + 4]);
+    for (int i = 0; i < 4; ++i) {
+      const float p0 = sc[2 * s + (i >> 1)][2 * (i & 1)], p1 = sc[2 * s + (i >> 1)][2 * (i & 1) + 1];
+      const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+      ap[i] = pack_bf16x2(h0, h1);
+      apl[i] = pack_bf16x2(p0 - h0, p1 - h1);
+    }
+    const uint32_t *vr = Vt + g * kWinLd + 8 * s + tq, *vl = Vl + g * kWinLd + 8 * s + tq;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const uint32_t b0 = vr[8 * n * kWinLd], b1 = vr[8 * n * kWinLd + 4];
+      mma_bf16(o[n], apl, b0, b1);
+      mma_bf16(o[n], ap, vl[8 * n * kWinLd], vl[8 * n * kWinLd + 4]);
+      mma_bf16(o[n], ap, b0, b1);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
