@@ -142,32 +142,68 @@ __global__ void __launch_bounds__(kThreads, 1) lra_col_sm100_kernel(const Params
       for (int mt = 0; mt < p.n_mt; ++mt) {
         ptx::mbar_wait_parked(BAR(kBarSFull), gt & 1u);
         ptx::tc_fence_after();
-        // pass 1: row maximum over the live keys
+        // pass 1: row maximum over the live keys.  The tcgen05.ld of chunk c + 1 is in flight while chunk c is reduced (two register
+        // buffers); only the last chunk can hold keys >= H (stale columns), so only it pays the bounds checks.
         float mx = -INFINITY;
-        for (int c = 0; c < n32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(lane_base + c * 32, r);          // (columns >= Hp of the last chunk hold stale but finite-or-not data: masked below)
-          ptx::tmem_ld_wait();
+        uint32_t ra[32], rb[32];
+        auto max_chunk = [&](const uint32_t (&r)[32], int c) {
+          if (c * 32 + 32 <= H) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < H) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < H) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+        };
+        ptx::tmem_ld32(lane_base, ra);
+        for (int c = 0; c < n32; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < n32) ptx::tmem_ld32(lane_base + (c + 1) * 32, rb);
+          max_chunk(ra, c);
+          if (c + 1 < n32) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < n32) ptx::tmem_ld32(lane_base + (c + 2) * 32, ra);
+            max_chunk(rb, c + 1);
+          }
         }
-        // pass 2: p = exp(s - max) as bf16 back into tensor memory (over the consumed scores), row sum in fp32
+        // pass 2: p = exp(s - max) as bf16 back into tensor memory (over the consumed scores: chunk c writes columns [16 c, 16 c + 16), which
+        // belong to score chunk c / 2 <= c, already in registers or consumed; the prefetched chunk c + 1 starts at column 32 c + 32), row
+        // sum in fp32
         const float mneg = -mx * 1.4426950408889634f;
         float sum = 0.f;
-        for (int c = 0; c < n32; ++c) {
-          uint32_t r[32], o[16];
-          ptx::tmem_ld32(lane_base + c * 32, r);
-          ptx::tmem_ld_wait();
+        auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
+          uint32_t o[16];
+          if (c * 32 + 32 <= H) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k0 = c * 32 + 2 * i;
-            const float e0 = k0 < H ? ex2(fmaf(__uint_as_float(r[2 * i]), 1.4426950408889634f, mneg)) : 0.f;
-            const float e1 = k0 + 1 < H ? ex2(fmaf(__uint_as_float(r[2 * i + 1]), 1.4426950408889634f, mneg)) : 0.f;
-            sum += e0 + e1;
-            o[i] = pack_bf16x2(e0, e1);
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = ex2(fmaf(__uint_as_float(r[2 * i]), 1.4426950408889634f, mneg));
+              const float e1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), 1.4426950408889634f, mneg));
+              sum += e0 + e1;
+              o[i] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int k0 = c * 32 + 2 * i;
+              const float e0 = k0 < H ? ex2(fmaf(__uint_as_float(r[2 * i]), 1.4426950408889634f, mneg)) : 0.f;
+              const float e1 = k0 + 1 < H ? ex2(fmaf(__uint_as_float(r[2 * i + 1]), 1.4426950408889634f, mneg)) : 0.f;
+              sum += e0 + e1;
+              o[i] = pack_bf16x2(e0, e1);
+            }
           }
           if (c * 16 < Hp / 2) tmem_st16(lane_base + c * 16, o);      // warp-uniform condition
+        };
+        ptx::tmem_ld32(lane_base, ra);
+        for (int c = 0; c < n32; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < n32) ptx::tmem_ld32(lane_base + (c + 1) * 32, rb);
+          exp_chunk(ra, c);
+          if (c + 1 < n32) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < n32) ptx::tmem_ld32(lane_base + (c + 2) * 32, ra);
+            exp_chunk(rb, c + 1);
+          }
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -204,6 +240,13 @@ __global__ void __launch_bounds__(kThreads, 1) lra_col_sm100_kernel(const Params
 #pragma unroll
     for (int i = 0; i < 9; ++i) kh[i] = p.t.kh[i];
     if (bt < 9) kws[bt] = p.t.kw[bt];
+    // query / key rows >= H (up to Mp) are zero in both buffers for the whole launch: no column ever writes them
+    for (int bsel = 0; bsel < 2; ++bsel) {
+      uint4 *q4 = reinterpret_cast<uint4 *>(smem + (size_t)bsel * buf_bytes);
+      for (uint32_t e = bt; e < q_bytes / 16; e += kBuildThreads) q4[e] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBuildThreads) : "memory");
+    const float beta = p.t.beta, bh = p.t.bh;
     for (int ci = 0; ci < my_cols; ++ci) {
       const int buf = ci & 1;
       const int col = blockIdx.x + ci * gridDim.x, b = col / W, w = col - b * W;
@@ -227,47 +270,78 @@ __global__ void __launch_bounds__(kThreads, 1) lra_col_sm100_kernel(const Params
       {
         const float *vsrc = p.vrow_t + ((size_t)b * W + w) * H * 64;
         const int n_tasks = (Hp / 2) * 16;
-        for (int e = bt; e < n_tasks; e += kBuildThreads) {
-          const int kp = (e >> 6) * 4 + (e & 3), c4 = ((e >> 2) & 7) + ((e >> 5) & 1) * 8;      // e = [kp_hi | c4_hi | c4_lo(3) | kp_lo(2)]
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (2 * kp < H) v0 = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp) * 64 + c4 * 4));
-          if (2 * kp + 1 < H) v1 = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp + 1) * 64 + c4 * 4));
-          const uint32_t wv[4] = {pack_bf16x2(v0.x, v1.x), pack_bf16x2(v0.y, v1.y), pack_bf16x2(v0.z, v1.z), pack_bf16x2(v0.w, v1.w)};
-          uint32_t *base = reinterpret_cast<uint32_t *>(Vs + (size_t)(kp >> 2) * 1024) + (kp & 3);
+        for (int e0 = bt; e0 < n_tasks; e0 += 4 * kBuildThreads) {          // four tasks' loads in flight per thread
+          float4 v0[4], v1[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = (i + (c4 >> 1)) & 3, d = c4 * 4 + j;
-            base[(d >> 3) * 32 + (d & 7) * 4] = j == 0 ? wv[0] : (j == 1 ? wv[1] : (j == 2 ? wv[2] : wv[3]));
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kBuildThreads;
+            v0[u] = v1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < n_tasks) {
+              const int kp = (e >> 6) * 4 + (e & 3), c4 = ((e >> 2) & 7) + ((e >> 5) & 1) * 8;      // e = [kp_hi | c4_hi | c4_lo(3) | kp_lo(2)]
+              if (2 * kp < H) v0[u] = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp) * 64 + c4 * 4));
+              if (2 * kp + 1 < H) v1[u] = __ldg(reinterpret_cast<const float4 *>(vsrc + (size_t)(2 * kp + 1) * 64 + c4 * 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kBuildThreads;
+            if (e < n_tasks) {
+              const int kp = (e >> 6) * 4 + (e & 3), c4 = ((e >> 2) & 7) + ((e >> 5) & 1) * 8;
+              const uint32_t wv[4] = {pack_bf16x2(v0[u].x, v1[u].x), pack_bf16x2(v0[u].y, v1[u].y), pack_bf16x2(v0[u].z, v1[u].z),
+                                      pack_bf16x2(v0[u].w, v1[u].w)};
+              uint32_t *base = reinterpret_cast<uint32_t *>(Vs + (size_t)(kp >> 2) * 1024) + (kp & 3);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = (i + (c4 >> 1)) & 3, d = c4 * 4 + j;
+                base[(d >> 3) * 32 + (d & 7) * 4] = j == 0 ? wv[0] : (j == 1 ? wv[1] : (j == 2 ? wv[2] : wv[3]));
+              }
+            }
           }
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kBuildThreads) : "memory");      // cm / cq complete
-      // Q[h][c] = bh + sum_i kh[i] sq[h + i - 4][c],  sq[h'][c] = beta + kw[cm - c + 4] q inside the frame, 0 outside; rows >= H zero.
-      // A warp writes one core matrix per step: 8 rows x 16 bytes (8 channels) = 128 contiguous bytes.
+      // Q[h][c] = bh + sum_i kh[i] sq[h + i - 4][c],  sq[h'][c] = beta + kw[cm - c + 4] q inside the frame, 0 outside.
+      // A warp owns a run of ceil(H / 8) consecutive rows, a lane two channels: the nine sq rows a query row needs slide through
+      // registers (one new sq row per output row instead of nine; the window index is static after unrolling by 9), same fp32 operation
+      // order as lra_col_bf16_kernel.  The 4-byte stores of a warp fall on four banks (eight channel chunks Mp * 16 bytes apart):
+      // 8 wavefronts per row, negligible next to the arithmetic.
       {
-        const int n_cm = (Mp / 8) * 8;                       // core matrices: [row block][channel chunk]
-        for (int m = bw; m < n_cm; m += 8) {
-          const int hblk = m >> 3, kc = m & 7;
-          const int h = hblk * 8 + (bl >> 2), c0 = kc * 8 + (bl & 3) * 2;
-          float a0 = 0.f, a1 = 0.f;
-          if (h < H) {
-            a0 = a1 = p.t.bh;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-              const int c = cm[h + i];
-              if (c < 0) continue;
-              float s0 = p.t.beta, s1 = p.t.beta;
-              if (c != 255) {
-                const int t0 = c - c0 + 4, t1 = t0 - 1;
-                const float q = cq[h + i];
-                if (t0 >= 0 && t0 <= 8) s0 = fmaf(kws[t0], q, s0);
-                if (t1 >= 0 && t1 <= 8) s1 = fmaf(kws[t1], q, s1);
-              }
-              a0 = fmaf(kh[i], s0, a0);
-              a1 = fmaf(kh[i], s1, a1);
+        const int L = (H + 7) >> 3, r0 = bw * L, r1 = min(r0 + L, H);
+        const int c0 = 2 * bl;
+        auto sq_row = [&](int e, float &s0, float &s1) {       // e = row + 4
+          const int c = cm[e];
+          s0 = s1 = 0.f;
+          if (c >= 0) {
+            s0 = s1 = beta;
+            if (c != 255) {
+              const int t0 = c - c0 + 4, t1 = t0 - 1;
+              const float q = cq[e];
+              if (t0 >= 0 && t0 <= 8) s0 = fmaf(kws[t0], q, s0);
+              if (t1 >= 0 && t1 <= 8) s1 = fmaf(kws[t1], q, s1);
             }
           }
-          reinterpret_cast<uint32_t *>(Qs + (size_t)kc * Mp * 16 + (size_t)hblk * 128)[bl] = pack_bf16x2(a0, a1);
+        };
+        if (r0 < r1) {
+          float w0[9], w1[9];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sq_row(r0 + i, w0[i], w1[i]);
+          uint32_t *qdst = reinterpret_cast<uint32_t *>(Qs + (size_t)(bl >> 2) * Mp * 16) + (bl & 3);
+          for (int hb = r0; hb < r1; hb += 9) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              const int h = hb + j;
+              if (h < r1) {
+                sq_row(h + 8, w0[(8 + j) % 9], w1[(8 + j) % 9]);
+                float a0 = bh, a1 = bh;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                  a0 = fmaf(kh[i], w0[(i + j) % 9], a0);
+                  a1 = fmaf(kh[i], w1[(i + j) % 9], a1);
+                }
+                qdst[(h >> 3) * 32 + (h & 7) * 4] = pack_bf16x2(a0, a1);
+              }
+            }
+          }
         }
       }
       ptx::fence_proxy_async_smem();            // generic-proxy stores -> visible to tcgen05.mma's operand reads

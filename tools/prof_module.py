@@ -9,6 +9,7 @@ from cdfo_b200.model import CVSR_V8  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--stage", default="rdab")
 ap.add_argument("--seqs", type=int, default=2)
+ap.add_argument("--plain", action="store_true", help="run the stage three times without torch.profiler (for ncu)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 S, H, W = a.seqs, 272, 480
@@ -34,6 +35,10 @@ with torch.no_grad():
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
+    if a.plain:
+        fn()
+        torch.cuda.synchronize()
+        sys.exit(0)
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         fn()
         torch.cuda.synchronize()
