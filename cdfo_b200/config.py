@@ -24,6 +24,9 @@ conv_fold_half = os.environ.get("CDFO_CONV_FOLD_HALF", "1") != "0"
 # launch at 2 x 544x960).  Measured (tools/bench_conv.py) once the MMA issuer stopped being the bottleneck: 193.6 -> 153.8 us for the
 # folded convolution against +16 us for the producer's scattered stores.
 conv_parity_planes = os.environ.get("CDFO_CONV_PARITY_PLANES", "1") != "0"
+# With conv_fold_half: True = the folded convolution's epilogue closes the block (adds the bilinear x2 of the half-resolution branch and writes
+# the x0.5 of the sum for the next block): no resampling pass over HBM between the blocks of a group.  False = round 1's resample kernels.
+trunk_fused_resample = os.environ.get("CDFO_TRUNK_FUSED_RESAMPLE", "1") != "0"
 
 # Offset / mask head of MVDualAttAlignment: True = both evaluations of conv_offset[-1] in one launch (the first one stays in the
 # epilogue's registers, cdfo_mv_offset_head_dual_sm100_fwd); False = two launches with the intermediate fields in HBM.

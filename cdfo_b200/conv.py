@@ -74,10 +74,12 @@ _wcache_4x4 = _lib.TensorCache()
 
 
 @torch.no_grad()
-def conv3x3_then_half(x8, weight, bias=None, resid8=None):
+def conv3x3_then_half(x8, weight, bias=None, resid8=None, up8=None, want_half=False):
     """bilinear_x0.5(conv3x3(x8, weight) + bias) + resid8 as ONE 4x4 / stride-2 convolution on a CTA pair (cdfo_conv4x4s2_pair_sm100_fwd).
     x8 [B, Cin/8, 2H, 2W, 8] bf16 -- or its parity planes [B, Cin/8, 2, 2, H, W, 8] as conv3x3(..., parity_planes=True) writes them
-    (dense TMA boxes instead of stride-2 loads) -- weight [64, Cin, 3, 3] -> [B, 8, H, W, 8] bf16; resid8 at the output size."""
+    (dense TMA boxes instead of stride-2 loads) -- weight [64, Cin, 3, 3] -> [B, 8, H, W, 8] bf16; resid8 at the output size.
+    up8 [B, 8, H/2, W/2, 8]: its bilinear x2 is added in the epilogue; want_half: also returns bilinear_x0.5 of the result
+    [B, 8, H/2, W/2, 8] (taken from the fp32 values) -- the two resampling passes that close / open a cross-scale block."""
     planes = x8.dim() == 7
     if planes:
         B, C8, _, _, Ho, Wo, _ = x8.shape
@@ -101,9 +103,16 @@ def conv3x3_then_half(x8, weight, bias=None, resid8=None):
     if resid8 is not None and (tuple(resid8.shape) != tuple(y.shape) or resid8.dtype != torch.bfloat16 or not resid8.is_contiguous()):
         raise _lib.CdfoError("conv3x3_then_half: residual must be a contiguous bf16 c8 tensor of the output shape")
     b = None if bias is None else bias.detach().contiguous().float()
-    _lib.call("cdfo_conv4x4s2_pair_sm100_planes_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(y), B, Cin, Hi, Wi,
-              1 if planes else 0, _lib.stream_ptr(x8.device))
-    return y
+    half = None
+    if up8 is not None or want_half:
+        hs = (B, Cout // 8, Hi // 4, Wi // 4, 8)
+        if Hi % 4 or Wi % 4 or (up8 is not None and (tuple(up8.shape) != hs or up8.dtype != torch.bfloat16 or not up8.is_contiguous())):
+            raise _lib.CdfoError("conv3x3_then_half: up8 must be a contiguous bf16 c8 tensor of half the output size (output size even)")
+        if want_half:
+            half = torch.empty(hs, dtype=torch.bfloat16, device=x8.device)
+    _lib.call("cdfo_conv4x4s2_pair_sm100_block_fwd", _lib.ptr(x8), _lib.ptr(wpk), _lib.ptr(b), _lib.ptr(resid8), _lib.ptr(up8), _lib.ptr(y),
+              _lib.ptr(half), B, Cin, Hi, Wi, 1 if planes else 0, _lib.stream_ptr(x8.device))
+    return (y, half) if want_half else y
 
 
 _derived = _lib.TensorCache()

@@ -45,7 +45,9 @@ constexpr int kAccCols = 64, kTmemCols = 128;
 struct Params {
   const float *bias;    // [64] or nullptr
   const uint4 *resid;   // c8 bf16 [B][8][H][W][8] or nullptr
+  const uint4 *up;      // c8 bf16 [B][8][H/2][W/2][8] or nullptr: its bilinear x2 (align_corners=False) is added (Block_'s up(body(down(x))))
   uint4 *y;             // c8 bf16 [B][8][H][W][8]
+  uint4 *half_out;      // c8 bf16 [B][8][H/2][W/2][8] or nullptr: bilinear x0.5 (2x2 mean) of the fp32 result = the next block's down input
   int B, Cin, H, W;     // H, W = OUTPUT size (input is 2H x 2W)
   int tiles_x, tiles_y, m_tiles;
   int x_planes;         // 1: x is stored as parity planes [B][Cin/8][2][2][H][W][8] (what cdfo_conv3x3_pair_sm100_planes_fwd writes):
@@ -210,25 +212,84 @@ conv4x4s2_pair_sm100_kernel(const __grid_constant__ CUtensorMap xmap, const __gr
             else mbar_arrive_cluster(BAR(10 + acc), 0);
           }
         }
-        if (!live) continue;
+        // all global loads of the pass first (residual: 2, bilinear x2 source: 2 chunks x 4 taps), then the arithmetic
         float v[16];
+        if (live) {
+          uint4 rq[2] = {}, uq[8] = {};
+          float wq[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.resid) {
+            rq[0] = __ldg(p.resid + ((size_t)b * 8 + c0 / 8) * HW + pix);
+            rq[1] = __ldg(p.resid + ((size_t)b * 8 + c0 / 8 + 1) * HW + pix);
+          }
+          if (p.up) {
+            // bilinear x2, align_corners=False: source d / 2 - 0.25 clamped at 0 -> taps (0.25, 0.75) / (0.75, 0.25), edge pixel repeated
+            const int Hh = p.H >> 1, Wh = p.W >> 1, hk = h >> 1, wk = w >> 1;
+            const int r0 = (h & 1) ? hk : max(hk - 1, 0), r1 = (h & 1) ? min(hk + 1, Hh - 1) : hk;
+            const int q0 = (w & 1) ? wk : max(wk - 1, 0), q1 = (w & 1) ? min(wk + 1, Wh - 1) : wk;
+            const float ah = (h & 1) ? 0.75f : 0.25f, aw = (w & 1) ? 0.75f : 0.25f;
+            wq[0] = ah * aw; wq[1] = ah * (1.f - aw); wq[2] = (1.f - ah) * aw; wq[3] = (1.f - ah) * (1.f - aw);
+            const size_t HWh = (size_t)Hh * Wh;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[c0 + i];
-        if (p.resid) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint4 q = __ldg(p.resid + ((size_t)b * 8 + c0 / 8 + half) * HW + pix);
-            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              v[half * 8 + 2 * i] += __uint_as_float(qq[i] << 16);
-              v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
+            for (int half = 0; half < 2; ++half) {
+              const uint4 *src = p.up + ((size_t)b * 8 + c0 / 8 + half) * HWh;
+              uq[half * 4 + 0] = __ldg(src + (size_t)r0 * Wh + q0);
+              uq[half * 4 + 1] = __ldg(src + (size_t)r0 * Wh + q1);
+              uq[half * 4 + 2] = __ldg(src + (size_t)r1 * Wh + q0);
+              uq[half * 4 + 3] = __ldg(src + (size_t)r1 * Wh + q1);
             }
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[c0 + i];
+          if (p.resid) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t qq[4] = {rq[half].x, rq[half].y, rq[half].z, rq[half].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[half * 8 + 2 * i] += __uint_as_float(qq[i] << 16);
+                v[half * 8 + 2 * i + 1] += __uint_as_float(qq[i] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.up) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int tp = 0; tp < 4; ++tp) {
+                const uint4 q = uq[half * 4 + tp];
+                const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[half * 8 + 2 * i] = fmaf(wq[tp], __uint_as_float(qq[i] << 16), v[half * 8 + 2 * i]);
+                  v[half * 8 + 2 * i + 1] = fmaf(wq[tp], __uint_as_float(qq[i] & 0xffff0000u), v[half * 8 + 2 * i + 1]);
+                }
+              }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
-        uint4 *y = p.y + ((size_t)b * 8 + c0 / 8) * HW + pix;
-        y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
-        y[HW] = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
+        if (p.half_out) {
+          // 2x2 mean of the fp32 result: the quad of pixel (ty, tx) is lanes ^1 (column) and ^8 (row); tiles start at even (h, w) and
+          // H, W are even, so a quad is live or dead as a whole.  Every lane of the warp takes part in the shuffles.
+          float m[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            m[i] = 0.25f * t;
+          }
+          if (live && (lane & 9) == 0) {
+            uint4 *d = p.half_out + ((size_t)b * 8 + c0 / 8) * ((size_t)(p.H >> 1) * (p.W >> 1)) + (size_t)(h >> 1) * (p.W >> 1) + (w >> 1);
+            d[0] = make_uint4(pack_bf2(m[0], m[1]), pack_bf2(m[2], m[3]), pack_bf2(m[4], m[5]), pack_bf2(m[6], m[7]));
+            d[(size_t)(p.H >> 1) * (p.W >> 1)] = make_uint4(pack_bf2(m[8], m[9]), pack_bf2(m[10], m[11]), pack_bf2(m[12], m[13]), pack_bf2(m[14], m[15]));
+          }
+        }
+        if (live) {
+          uint4 *y = p.y + ((size_t)b * 8 + c0 / 8) * HW + pix;
+          y[0] = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
+          y[HW] = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -296,6 +357,8 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_pack_weight(const float *w3, void *wpk,
 
 extern "C" int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
                                                     int B, int Cin, int H_in, int W_in, int x_planes, void *stream);
+extern "C" int cdfo_conv4x4s2_pair_sm100_block_fwd(const void *x, const void *wpk, const float *bias, const void *resid_c8, const void *up_c8,
+                                                   void *y_c8, void *half_c8, int B, int Cin, int H_in, int W_in, int x_planes, void *stream);
 
 extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B,
                                              int Cin, int H_in, int W_in, void *stream) {
@@ -304,7 +367,16 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, 
 
 extern "C" int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
                                                     int B, int Cin, int H_in, int W_in, int x_planes, void *stream) {
+  return cdfo_conv4x4s2_pair_sm100_block_fwd(x_c8, wpk, bias, resid_c8, nullptr, y_c8, nullptr, B, Cin, H_in, W_in, x_planes, stream);
+}
+
+extern "C" int cdfo_conv4x4s2_pair_sm100_block_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, const void *up_c8,
+                                                   void *y_c8, void *half_c8, int B, int Cin, int H_in, int W_in, int x_planes, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv4x4s2_pair_sm100_fwd: NULL pointer");
+  CDFO_REQUIRE((!up_c8 && !half_c8) || (H_in % 4 == 0 && W_in % 4 == 0), CDFO_ERR_SHAPE,
+               "cdfo_conv4x4s2_pair_sm100_block_fwd: up_c8 / half_c8 need an even output size (input %d x %d)", H_in, W_in);
+  CDFO_REQUIRE(((uintptr_t)up_c8 & 15) == 0 && ((uintptr_t)half_c8 & 15) == 0, CDFO_ERR_SHAPE,
+               "cdfo_conv4x4s2_pair_sm100_block_fwd: pointers must be 16-byte aligned");
   CDFO_REQUIRE(x_planes == 0 || x_planes == 1, CDFO_ERR_UNSUPPORTED, "cdfo_conv4x4s2_pair_sm100_planes_fwd: x_planes %d", x_planes);
   CDFO_REQUIRE(B > 0 && H_in > 0 && W_in > 0 && H_in % 2 == 0 && W_in % 2 == 0, CDFO_ERR_SHAPE,
                "cdfo_conv4x4s2_pair_sm100_fwd: the input size must be even (got %d x %d)", H_in, W_in);
@@ -348,6 +420,7 @@ extern "C" int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x_c8, const void
   }
   c4::Params p;
   p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = (uint4 *)y_c8;
+  p.up = (const uint4 *)up_c8; p.half_out = (uint4 *)half_c8;
   p.B = B; p.Cin = Cin; p.H = H_in / 2; p.W = W_in / 2; p.x_planes = x_planes;
   p.tiles_x = ceil_div(p.W, c4::kTileW); p.tiles_y = ceil_div(p.H, c4::kTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;

@@ -352,30 +352,37 @@ def _block_weights(blk):
 
 
 @torch.no_grad()
-def cross_scale_block(blk, x8):
+def cross_scale_block(blk, x8, x8_half=None, want_half=False):
     """Block_.forward, arch:401-406, on c8 bf16.  Bilinear x0.5 / x2 commute with the 1x1 convs (per-pixel linear maps whose
     bias passes through weights that sum to 1), so every 1x1 runs at the lower of its two resolutions, and the 1x1 that
     follows a body is composed into the body's second 3x3:
         x + body(x)                         two convs at 1x (residual add in the epilogue)
         up(body(down(x)))                   x0.5 -> 1x1 -> conv -> conv o up-1x1 at 1/2x, then x2
         down(body(up(x)))                   1x1 at 1x -> x2 -> conv -> conv o down-1x1 at 2x, then x0.5
-    and one kernel sums the three branches."""
+    and the three branches are summed in the epilogue of the last convolution (config.trunk_fused_resample; a resampling kernel
+    otherwise).  x8_half: bilinear x0.5 of x8 if the producer of x8 already wrote it; want_half: return (out, x0.5 of out)."""
     b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
     dn, up = blk.down._modules["0"], blk.up._modules["0"]
     wts = _block_weights(blk)
     y = conv.conv3x3(conv.conv3x3(x8, b0.weight, b0.bias, conv.ACT_LRELU), b2.weight, b2.bias, conv.ACT_NONE, resid8=x8)
-    xd = conv.conv3x3(conv.resample(x8, 0), dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
+    fused = config.trunk_fused_resample and config.conv_fold_half and x8.size(2) % 2 == 0 and x8.size(3) % 2 == 0
+    xd = conv.conv3x3(x8_half if x8_half is not None else conv.resample(x8, 0), dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
     cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
     xu = conv.resample(conv.conv3x3(x8, up.weight, up.bias, conv.ACT_NONE), 1)               # 1x1
     if config.conv_fold_half:
         # the 2x-resolution intermediate lives as its four parity planes: the stride-2 taps of the folded convolution are dense boxes
         t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU, parity_planes=config.conv_parity_planes and config.conv_pair)
         # bilinear x0.5 of a 3x3 convolution = one 4x4 / stride-2 convolution: evaluated at 1x, the branch sum starts in its epilogue
+        if fused:
+            # ... and ends there: + bilinear x2 of the half-resolution branch, and the x0.5 of the sum for the next block's down branch
+            return conv.conv3x3_then_half(t2, wts["dn_body2"][0], wts["dn_body2"][1], resid8=y, up8=cu, want_half=want_half)
         yb = conv.conv3x3_then_half(t2, wts["dn_body2"][0], wts["dn_body2"][1], resid8=y)
-        return conv.resample(None, 3, b=cu, base=yb)
-    t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU)
-    b3 = conv.conv3x3(t2, wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
-    return conv.resample(b3, 2, b=cu, base=y)
+        out = conv.resample(None, 3, b=cu, base=yb)
+    else:
+        t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU)
+        b3 = conv.conv3x3(t2, wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
+        out = conv.resample(b3, 2, b=cu, base=y)
+    return (out, None) if want_half else out
 
 
 @torch.no_grad()
@@ -383,9 +390,13 @@ def recon_trunk(trunk, x8):
     """SCNet_(7 x SCGroup_(3 x Block_)), arch:430-480, c8 bf16 in and out."""
     y = x8
     for grp in trunk.body._modules.values():
-        r = y
-        for blk in grp.body._modules.values():
-            r = cross_scale_block(blk, r)
+        r, r_half = y, None
+        blocks = list(grp.body._modules.values())
+        for k, blk in enumerate(blocks):
+            if k + 1 < len(blocks):
+                r, r_half = cross_scale_block(blk, r, r_half, want_half=True)
+            else:
+                r = cross_scale_block(blk, r, r_half)
         y = conv.conv3x3(r, grp.conv.weight, grp.conv.bias, conv.ACT_NONE, resid8=y)
     return y + x8
 

@@ -306,6 +306,12 @@ int cdfo_conv4x4s2_pair_sm100_fwd(const void *x_c8, const void *wpk, const float
  * TMA box (the plain c8 input is loaded with elementStrides = 2, one L2 request per 16-byte pixel chunk). */
 int cdfo_conv4x4s2_pair_sm100_planes_fwd(const void *x, const void *wpk, const float *bias, const void *resid_c8, void *y_c8, int B,
                                          int Cin, int H_in, int W_in, int x_planes, void *stream);
+/* Same, closing a whole cross-scale block (Block_.forward, arch/SIDECVSR_our.py:401-406) in the epilogue:
+ *   y = conv + bias + resid_c8 + bilinear_x2(up_c8)        up_c8 [B,8,H_in/4,W_in/4,8] bf16 or NULL: the up(body(down(x))) branch
+ *   half_c8 = bilinear_x0.5(y) from the fp32 values        [B,8,H_in/4,W_in/4,8] bf16 or NULL: the next block's down(x) input
+ * (no separate resampling passes over HBM; H_in, W_in multiples of 4 when either is given). */
+int cdfo_conv4x4s2_pair_sm100_block_fwd(const void *x, const void *wpk, const float *bias, const void *resid_c8, const void *up_c8,
+                                        void *y_c8, void *half_c8, int B, int Cin, int H_in, int W_in, int x_planes, void *stream);
 /* ---- frame I/O of the evaluation loop ----
  * Integer planes [n_planes, H_in, W] (src_kind 0 uint8, 1 int8, 2 int16, 3 int32) -> fp32 k / 255 [n_planes, H_out, W], rows
  * H_in..H_out-1 zero: generate_input / generate_PM_input / generate_RM_input (test_LD_37.py:19-29,33-46,64-74; 270 -> 272 rows). */
@@ -332,6 +338,9 @@ int cdfo_umma_selftest(const void *A, const void *B, float *D, int swap_lbo_sbo,
 size_t cdfo_lra_mask_logits_workspace_bytes(int B, int H, int W);
 int cdfo_lra_mask_logits_fwd(const float *v, const float *w2, const float *b2, const float *w3, const float *b3, float *vmax,
                              void *workspace, int B, int H, int W, void *stream);
+/* Stride-2 convolution of the mask logits: 1 (default) = input patches by tiled TMA (mbarrier ring; needs W % 4 == 0),
+ * 0 = the 4-byte cp.async kernel.  A measurement / test switch. */
+int cdfo_lra_set_logit_tma(int on);
 
 /* ---- feature extraction on c8 bf16 (csrc/features_c8.cu; arch/SIDECVSR_our.py:1441-1475, :1643-1653) ----
  * "c8" = [B, C/8, H, W, 8] bf16.  fp32 arithmetic, fixed reduction orders. */

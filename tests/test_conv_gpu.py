@@ -130,6 +130,43 @@ def test_conv3x3_then_half_as_4x4_stride2(cuda_dev, case):
     assert torch.equal(y, y3)
 
 
+@pytest.mark.parametrize("case", [(1, 256, 32, 16, True), (2, 256, 72, 44, True), (1, 64, 40, 24, False), (2, 256, 544, 960, True)])
+def test_conv4x4s2_block_epilogue(cuda_dev, case):
+    """The folded convolution closing a cross-scale block in its epilogue (cdfo_conv4x4s2_pair_sm100_block_fwd): + bilinear x2 of the
+    half-resolution branch and the x0.5 of the sum, against torch on the same bf16 operands (Block_.forward, arch:401-406; ragged tiles
+    included), and against the two resampling kernels it replaces (which round once more)."""
+    from cdfo_b200 import conv
+    B, Cin, Hi, Wi, use_res = case
+    g = torch.Generator().manual_seed(sum(case[:4]) + 1)
+    d = lambda t: t.to(cuda_dev)
+    x = d(torch.randn(B, Cin, Hi, Wi, generator=g).to(torch.bfloat16).float())
+    w = d((torch.randn(64, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float())
+    b = d(torch.randn(64, generator=g) * 0.1)
+    r = d(torch.randn(B, 64, Hi // 2, Wi // 2, generator=g).to(torch.bfloat16).float()) if use_res else None
+    low = d(torch.randn(B, 64, Hi // 4, Wi // 4, generator=g).to(torch.bfloat16).float())
+    ref = F.interpolate(F.conv2d(x, w, b, 1, 1), scale_factor=0.5, mode="bilinear", align_corners=False) + \
+        F.interpolate(low, scale_factor=2.0, mode="bilinear", align_corners=False)
+    if use_res:
+        ref = ref + r
+    ref_half = F.interpolate(ref, scale_factor=0.5, mode="bilinear", align_corners=False)
+    x8, r8, low8 = conv.to_c8(x), (conv.to_c8(r) if use_res else None), conv.to_c8(low)
+    y8, h8 = conv.conv3x3_then_half(x8, w, b, r8, up8=low8, want_half=True)
+    y, h = conv.from_c8(y8), conv.from_c8(h8)
+    scale = max(1.0, ref.abs().max().item())
+    err, err_h = (y - ref).abs().max().item(), (h - ref_half).abs().max().item()
+    print("conv4x4s2 block epilogue %s: max err %.3g, half %.3g (max|ref| %.3g)" % (case, err, err_h, scale))
+    assert err <= 1.2e-2 * scale and err_h <= 1.2e-2 * scale
+    # the three-kernel form: folded convolution, then base + x2(low), then x0.5 -- rounds to bf16 after each kernel
+    y_old8 = conv.resample(None, 3, b=low8, base=conv.conv3x3_then_half(x8, w, b, r8))
+    assert (y - conv.from_c8(y_old8)).abs().max().item() <= 2 ** -7 * scale
+    assert (h - conv.from_c8(conv.resample(y_old8, 0))).abs().max().item() <= 2 ** -7 * scale
+    # only one of the two options, and reruns are bit-identical
+    assert torch.equal(conv.conv3x3_then_half(x8, w, b, r8, up8=low8), y8)
+    y_b, h_b = conv.conv3x3_then_half(x8, w, b, r8, want_half=True)
+    assert torch.equal(y_b, conv.conv3x3_then_half(x8, w, b, r8))
+    assert (conv.from_c8(h_b) - conv.from_c8(conv.resample(y_b, 0))).abs().max().item() <= 2 ** -7 * scale
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(1, 64, 256, 32, 16), (2, 64, 256, 66, 42), (1, 256, 64, 34, 18), (1, 64, 256, 544, 960)])
 def test_conv3x3_pair_parity_plane_output(cuda_dev, B, Cin, Cout, H, W):
     """The CTA-pair convolution writing its output as four parity planes [B, C/8, 2, 2, H/2, W/2, 8] (the layout the folded

@@ -186,3 +186,22 @@ def test_lra_window_tensor_core_vs_fp32(cuda_dev, B, H, W, scale):
     err = (out - ref).abs().max().item()
     print("LRA window pass tensor cores vs fp32 (x scale %.1f): max diff %.3g (max|out| %.3g)" % (scale, err, ref.abs().max().item()))
     assert err <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_mask_logits_tma_vs_cp_async(cuda_dev):
+    """The TMA-fed stride-2 convolution of the mask logits (one box per stage, mbarrier ring; the default when W % 4 == 0) against
+    the cp.async kernel: same TF32 products, different summation order over the input-channel chunks."""
+    from cdfo_b200 import _lib, hotpath
+    m = _model(cuda_dev)
+    g = torch.Generator().manual_seed(11)
+    v = torch.rand(3, 64, 46, 52, generator=g).to(cuda_dev)       # ragged tiles in both directions
+    try:
+        _lib.call("cdfo_lra_set_logit_tma", 0)
+        ref = hotpath.mask_logits(m.RDAB, v)
+    finally:
+        _lib.call("cdfo_lra_set_logit_tma", 1)
+    got = hotpath.mask_logits(m.RDAB, v)
+    err = (got - ref).abs().max().item()
+    print("mask logits TMA vs cp.async: max diff %.3g (max|ref| %.3g)" % (err, ref.abs().max().item()))
+    assert err <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(hotpath.mask_logits(m.RDAB, v), got)

@@ -29,9 +29,12 @@ def test_resample_c8_vs_interpolate(cuda_dev, H, W):
     assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
 
 
-def test_trunk_vs_oracle(cuda_dev):
-    """SCNet_ (21 cross-scale blocks) on c8 bf16 with composed 1x1 convolutions vs the fp32 oracle (arch:378-480)."""
-    from cdfo_b200 import conv, hotpath
+@pytest.mark.parametrize("fused", [True, False])
+def test_trunk_vs_oracle(cuda_dev, fused):
+    """SCNet_ (21 cross-scale blocks) on c8 bf16 with composed 1x1 convolutions vs the fp32 oracle (arch:378-480), with the block sums in
+    the folded convolution's epilogue (default) and with round 1's resampling kernels.  Observed on the B200: 7.2e-3 / 7.4e-3 of max|ref|
+    (21 blocks of bf16 activations); the bound is 1e-2."""
+    from cdfo_b200 import config, conv, hotpath
     from cdfo_b200.model import CVSR_V8
     sd = G.seeded_weights("O1")
     m = CVSR_V8()
@@ -41,10 +44,15 @@ def test_trunk_vs_oracle(cuda_dev):
     x = torch.randn(1, 64, 24, 40, generator=g)
     with torch.no_grad():
         ref = torch_ref.trunk(sd, x)
-    got = conv.from_c8(hotpath.recon_trunk(m.recon_trunk, conv.to_c8(x.to(cuda_dev)))).cpu()
+    keep = config.trunk_fused_resample
+    try:
+        config.trunk_fused_resample = fused
+        got = conv.from_c8(hotpath.recon_trunk(m.recon_trunk, conv.to_c8(x.to(cuda_dev)))).cpu()
+    finally:
+        config.trunk_fused_resample = keep
     err = (got - ref).abs().max().item()
-    print("trunk max err %.3g (max|ref| %.3g)" % (err, ref.abs().max().item()))
-    assert err <= 2e-2 * ref.abs().max().item()
+    print("trunk (fused resampling %s) max err %.3g (max|ref| %.3g)" % (fused, err, ref.abs().max().item()))
+    assert err <= 1e-2 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
