@@ -41,3 +41,6 @@ fused_head_dcn = os.environ.get("CDFO_FUSED_HEAD_DCN", "1") != "0"
 # False = round 1's path (cuDNN bf16 convolutions under autocast + own LayerNorm / depthwise / Gram kernels).  model.lowp = None
 # always takes the fp32 cuDNN path (a debugging reference, not the benchmarked configuration).
 features_c8 = os.environ.get("CDFO_FEATURES_C8", "1") != "0"
+# True: on the fused-alignment path the MDTA kernels of MVDualAttAlignment read c8 bf16 inputs (conv_expand_fea_r's output, the ufs prior
+# features, the packed centre feature) and keep the warped features in bf16 (cdfo_mdta_c8_fwd); False: fp32 NCHW copies as in round 1.
+mdta_c8 = os.environ.get("CDFO_MDTA_C8", "1") != "0"

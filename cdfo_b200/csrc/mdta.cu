@@ -38,7 +38,8 @@ __host__ __device__ inline int stats_len(int hc) { return 256 + 64 * hc; }
 
 struct StatsParams {
   const float *x, *extra, *pred, *flow, *wf;   // wf = fusion_out weight [64][128]
-  float *warped, *partial;                     // partial [B][parts][stats_len]
+  void *warped;                                // NCHW fp32 [B][64][HW], or c8 bf16 [B][8][HW][8] (C8)
+  float *partial;                              // partial [B][parts][stats_len]
   int H, W, x_batch, hc, relu;
 };
 
@@ -112,6 +113,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void unpack8(const uint4 q, float (&v)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// C8 = true: x, extra, pred are c8 bf16 [B][8][HW][8] (what their producers write: conv_expand_fea_r's tcgen05 epilogue, the prior
+// convolution, the centre feature packed for the stack) and warped leaves as c8 bf16 -- a corner of the gather is ONE 16-byte load per
+// 8 channels (32 loads per pixel instead of 256 scalar ones) and the kernel moves half the bytes; arithmetic stays fp32 / TF32.
+template <bool C8>
 __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsParams p) {
   extern __shared__ __align__(16) float sm[];
   float *Wt = sm;                    // [64][kLd] warped, later fused
@@ -126,14 +144,27 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
   const float *xs = p.x + (size_t)(b % p.x_batch) * 64 * HW;
   const float *ex = p.extra + (size_t)b * 64 * HW;
   const float *pr = p.pred + (size_t)b * 64 * HW;
-  float *wo = p.warped + (size_t)b * 64 * HW;
+  float *wo = reinterpret_cast<float *>(p.warped) + (size_t)b * 64 * HW;
   const int hc = p.hc, npairs = 64 * hc;
   float rs = 0.f, g[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int tile = t0; tile < t1; ++tile) {
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
     __syncthreads();   // previous tile's readers are done (and Wm is complete on the first pass)
-    const bool vec = (HW & 3) == 0;
+    const bool vec = !C8 && (HW & 3) == 0;
+    uint4 pq[2] = {}, xq[2] = {};
+    if (C8) {    // pred and x chunks of this thread (pixel tid & 63, chunks tid >> 6 and + 4): in flight underneath the gather
+      const uint4 *pr8 = reinterpret_cast<const uint4 *>(p.pred) + (size_t)b * 8 * HW;
+      const uint4 *xs8 = reinterpret_cast<const uint4 *>(p.x) + (size_t)(b % p.x_batch) * 8 * HW;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ch = (tid >> kTPShift) + 4 * j, q = tid & (kTP - 1);
+        if (q < npx) {
+          pq[j] = __ldg(pr8 + (size_t)ch * HW + p0 + q);
+          xq[j] = __ldg(xs8 + (size_t)ch * HW + p0 + q);
+        }
+      }
+    }
     if (vec) {   // pred and x tiles: asynchronous 16-byte copies, in flight while this thread gathers its 16 channels below
       for (int e = tid; e < 64 * (kTP / 4); e += kThreads) {
         const int c = e / (kTP / 4), q = (e % (kTP / 4)) * 4;
@@ -168,6 +199,50 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
         const int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x1, 0), p.W - 1);
         o00 = cy0 * p.W + cx0; o01 = cy0 * p.W + cx1; o10 = cy1 * p.W + cx0; o11 = cy1 * p.W + cx1;
       }
+      if (C8) {
+        // 16 channels = two chunks: eight 16-byte loads in flight per thread
+        const uint4 *ex8 = reinterpret_cast<const uint4 *>(p.extra) + ((size_t)b * 8 + part * 2) * HW;
+        uint4 *wo8 = reinterpret_cast<uint4 *>(p.warped) + ((size_t)b * 8 + part * 2) * HW;
+        uint4 t[2][4] = {};
+        if (valid) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint4 *plane = ex8 + (size_t)half * HW;
+            t[half][0] = __ldg(plane + o00);
+            t[half][1] = __ldg(plane + o01);
+            t[half][2] = __ldg(plane + o10);
+            t[half][3] = __ldg(plane + o11);
+          }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float c00[8], c01[8], c10[8], c11[8], v[8];
+          unpack8(t[half][0], c00); unpack8(t[half][1], c01); unpack8(t[half][2], c10); unpack8(t[half][3], c11);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // same accumulation order as grid_sample: nw, ne, sw, se
+            float a = c00[i] * nw;
+            a += c01[i] * ne;
+            a += c10[i] * sw;
+            a += c11[i] * se;
+            v[i] = a;
+            Wt[(part * 16 + half * 8 + i) * kLd + px] = a;
+          }
+          if (valid) wo8[(size_t)half * HW + pp] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int ch = part + 4 * j;
+          float a[8], c[8];
+          unpack8(pq[j], a);
+          unpack8(xq[j], c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            Pt[(ch * 8 + i) * kLd + px] = a[i];
+            Xt[(ch * 8 + i) * kLd + px] = c[i];
+          }
+        }
+      } else {
       // two batches of 8 channels: 32 independent loads in flight per thread (the kernel is latency-bound: 16 warps per SM)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -200,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
           Pt[c * kLd + q] = ok ? __ldg(pr + (size_t)c * HW + p0 + q) : 0.f;
           Xt[c * kLd + q] = ok ? __ldg(xs + (size_t)c * HW + p0 + q) : 0.f;
         }
+      }
       }
     }
     cp_async_wait<0>();
@@ -341,18 +417,13 @@ __global__ void __launch_bounds__(256) mdta_attn_kernel(const AttnParams p) {
 }
 
 struct ApplyParams {
-  const float *warped, *pred, *x;
+  const void *warped, *pred, *x;   // NCHW fp32, or c8 bf16 (mdta_apply_c8_kernel)
   const float *mats;      // [B][3][64][64] (out, in)
   void *out;              // mode 0: c8 bf16 [2B][8][HW][8]; mode 1: NCHW fp32 [B][64][HW]
   float *ca_partial;      // mode 1: [B][parts][64] channel sums of out
   int H, W, B, x_batch, mode;
   int nstages;            // 2: input tiles double-buffered by cp.async (H * W % 4 == 0, mode 0); 1: one stage
 };
-
-__device__ __forceinline__ uint32_t bf2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t *>(&v);
-}
 
 __global__ void __launch_bounds__(kThreads, 2) mdta_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) float sm[];
@@ -366,8 +437,8 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_apply_kernel(const ApplyPara
   const int stage_f = nm * 64 * kLd;
   for (int e = tid; e < nm * 4096; e += kThreads)
     Mm[(e >> 12) * 64 * 68 + ((e >> 6) & 63) * 68 + (e & 63)] = __uint_as_float(to_tf32(p.mats[(size_t)b * 3 * 4096 + e]));
-  const float *wp = p.warped + (size_t)b * 64 * HW, *pr = p.pred + (size_t)b * 64 * HW;
-  const float *xs = p.x ? p.x + (size_t)(b % p.x_batch) * 64 * HW : nullptr;
+  const float *wp = reinterpret_cast<const float *>(p.warped) + (size_t)b * 64 * HW, *pr = reinterpret_cast<const float *>(p.pred) + (size_t)b * 64 * HW;
+  const float *xs = p.x ? reinterpret_cast<const float *>(p.x) + (size_t)(b % p.x_batch) * 64 * HW : nullptr;
   const int cb = tid >> 5, pg = tid & 31;
   const bool vec = (HW & 3) == 0;
   // input tiles arrive by cp.async (16-byte rows); with two stages tile i + 1 is in flight while tile i is multiplied and stored
@@ -469,6 +540,77 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_apply_kernel(const ApplyPara
   }
 }
 
+// mode 0 with c8 bf16 inputs (warped as mdta_stats_kernel<true> wrote it, pred): o1 = M1 warped, o2 = M2 pred -> c8 bf16 [2B].
+// A thread's four 16-byte chunks of tile i + 1 are loaded into registers before the GEMMs of tile i (one shared-memory stage).
+__global__ void __launch_bounds__(kThreads, 2) mdta_apply_c8_kernel(const ApplyParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  const int HW = p.H * p.W;
+  const int ntiles = (HW + kTP - 1) / kTP;
+  const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
+  float *Mm = sm;                    // [2][64][68] TF32 bits
+  float *Wt = Mm + 2 * 64 * 68;      // [64][kLd] warped, then o1
+  float *Pt = Wt + 64 * kLd;         // [64][kLd] pred, then o2
+  for (int e = tid; e < 2 * 4096; e += kThreads)
+    Mm[(e >> 12) * 64 * 68 + ((e >> 6) & 63) * 68 + (e & 63)] = __uint_as_float(to_tf32(p.mats[(size_t)b * 3 * 4096 + e]));
+  const uint4 *wp8 = reinterpret_cast<const uint4 *>(p.warped) + (size_t)b * 8 * HW;
+  const uint4 *pr8 = reinterpret_cast<const uint4 *>(p.pred) + (size_t)b * 8 * HW;
+  const int cb = tid >> 5, pg = tid & 31;
+  const int q_ld = tid & (kTP - 1), ch_ld = tid >> kTPShift;      // this thread's pixel and chunks (ch_ld, ch_ld + 4) of the tile loads
+  uint4 wq[2], pq[2];
+  auto fetch = [&](int tile) {
+    const int p0 = tile * kTP, npx = min(kTP, HW - p0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      wq[j] = pq[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (q_ld < npx) {
+        wq[j] = __ldg(wp8 + (size_t)(ch_ld + 4 * j) * HW + p0 + q_ld);
+        pq[j] = __ldg(pr8 + (size_t)(ch_ld + 4 * j) * HW + p0 + q_ld);
+      }
+    }
+  };
+  if (t0 < t1) fetch(t0);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int p0 = tile * kTP, npx = min(kTP, HW - p0);
+    __syncthreads();       // the previous tile's staged outputs have been read; Mm is complete on the first pass
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float a[8], c[8];
+      unpack8(wq[j], a);
+      unpack8(pq[j], c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        Wt[((ch_ld + 4 * j) * 8 + i) * kLd + q_ld] = a[i];
+        Pt[((ch_ld + 4 * j) * 8 + i) * kLd + q_ld] = c[i];
+      }
+    }
+    __syncthreads();
+    if (tile + 1 < t1) fetch(tile + 1);
+    const int warp = tid >> 5, lane = tid & 31;
+    float a1[2][2][4], a2[2][2][4];
+    zero_frags(a1);
+    zero_frags(a2);
+    tile_gemm_mma(a1, Mm, 68, Wt, 64, warp, lane);
+    tile_gemm_mma(a2, Mm + 64 * 68, 68, Pt, 64, warp, lane);
+    __syncthreads();                       // every warp is done reading the input tiles
+    stage_frags(a1, Wt, warp, lane, false);
+    stage_frags(a2, Pt, warp, lane, false);
+    __syncthreads();
+    uint4 *z = reinterpret_cast<uint4 *>(p.out);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int q = pg * 2 + j;
+      if (q < npx) {
+        const float *r1 = Wt + cb * 8 * kLd + q, *r2 = Pt + cb * 8 * kLd + q;
+        z[((size_t)b * 8 + cb) * HW + p0 + q] = make_uint4(bf2(r1[0], r1[kLd]), bf2(r1[2 * kLd], r1[3 * kLd]),
+                                                            bf2(r1[4 * kLd], r1[5 * kLd]), bf2(r1[6 * kLd], r1[7 * kLd]));
+        z[((size_t)(p.B + b) * 8 + cb) * HW + p0 + q] = make_uint4(bf2(r2[0], r2[kLd]), bf2(r2[2 * kLd], r2[3 * kLd]),
+                                                                    bf2(r2[4 * kLd], r2[5 * kLd]), bf2(r2[6 * kLd], r2[7 * kLd]));
+      }
+    }
+  }
+}
+
 // gate[b][c] = sigmoid(W2 relu(W1 mean + b1) + b2), mean = sum of per-part channel sums / HW   (CALayer, arch:2032-2043)
 __global__ void channel_gate_kernel(const float *__restrict__ partial, int parts, float inv_hw, const float *__restrict__ w1,
                                     const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
@@ -545,10 +687,31 @@ extern "C" size_t cdfo_mdta_workspace_bytes(int B, int H, int W, int heads) {
   return ((size_t)B * parts * mdta::stats_len(hc) + (size_t)B * 3 * 4096 + (size_t)B * 64 * H * W) * 4;
 }
 
+static int mdta_run(const void *x, int x_batch, const void *extra, const void *pred, const float *flow, const float *fusion_w,
+                    const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2, const float *temperature,
+                    const float *proj_w, int heads, int mode, void *out, float *ca_sums, void *workspace, int B, int H, int W, void *stream,
+                    bool c8);
+
 extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, const float *pred, const float *flow,
                              const float *fusion_w, const float *du_w1, const float *du_b1, const float *du_w2,
                              const float *du_b2, const float *temperature, const float *proj_w, int heads, int mode,
                              void *out, float *ca_sums, void *workspace, int B, int H, int W, void *stream) {
+  return mdta_run(x, x_batch, extra, pred, flow, fusion_w, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, heads, mode, out, ca_sums, workspace,
+                  B, H, W, stream, false);
+}
+
+extern "C" int cdfo_mdta_c8_fwd(const void *x_c8, int x_batch, const void *extra_c8, const void *pred_c8, const float *flow,
+                                const float *fusion_w, const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2,
+                                const float *temperature, const float *proj_w, int heads, void *out_c8, void *workspace, int B, int H, int W,
+                                void *stream) {
+  return mdta_run(x_c8, x_batch, extra_c8, pred_c8, flow, fusion_w, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, heads, 0, out_c8, nullptr,
+                  workspace, B, H, W, stream, true);
+}
+
+static int mdta_run(const void *x, int x_batch, const void *extra, const void *pred, const float *flow, const float *fusion_w,
+                    const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2, const float *temperature,
+                    const float *proj_w, int heads, int mode, void *out, float *ca_sums, void *workspace, int B, int H, int W, void *stream,
+                    bool c8) {
   CDFO_REQUIRE(x && extra && pred && flow && fusion_w && du_w1 && du_b1 && du_w2 && du_b2 && temperature && proj_w && out && workspace,
                CDFO_ERR_NULL, "cdfo_mdta_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, CDFO_ERR_SHAPE, "cdfo_mdta_fwd: bad shape");
@@ -569,20 +732,26 @@ extern "C" int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, co
   const int nstages = (mode == 0 && (H * W) % 4 == 0) ? 2 : 1;
   const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 64 * 132) * 4;
   const size_t smem3 = (size_t)(nstages * nm * 64 * mdta::kLd + nm * 64 * 68) * 4, smem3_max = (size_t)(4 * 64 * mdta::kLd + 3 * 64 * 68) * 4;
+  const size_t smem3_c8 = (size_t)(2 * 64 * mdta::kLd + 2 * 64 * 68) * 4;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e1 = cudaFuncSetAttribute(mdta::mdta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaError_t e1 = cudaFuncSetAttribute(mdta::mdta_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     cudaError_t e2 = cudaFuncSetAttribute(mdta::mdta_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_max);
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
-      return fail(CDFO_ERR_CUDA, "cdfo_mdta_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    cudaError_t e3 = cudaFuncSetAttribute(mdta::mdta_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaError_t e4 = cudaFuncSetAttribute(mdta::mdta_apply_c8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_c8);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
+      return fail(CDFO_ERR_CUDA, "cdfo_mdta_fwd: cudaFuncSetAttribute: %s",
+                  cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4))));
     attr = true;
   }
-  mdta::StatsParams sp{x, extra, pred, flow, fusion_w, warped, partial, H, W, x_batch, hc, mode == 1 ? 1 : 0};
-  mdta::mdta_stats_kernel<<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
+  mdta::StatsParams sp{(const float *)x, (const float *)extra, (const float *)pred, flow, fusion_w, warped, partial, H, W, x_batch, hc, mode == 1 ? 1 : 0};
+  if (c8) mdta::mdta_stats_kernel<true><<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
+  else mdta::mdta_stats_kernel<false><<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
   mdta::AttnParams ap{partial, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, mode == 1 ? fusion_w : nullptr, mats, parts, hc, HW};
   mdta::mdta_attn_kernel<<<B, 256, 0, s>>>(ap);
   mdta::ApplyParams pp{warped, pred, x, mats, out, ca_sums, H, W, B, x_batch, mode, nstages};
-  mdta::mdta_apply_kernel<<<dim3(parts, B), mdta::kThreads, smem3, s>>>(pp);
+  if (c8) mdta::mdta_apply_c8_kernel<<<dim3(parts, B), mdta::kThreads, smem3_c8, s>>>(pp);
+  else mdta::mdta_apply_kernel<<<dim3(parts, B), mdta::kThreads, smem3, s>>>(pp);
   return check_launch("cdfo_mdta_fwd");
 }
 

@@ -50,11 +50,31 @@ def _f32(t):
     return t.detach().contiguous().float()
 
 
+def _is_c8(t):
+    return t.dim() == 5 and t.dtype == torch.bfloat16 and t.size(1) == 8 and t.size(4) == 8
+
+
 def dual_mdta(mod, x, extra_feat, pred_feat, flow, mode):
     """warp + fusion_out + the two MDTA passes + project_out (arch:3304-3337 / :3456-3492) in csrc/mdta.cu.
     mode 0 (MVDualAttAlignment): returns c8 bf16 [2B, 8, H, W, 8] = cat([o1, o2], 0), the input of conv_offset.0.
     mode 1 (DualAttAlignment): returns (ReLU(fusion_out(cat[o1 + o2, x])) [B,64,H,W] fp32, per-part channel sums of it).
-    `x` may hold fewer samples than the others (sample b uses x[b % x.size(0)])."""
+    `x` may hold fewer samples than the others (sample b uses x[b % x.size(0)]).
+    Mode 0 also takes x, extra_feat and pred_feat as c8 bf16 [., 8, H, W, 8] (all three): cdfo_mdta_c8_fwd."""
+    if mode == 0 and _is_c8(extra_feat):
+        if not (_is_c8(x) and _is_c8(pred_feat)) or pred_feat.shape != extra_feat.shape or extra_feat.size(0) % x.size(0) \
+                or x.shape[2:4] != extra_feat.shape[2:4]:
+            raise _lib.CdfoError("dual_mdta: x, extra_feat and pred_feat must all be c8 bf16 tensors of one size")
+        B, _, H, W, _ = extra_feat.shape
+        x, extra_feat, pred_feat, flow = x.contiguous(), extra_feat.contiguous(), pred_feat.contiguous(), _f32(flow)
+        dev = x.device
+        du0, du2 = mod.conv_du._modules["0"], mod.conv_du._modules["2"]
+        ws = torch.empty(_lib.lib().cdfo_mdta_workspace_bytes(B, H, W, mod.num_heads), dtype=torch.uint8, device=dev)
+        out = torch.empty((2 * B, 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+        _lib.call("cdfo_mdta_c8_fwd", _lib.ptr(x), int(x.size(0)), _lib.ptr(extra_feat), _lib.ptr(pred_feat), _lib.ptr(flow),
+                  _lib.ptr(_f32(mod.fusion_out.weight)), _lib.ptr(_f32(du0.weight)), _lib.ptr(_f32(du0.bias)), _lib.ptr(_f32(du2.weight)),
+                  _lib.ptr(_f32(du2.bias)), _lib.ptr(_f32(mod.temperature)), _lib.ptr(_f32(mod.project_out.weight)), int(mod.num_heads),
+                  _lib.ptr(out), _lib.ptr(ws), B, H, W, _lib.stream_ptr(dev))
+        return out
     B, C, H, W = extra_feat.shape
     if C != 64 or x.size(1) != 64 or pred_feat.shape != extra_feat.shape or B % x.size(0):
         raise _lib.CdfoError("dual_mdta: 64-channel inputs of one size expected")
@@ -167,14 +187,15 @@ unpack_fields = dcn_sm100.unpack_fields   # (residual [B, dg*18, H, W], mask [B,
 
 
 @torch.no_grad()
-def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow, stack=None, group_chunk=None):
+def mv_dual_att_alignment(mod, x, extra_feat, pred_feat, flow, stack=None, group_chunk=None, x8=None):
     """MVDualAttAlignment.forward, arch:3303-3352: DCN with offset = residual + decoded MV prior.
     `x` may hold fewer samples than the other arguments (sample b uses x[b % x.size(0)]): the model's six
     neighbour calls share the centre-frame feature (arch:4456).  With `stack` ([n_seq, chunks, H, W, 8] bf16) the DCN
-    epilogue writes group g of the group-major batch into chunks [group_chunk[g], +8) of it and None is returned."""
+    epilogue writes group g of the group-major batch into chunks [group_chunk[g], +8) of it and None is returned.
+    extra_feat / pred_feat may be c8 bf16 (then x8 = the c8 copy of x is required: the MDTA kernels read c8, the DCN samples x)."""
     if config.dcn_gather == "tex" and config.fused_head_dcn and mod.deformable_groups == 16:
         # ONE kernel from the hidden maps to the aligned feature: the offset / mask fields stay on the SM
-        z = mv_hidden_maps(mod, x, extra_feat, pred_feat, flow)
+        z = mv_hidden_maps(mod, x8 if _is_c8(extra_feat) else x, extra_feat, pred_feat, flow)
         hw, hb = _head_weights_fused(mod.conv_offset._modules["2"], 16)
         return dcn_sm100.mv_head_dcn_fused(z, hw, hb, mod.max_residue_magnitude, dcn_sm100.pack_q4t(x), flow,
                                            dcn_sm100.pack_weight_f16(mod.weight), mod.bias, stack=stack, group_chunk=group_chunk)
@@ -291,7 +312,13 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     Returns the fused feature as c8 bf16 [B, 8, H, W, 8].  The 448-channel stack is written once, in bf16, directly by the
     DCN epilogue (O2) and read by the tcgen05 convolution kernel (kernel size 1)."""
     H, W = center.shape[2:]
-    ufs_prior = prior_conv(model.conv_expand_ufs, ufs_nb)
+    c8_align = (config.mdta_c8 and model.alignment == "mv_dcn" and config.dcn_gather == "tex" and config.fused_head_dcn
+                and model.MV_deform_align.deformable_groups == 16)
+    if c8_align:
+        from . import features
+        ufs_prior = features.prior_conv_c8(model.conv_expand_ufs, ufs_nb, lrelu=False)
+    else:
+        ufs_prior = prior_conv(model.conv_expand_ufs, ufs_nb)
     rms_prior = prior_conv(model.conv_expand_rms, rms_nb)
     # fea_nb: [6B, 64, H, W], or the contiguous runs of it (model.FeatureRing: frames 0-2 and 4-6); cat([fea, x_n]) (arch:4454) is
     # two packs into one c8 tensor
@@ -304,10 +331,17 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
         conv.to_c8(run, out=cat8[sl], channel0=0)
         off += run.size(0)
     fr = model.conv_expand_fea_r
-    fea_i = conv.conv3x3(cat8, fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
     stack = torch.empty((B, 56, H, W, 8), dtype=torch.bfloat16, device=center.device)
-    stack[:, 24:32] = conv.to_c8(center)
+    center8 = conv.to_c8(center)
+    stack[:, 24:32] = center8
     al = model.MV_deform_align
+    if c8_align:
+        # the alignment's MDTA kernels read conv_expand_fea_r's c8 bf16 output, the c8 prior features and the packed centre feature as
+        # they are (no fp32 NCHW copies of any of them)
+        fea_i = conv.conv3x3(cat8, fr.weight, fr.bias, conv.ACT_NONE)
+        mv_dual_att_alignment(al, center, fea_i, ufs_prior, mv_nb, stack=stack, group_chunk=[8 * f for f in _SLOT], x8=center8)
+        return conv.conv3x3(stack, model.tsa_fusion.weight, model.tsa_fusion.bias, conv.ACT_LRELU)   # 1x1, 448 -> 64
+    fea_i = conv.conv3x3(cat8, fr.weight, fr.bias, conv.ACT_NONE, out_nchw=True)
     if model.alignment == "mv_dcn" and config.dcn_gather == "tex":
         mv_dual_att_alignment(al, center, fea_i, ufs_prior, mv_nb, stack=stack, group_chunk=[8 * f for f in _SLOT])
     else:

@@ -219,6 +219,12 @@ int cdfo_mdta_fwd(const float *x, int x_batch, const float *extra, const float *
                   const float *fusion_w, const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2,
                   const float *temperature, const float *proj_w, int heads, int mode, void *out, float *ca_sums,
                   void *workspace, int B, int H, int W, void *stream);
+/* Mode 0 with x, extra, pred as c8 bf16 [.,8,H,W,8] (what their producers write: the tcgen05 convolution's epilogue, the prior
+ * convolution, the centre feature packed for the stack): the bilinear gather loads 16 bytes per corner and 8 channels, the warped
+ * features live in the workspace as bf16, the arithmetic stays fp32 / TF32.  Same workspace size. */
+int cdfo_mdta_c8_fwd(const void *x_c8, int x_batch, const void *extra_c8, const void *pred_c8, const float *flow, const float *fusion_w,
+                     const float *du_w1, const float *du_b1, const float *du_w2, const float *du_b2, const float *temperature,
+                     const float *proj_w, int heads, void *out_c8, void *workspace, int B, int H, int W, void *stream);
 size_t cdfo_mdta_workspace_bytes(int B, int H, int W, int heads);
 int cdfo_mdta_parts(int B);
 /* gate [B,C] = sigmoid(W2 relu(W1 mean + b1) + b2), mean = (sum over `parts` of partial_sums [B,parts,C]) / HW; w1 [Cmid,C], w2 [C,Cmid]. */

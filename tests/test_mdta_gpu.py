@@ -50,6 +50,39 @@ def test_mdta_mode0_vs_oracle(cuda_dev, B, xB, H, W):
     assert err <= 6e-3 * scale + 1e-5          # bf16 output rounding (2^-9) dominates
 
 
+@pytest.mark.parametrize("B,xB,H,W", [(2, 1, 16, 24), (3, 3, 19, 23), (6, 2, 32, 40), (12, 2, 72, 120)])
+def test_mdta_mode0_c8_inputs_vs_oracle(cuda_dev, B, xB, H, W):
+    """The same front end fed with c8 bf16 tensors (cdfo_mdta_c8_fwd: what conv_expand_fea_r, the prior convolution and the stack pack
+    write), against the oracle evaluated on the SAME bf16-rounded inputs, and against the fp32-input kernels."""
+    from cdfo_b200 import conv, hotpath
+    from cdfo_b200.model import CVSR_V8
+    m = CVSR_V8(alignment="mv_dcn")
+    sd = G.seeded_weights("O2")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda_dev).eval()
+    x, extra, pred, flow = _inputs(B, xB, H, W, seed=B * 100 + H + 1)
+    x, extra, pred = (t.to(torch.bfloat16).float() for t in (x, extra, pred))
+    pre = "MV_deform_align."
+    xr = x.repeat(B // xB, 1, 1, 1)
+    with torch.no_grad():
+        warped = torch_ref.flow_warp(extra, flow.permute(0, 2, 3, 1))
+        fused = F.conv2d(torch.cat([warped, pred], 1), sd[pre + "fusion_out.weight"])
+        t = sd[pre + "temperature"]
+        o1 = F.conv2d(torch_ref._mdta(xr, fused, warped * torch_ref._channel_gate(sd, pre + "conv_du", warped), t, 8), sd[pre + "project_out.weight"])
+        o2 = F.conv2d(torch_ref._mdta(xr, fused, pred * torch_ref._channel_gate(sd, pre + "conv_du", pred), t, 8), sd[pre + "project_out.weight"])
+    d = lambda v: v.to(cuda_dev)
+    z = hotpath.dual_mdta(m.MV_deform_align, conv.to_c8(d(x)), conv.to_c8(d(extra)), conv.to_c8(d(pred)), d(flow), mode=0)
+    z32 = hotpath.dual_mdta(m.MV_deform_align, d(x), d(extra), d(pred), d(flow), mode=0)
+    got, got32 = conv.from_c8(z).cpu(), conv.from_c8(z32).cpu()
+    ref = torch.cat([o1, o2], 0)
+    err, dd = (got - ref).abs().max().item(), (got - got32).abs().max().item()
+    scale = ref.abs().max().item()
+    print("mdta mode0 c8 inputs B%d xB%d %dx%d: max err %.3g, vs fp32-input kernels %.3g (max|ref| %.3g)" % (B, xB, H, W, err, dd, scale))
+    assert err <= 8e-3 * scale + 1e-5          # bf16 rounding of the warped features (2^-9) on top of the output rounding
+    assert dd <= 8e-3 * scale + 1e-5
+    assert torch.equal(hotpath.dual_mdta(m.MV_deform_align, conv.to_c8(d(x)), conv.to_c8(d(extra)), conv.to_c8(d(pred)), d(flow), mode=0), z)
+
+
 @pytest.mark.parametrize("B,xB,H,W", [(2, 1, 16, 24), (3, 3, 19, 23)])
 def test_dual_att_alignment_vs_oracle(cuda_dev, B, xB, H, W):
     """Whole DualAttAlignment (arch:3455-3496): MDTA kernels (fp32) + CALayer gate + bf16 tcgen05 residual blocks."""
