@@ -15,7 +15,11 @@
 //   lra_win_kernel    per 8x8 window: q with the masked channel zeroed, softmax(64) . v -> loc_out (NHWC)
 //   fuse              1x1 conv(128 -> 64) over [long_out, loc_out] + bias + x -> NCHW fp32 (csrc/pointwise.cu, tensor cores)
 // All arithmetic fp32 (the 0.5 threshold makes the mask discontinuous: keep it and the softmax exponents exact).
+#include <cuda.h>
+#include <cstring>
+
 #include "cdfo_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace cdfo {
 
@@ -119,10 +123,18 @@ __device__ __forceinline__ void flash_tile_block(float (&sc)[8][4], float (&m_ru
 // queries (~20 % of the tokens) get their own softmax over the row: their scores come from the closed form (tables,
 // no dot products), and the P V products run on the tensor cores in 16-query tiles (flash_tile_block above).
 constexpr int kRowWarps = 9, kRowThreads = kRowWarps * 32;
-__global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__restrict__ qv, const uint8_t *__restrict__ midx,
-                                                                const float *__restrict__ qsel, float *__restrict__ vrow_t,
-                                                                LraTables t, int H, int W) {
-  extern __shared__ __align__(16) float sm[];
+// TMA = true (W % 4 == 0): the raw v row arrives as 64-pixel pieces [64 channels][64 pixels] by tiled TMA (one box per piece from the NCHW
+// map, zero-filled past W) through a two-stage mbarrier ring issued by warp 8, and warps 0-7 run the channel convolution from the piece
+// (thread = pixel x 16 channels) straight into vr[w][c] -- the 4-byte cp.async copies of the other variant cost the LSU one request per
+// element (32 768 per row: two thirds of the kernel, ncu + the same finding as csrc/lra_mask_logits.cu).  Same fp32 operation order.
+constexpr int kRowPiece = 64;
+constexpr int kRowRawBytes = 2 * 64 * kRowPiece * 4 + 64;      // two pieces + four mbarriers (128-byte aligned in front of vr)
+template <bool TMA>
+__global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const __grid_constant__ CUtensorMap qvmap, const float *__restrict__ qv,
+                                                                const uint8_t *__restrict__ midx, const float *__restrict__ qsel,
+                                                                float *__restrict__ vrow_t, LraTables t, int H, int W) {
+  extern __shared__ __align__(1024) float sm_all[];
+  float *sm = TMA ? sm_all + kRowRawBytes / 4 : sm_all;
   const int b = blockIdx.y, h = blockIdx.x;
   const int HW = H * W;
   const int Wk = (W + 63) & ~63;      // keys padded to whole 64-key blocks
@@ -143,7 +155,60 @@ __global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__
   for (int i = 0; i < 9; ++i) kw[i] = t.kw[i];
   for (int e = tid; e < 4096; e += kRowThreads) Rs[e] = t.r[e];
 
-  // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219): the raw row is read from
+  // v_r[w][c] = beta + sum_t kw[t] v[c + t - 4][w]   (conv along the channel axis, arch:2219)
+  if (TMA) {
+    float *raw = sm_all;                                                    // [2][64 c][64 px]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm_all + 2 * 64 * kRowPiece);
+    const uint32_t bar0 = ptx::smem_u32(bars);                              // full 0, 1 | empty 0, 1
+    if (tid == 0) {
+      ptx::mbar_init(bar0, 1);
+      ptx::mbar_init(bar0 + 8, 1);
+      ptx::mbar_init(bar0 + 16, 8);
+      ptx::mbar_init(bar0 + 24, 8);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    const int n_pieces = Wk / kRowPiece;
+    if (warp == 8) {
+      if (lane == 0) {
+        for (int pc = 0; pc < n_pieces; ++pc) {
+          const int st = pc & 1;
+          ptx::mbar_wait_parked(bar0 + 16 + 8 * st, ((pc >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(bar0 + 8 * st, 64 * kRowPiece * 4);
+          ptx::tma_load_3d(ptx::smem_u32(raw) + st * 64 * kRowPiece * 4, &qvmap, bar0 + 8 * st, pc * kRowPiece, h, b * 128 + 64);
+        }
+      }
+    } else {
+      const int px = tid & 63, c0 = (tid >> 6) * 16;                        // 256 threads: pixel x quarter of the channels
+      for (int pc = 0; pc < n_pieces; ++pc) {
+        const int st = pc & 1, w = pc * kRowPiece + px;
+        ptx::mbar_wait_parked(bar0 + 8 * st, (pc >> 1) & 1);
+        const float *rp = raw + st * 64 * kRowPiece + px;
+        float win[24];                                                      // channels c0 - 4 .. c0 + 19 (zero outside 0 .. 63)
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+          const int c = c0 - 4 + i;
+          win[i] = (c >= 0 && c < 64) ? rp[c * kRowPiece] : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar0 + 16 + 8 * st);                // the piece is in registers
+        float *row = vr + w * kLd + c0;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float acc = t.beta;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc = fmaf(kw[i], win[4 * c4 + j + i], acc);
+            o[j] = w < W ? acc : 0.f;                                       // key rows past the frame stay zero
+          }
+          *reinterpret_cast<float4 *>(row + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  } else {
+  // the raw row is read from
   // global once (coalesced along w) into vr[w][c]; then one thread per pixel slides the 9 taps over its 64 channels in place
   const float *vbase = qv + ((size_t)b * 128 + 64) * HW + (size_t)h * W;
   // (4-byte cp.async: the ~107 copies of a thread are all in flight at once -- with one CTA of 9 warps per SM a load -> store loop
@@ -181,6 +246,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) lra_row_kernel(const float *__
       }
       *reinterpret_cast<float4 *>(row + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
     }
+  }
   }
   if (tid == 0) mcount = 0;
   __syncthreads();
@@ -851,6 +917,25 @@ __global__ void __launch_bounds__(kWinTcThreads, 6) lra_win_tc_kernel(const floa
 
 using namespace cdfo;
 
+typedef CUresult (*LraEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static LraEncodeTiledFn lra_encode_tiled_fn() {
+  static LraEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<LraEncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static bool g_lra_row_tma = true;     // cdfo_lra_set_row_tma: the TMA-fed load phase of the row kernel (default) vs 4-byte cp.async
+extern "C" int cdfo_lra_set_row_tma(int on) {
+  g_lra_row_tma = on != 0;
+  return CDFO_OK;
+}
 static bool g_lra_col_tf32 = false;   // cdfo_lra_set_col_precision: A/B switch (tests, tools)
 static bool g_lra_col_tc = true;      // cdfo_lra_set_col_tcgen05: the tcgen05 column kernel (default) vs the warp-level mma.sync kernels
 static bool g_lra_win_tc = true;      // cdfo_lra_set_win_tensor_core: the bf16 split tensor-core window kernel (default) vs the fp32 SIMT one
@@ -922,7 +1007,8 @@ static int lra_run(const float *qv, const float *u, const float *vmax, const flo
                "cdfo_lra_fwd: frame %d x %d exceeds the shared-memory row/column buffers (W <= 704, H <= 384)", H, W);
   static bool attr = false;
   if (!attr) {
-    cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
+    cudaError_t e1 = cudaFuncSetAttribute(lra_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(lra_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e2 = cudaFuncSetAttribute(lra_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(lra_col_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMax);
     cudaError_t e3 = cudaFuncSetAttribute(lra_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem);
@@ -930,7 +1016,27 @@ static int lra_run(const float *qv, const float *u, const float *vmax, const flo
       return fail(CDFO_ERR_CUDA, "cdfo_lra_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     attr = true;
   }
-  lra_row_kernel<<<dim3(H, B), kRowThreads, row_smem, s>>>(qv, midx, qsel, vrow_t, t, H, W);
+  {
+    CUtensorMap qm;
+    memset(&qm, 0, sizeof(qm));
+    bool row_tma = g_lra_row_tma && W % 4 == 0 && ((uintptr_t)qv & 15) == 0 && row_smem + kRowRawBytes <= (size_t)kDynMax;
+    if (row_tma) {
+      static LraEncodeTiledFn enc = lra_encode_tiled_fn();
+      if (enc) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 128};
+        const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+        const cuuint32_t box[3] = {kRowPiece, 1, 64};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult cr = enc(&qm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(qv), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled(qv rows) failed with CUresult %d", (int)cr);
+      } else {
+        row_tma = false;
+      }
+    }
+    if (row_tma) lra_row_kernel<true><<<dim3(H, B), kRowThreads, row_smem + kRowRawBytes, s>>>(qm, qv, midx, qsel, vrow_t, t, H, W);
+    else lra_row_kernel<false><<<dim3(H, B), kRowThreads, row_smem, s>>>(qm, qv, midx, qsel, vrow_t, t, H, W);
+  }
   int col_done = 0;
   if (!g_lra_col_tf32 && g_lra_col_tc) {     // csrc/lra_col_sm100.cu: whole score tile in tensor memory (H <= 448)
     col_done = lra_col_sm100_launch(vrow_t, midx, qsel, long_out, t, B, H, W, s);

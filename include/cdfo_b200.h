@@ -259,6 +259,8 @@ int cdfo_lra_set_col_precision(int tf32);
 int cdfo_lra_set_col_tcgen05(int on);
 /* 8x8 window pass: 1 (default) = tensor cores (bf16 hi/lo split scores, mma.sync), 0 = round 1's fp32 SIMT kernel. */
 int cdfo_lra_set_win_tensor_core(int on);
+/* Row pass: 1 (default) = the raw v row arrives by tiled TMA (mbarrier ring; needs W % 4 == 0), 0 = 4-byte cp.async copies. */
+int cdfo_lra_set_row_tma(int on);
 int cdfo_lra_c8_fwd(const float *qv, const float *u, const float *vmax, const float *x, const float *x2, const float *tables,
                     float beta, float bh, const float *fuse_w, const float *fuse_b, void *out_c8, int out_channels, int channel0,
                     void *workspace, int B, int H, int W, void *stream);

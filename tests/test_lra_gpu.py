@@ -205,3 +205,20 @@ def test_mask_logits_tma_vs_cp_async(cuda_dev):
     print("mask logits TMA vs cp.async: max diff %.3g (max|ref| %.3g)" % (err, ref.abs().max().item()))
     assert err <= 1e-5 * max(1.0, ref.abs().max().item())
     assert torch.equal(hotpath.mask_logits(m.RDAB, v), got)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 24, 40), (1, 16, 72), (2, 272, 480)])
+def test_lra_row_tma_equals_cp_async(cuda_dev, B, H, W):
+    """The row pass fed by tiled TMA (64-pixel pieces through an mbarrier ring, the default) against the 4-byte cp.async load phase:
+    same fp32 operations in the same order, so the module output is bit-identical (one, two and eight pieces; a partial last piece)."""
+    from cdfo_b200 import _lib
+    res, x, u = _inputs(B, H, W, seed=3 * H + W)
+    m = _model(cuda_dev)
+    res, x, u = res.to(cuda_dev), x.to(cuda_dev), u.to(cuda_dev)
+    try:
+        _lib.call("cdfo_lra_set_row_tma", 0)
+        ref = m.RDAB(res, x, u)
+    finally:
+        _lib.call("cdfo_lra_set_row_tma", 1)
+    out = m.RDAB(res, x, u)
+    assert torch.equal(out, ref)

@@ -30,6 +30,20 @@ fns = {
     "tail": lambda: hotpath.tail(m, center, x1),
     "features": lambda: m._features(x1, x1),
 }
+if a.stage == "step":
+    # one steady-state step of the whole model (cached L1 features, feature ring), as bench.py runs it
+    m.feature_ring = True
+    clip = synthetic.make_clip(1, H, W, S)
+    d = {k: clip[k].to(dev) for k in ("x", "pms", "rms", "ufs")}
+    mvs = torch.cat([cdfo_b200.mv2mvs(clip["mv_l0"].to(dev)[s]) for s in range(S)], 0)
+    noise = torch.rand(6 * S, 64, H, W, device=dev, generator=g).clamp_min(1e-12)
+    state = {}
+    with torch.no_grad():
+        _, state["l1"] = m(d["x"], None, mvs, d["pms"], d["rms"], d["ufs"], None, noise=noise)
+
+    def step():
+        _, state["l1"] = m(d["x"], None, mvs, d["pms"], d["rms"], d["ufs"], state["l1"], noise=noise)
+    fns["step"] = step
 fn = fns[a.stage]
 with torch.no_grad():
     for _ in range(2):
@@ -42,4 +56,4 @@ with torch.no_grad():
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         fn()
         torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
