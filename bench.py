@@ -366,7 +366,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload(args), "lr": [H, W], "seqs_per_gpu": S, "cuda_graph": bool(args.graph), "parallelism": "sequence-sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (per step > 1 GB of offsets/masks/activations; %d rotating windows)" % len(pool),
-                       "stages": "alignment / attention / fusion / trunk (CTA-pair tcgen05 convs) / tail: this repo's CUDA kernels (DESIGN.md 4 lists the small cuDNN calls left); feature extraction: cuDNN bf16 + own LayerNorm / depthwise kernels"},
+                       "stages": "feature extraction / alignment / attention / fusion / trunk (CTA-pair tcgen05 convs) / tail: this repo's CUDA kernels only (no cuDNN / cuBLAS launch in the step; DESIGN.md 4 lists the ATen copies left)"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }

@@ -8,8 +8,9 @@ same parameter names and shapes (reference state_dicts load with strict=True), b
   * the hot path -- prior-guided attention (RDAB), MV-guided alignment (DualAttAlignment /
     MVDualAttAlignment + DCN), fusion and the upsampling tail -- runs in the CUDA kernels of libcdfo_b200
     (see hotpath.py); CUDA only, no CPU fallback;
-  * the parts SURVEY.md 8(f) ranks as "next" (feature extraction, reconstruction trunk) are plain cuDNN
-    convolutions for now (`self.lowp` selects bf16 channels_last for them).
+  * the parts SURVEY.md 8(f) ranks as "next" (feature extraction, reconstruction trunk) run in this repo's c8 bf16 kernels when
+    `self.lowp` is torch.bfloat16 (features.py, hotpath.recon_trunk); with lowp = None the feature extraction is the plain fp32 torch
+    chain (used by the fp32 parity tests) and `trunk_backend = "cudnn"` selects torch convolutions for A/B runs.
 
 `alignment="dual_att"` is the model as shipped (O1); `alignment="mv_dcn"` swaps in the DCN alignment the
 reference carries commented out at arch:4396 (O2, the variant BASELINE.json's DCN roofline is quoted on).
@@ -43,7 +44,7 @@ def _seq(*mods_by_index):
     return h
 
 
-# ------------------------------------------------------------------------------------------ "next" rows (torch / cuDNN)
+# ------------------------------------------------------------------------------------------ "next" rows: parameter holders + fp32 torch chain
 class _ChannelLayerNorm(_Holder):
     """LayerNorm(dim, WithBias) over channels per pixel, arch:1169-1198; parameters live at `.body`."""
 
@@ -350,7 +351,7 @@ class CVSR_V8(nn.Module):
         self.trunk_backend = "cuda"   # "cuda": tcgen05 convs + resample kernels on c8 bf16; "cudnn": torch convolutions
         self.feature_ring = False     # True: the returned L1_fea is a FeatureRing handle (no per-frame copies of the window's features)
 
-    # -- feature extraction of `n` frames ("next" row f2; cuDNN for now)
+    # -- feature extraction of `n` frames ("next" row f2): own c8 bf16 kernels with lowp = bf16
     def _features(self, x, pms):
         dt = self.lowp
         if dt is torch.bfloat16 and config.features_c8 and x.is_cuda:
@@ -365,7 +366,7 @@ class CVSR_V8(nn.Module):
         return self.transformer_feature_extraction(l1, self.conv_second(pms))
 
     def _trunk(self, x8):
-        """c8 bf16 in -> NCHW fp32 out ("next" row f1; cuDNN for now)."""
+        """c8 bf16 in -> c8 bf16 out on the tcgen05 kernels ("next" row f1); NCHW fp32 out on the torch A/B backend."""
         from . import conv
         if self.trunk_backend == "cuda":
             return hotpath.recon_trunk(self.recon_trunk, x8)      # c8 bf16 out: the tail takes it as is
