@@ -141,11 +141,12 @@ def ps_order(t):
 
 
 @torch.no_grad()
-def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False, parity_planes=False):
+def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pixel_shuffle=False, parity_planes=False, bias_edge=None):
     """Convolution with a [Cout, Cin, k, k] weight, k = 1 or 3, stride 1, "same" padding, on the tcgen05 kernel.
     x8 [B, Cin/8, H, W, 8] bf16 -> [B, Cout/8, H, W, 8] bf16 (or [B, Cout, H, W] fp32 when out_nchw, or
     [B, Cout/32, 2H, 2W, 8] bf16 = PixelShuffle(2) when pixel_shuffle and the weight rows are in ps_order, or the four parity
-    planes [B, Cout/8, 2, 2, H/2, W/2, 8] when parity_planes: CTA-pair shapes only, the input layout of conv3x3_then_half)."""
+    planes [B, Cout/8, 2, 2, H/2, W/2, 8] when parity_planes: CTA-pair shapes only, the input layout of conv3x3_then_half).
+    bias_edge [9, Cout] fp32: per-class bias of the border pixels (cdfo_conv3x3_pair_sm100_edge_fwd; CTA-pair shapes only)."""
     B, C8, H, W, _ = x8.shape
     Cout, Cin, ks = weight.shape[:3]
     if C8 * 8 != Cin or ks not in (1, 3) or weight.shape[3] != ks:
@@ -158,6 +159,17 @@ def conv3x3(x8, weight, bias=None, act=ACT_NONE, resid8=None, out_nchw=False, pi
     # 64 -> 64 has one K block per tile: the single-SM kernel is faster there (795 vs 621 TFLOP/s); parity_planes forces the pair kernel
     pair_shape = _lib.lib().cdfo_conv3x3_pair_sm100_supported(Cout, Cin) and (parity_planes or not (Cin == 64 and Cout == 64))
     pair_ok = ks == 3 and not pixel_shuffle and not out_nchw and pair_shape
+    if bias_edge is not None:
+        if not (config.conv_pair and pair_ok) or b is None or tuple(bias_edge.shape) != (9, Cout) or bias_edge.dtype != torch.float32 \
+                or not bias_edge.is_contiguous() or H < 2 or W < 2:
+            raise _lib.CdfoError("conv3x3: bias_edge needs a CTA-pair shape, a bias and a contiguous fp32 [9, %d] table" % Cout)
+        if parity_planes and (resid8 is not None or H % 2 or W % 2):
+            raise _lib.CdfoError("conv3x3: parity_planes needs an even size and no residual")
+        shape = (B, Cout // 8, 2, 2, H // 2, W // 2, 8) if parity_planes else (B, Cout // 8, H, W, 8)
+        y = torch.empty(shape, dtype=torch.bfloat16, device=x8.device)
+        _lib.call("cdfo_conv3x3_pair_sm100_edge_fwd", _lib.ptr(x8), _lib.ptr(pack_weight_pair(weight)), _lib.ptr(b), _lib.ptr(bias_edge),
+                  _lib.ptr(resid8), _lib.ptr(y), B, Cin, Cout, H, W, int(act), 1 if parity_planes else 0, _lib.stream_ptr(x8.device))
+        return y
     if parity_planes:
         if not pair_ok or resid8 is not None or H % 2 or W % 2:
             raise _lib.CdfoError("conv3x3: parity_planes needs a CTA-pair shape (3x3, %d -> %d), an even size and no residual" % (Cin, Cout))

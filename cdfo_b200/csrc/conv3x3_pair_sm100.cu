@@ -35,6 +35,8 @@ constexpr int kThreads = 320, kEpiWarps = 8;
 struct Params {
   const uint8_t *wpk;   // [2 halves][9 taps][Cin/8][NH][8] bf16
   const float *bias;    // [2 NH] or nullptr
+  const float *bias_edge;  // [9][2 NH] or nullptr: the bias of border pixels by class (row top / middle / bottom) * 3 + (column left / middle /
+                           // right) -- a 1x1 convolution composed INTO this 3x3 one has its own bias under the taps inside the frame only
   const uint4 *resid;   // c8 bf16 [B][2 NH / 8][H][W][8] or nullptr (added after the activation)
   uint4 *y;             // c8 bf16 [B][2 NH / 8][H][W][8]
   int B, Cin, H, W, act;
@@ -212,9 +214,22 @@ conv3x3_pair_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         }
         if (!live) continue;
         float v[16];
+        const int cls = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
+        float bb[16];
+        if (p.bias_edge != nullptr && cls != 4) {             // border pixels only (< 1 %): ONE branch per pass, not one per channel
+          const float4 *be = reinterpret_cast<const float4 *>(p.bias_edge + cls * kN + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 q = __ldg(be + i);
+            bb[4 * i] = q.x; bb[4 * i + 1] = q.y; bb[4 * i + 2] = q.z; bb[4 * i + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bb[i] = bias_s[c0 + i];
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float t = __uint_as_float(rr[i]) + bias_s[c0 + i];
+          float t = __uint_as_float(rr[i]) + bb[i];
           if (p.act == 1) t = fmaxf(t, 0.f);
           else if (p.act == 2) t = t > 0.f ? t : 0.1f * t;
           v[i] = t;
@@ -321,6 +336,8 @@ extern "C" int cdfo_conv3x3_pair_sm100_pack_weight(const float *w, void *wpk, in
   return conv3x3_pack_weight_raw(w, wpk, Cout, Cin, cpair::half_channels(Cout, Cin), 2, 0, 9, (cudaStream_t)stream);
 }
 
+extern "C" int cdfo_conv3x3_pair_sm100_edge_fwd(const void *x_c8, const void *wpk, const float *bias, const float *bias_edge, const void *resid_c8,
+                                               void *y, int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream);
 extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y,
                                                   int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream);
 
@@ -331,6 +348,11 @@ extern "C" int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, co
 
 extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y_c8,
                                                   int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream) {
+  return cdfo_conv3x3_pair_sm100_edge_fwd(x_c8, wpk, bias, nullptr, resid_c8, y_c8, B, Cin, Cout, H, W, act, y_planes, stream);
+}
+
+extern "C" int cdfo_conv3x3_pair_sm100_edge_fwd(const void *x_c8, const void *wpk, const float *bias, const float *bias_edge, const void *resid_c8,
+                                               void *y_c8, int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream) {
   CDFO_REQUIRE(x_c8 && wpk && y_c8, CDFO_ERR_NULL, "cdfo_conv3x3_pair_sm100_fwd: NULL pointer");
   CDFO_REQUIRE(y_planes == 0 || y_planes == 2 || (y_planes == 1 && H % 2 == 0 && W % 2 == 0), CDFO_ERR_SHAPE,
                "cdfo_conv3x3_pair_sm100_planes_fwd: the parity-plane output needs an even size (got %d x %d)", H, W);
@@ -358,7 +380,7 @@ extern "C" int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CDFO_REQUIRE(cr == CUDA_SUCCESS, CDFO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
   cpair::Params p;
-  p.wpk = (const uint8_t *)wpk; p.bias = bias; p.resid = (const uint4 *)resid_c8; p.y = (uint4 *)y_c8;
+  p.wpk = (const uint8_t *)wpk; p.bias = bias; p.bias_edge = bias_edge; p.resid = (const uint4 *)resid_c8; p.y = (uint4 *)y_c8;
   p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.act = act; p.y_planes = y_planes; p.tma_wide = wide ? 1 : 0;
   p.tiles_x = ceil_div(W, cpair::kTileW); p.tiles_y = ceil_div(H, cpair::kTileH);
   const long long mt = (long long)B * p.tiles_x * p.tiles_y;

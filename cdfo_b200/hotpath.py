@@ -373,16 +373,31 @@ def _compose_1x1_after_3x3(w1, b1, w3, b3):
     return w, b
 
 
+def _compose_3x3_after_1x1(w3, b3, w1, b1):
+    """conv3x3(w3, b3, zero padding) o conv1x1(w1, b1) == conv3x3(w, .) with a bias that depends on the border class: the 1x1's bias is
+    seen only by the taps that lie inside the frame.  Returns (w [O, I, 3, 3], interior bias [O], bias_edge [9, O]) with class =
+    (row: top 0 / middle 1 / bottom 2) * 3 + (column: left 0 / middle 1 / right 2)."""
+    m = w1.float().reshape(w1.size(0), w1.size(1))
+    w = torch.einsum("omkl,mi->oikl", w3.float(), m).contiguous()
+    tapb = torch.einsum("omkl,m->okl", w3.float(), b1.float())                  # [O, 3, 3]: the 1x1 bias through each tap
+    rows = (slice(1, 3), slice(0, 3), slice(0, 2))                              # taps inside the frame for a top / middle / bottom row
+    be = torch.stack([b3.float() + tapb[:, rows[r], rows[c]].sum(dim=(1, 2)) for r in range(3) for c in range(3)], 0).contiguous()
+    return w, be[4].contiguous(), be
+
+
 def _block_weights(blk):
-    """Per cross-scale block: the 1x1 convs that FOLLOW a body, composed into the body's second 3x3 (cached on the block)."""
-    b2 = blk.body._modules["2"]
+    """Per cross-scale block: the 1x1 convs that FOLLOW a body, composed into the body's second 3x3, and the 1x1 convs that PRECEDE a
+    body (they commute with the bilinear resampling), composed into the body's first 3x3 with a border-aware bias (cached on the block)."""
+    b0, b2 = blk.body._modules["0"], blk.body._modules["2"]
     dn, up = blk.down._modules["0"], blk.up._modules["0"]
 
     def build():
         wu2, bu2 = _compose_1x1_after_3x3(up.weight.detach(), up.bias.detach(), b2.weight.detach(), b2.bias.detach())
         wd2, bd2 = _compose_1x1_after_3x3(dn.weight.detach(), dn.bias.detach(), b2.weight.detach(), b2.bias.detach())
-        return {"up_body2": (wu2, bu2), "dn_body2": (wd2, bd2)}
-    return _module_cache(blk, "composed", _pkey(b2.weight, b2.bias, dn.weight, dn.bias, up.weight, up.bias), build)
+        return {"up_body2": (wu2, bu2), "dn_body2": (wd2, bd2),
+                "body0_dn": _compose_3x3_after_1x1(b0.weight.detach(), b0.bias.detach(), dn.weight.detach(), dn.bias.detach()),
+                "body0_up": _compose_3x3_after_1x1(b0.weight.detach(), b0.bias.detach(), up.weight.detach(), up.bias.detach())}
+    return _module_cache(blk, "composed", _pkey(b0.weight, b0.bias, b2.weight, b2.bias, dn.weight, dn.bias, up.weight, up.bias), build)
 
 
 @torch.no_grad()
@@ -400,12 +415,22 @@ def cross_scale_block(blk, x8, x8_half=None, want_half=False):
     wts = _block_weights(blk)
     y = conv.conv3x3(conv.conv3x3(x8, b0.weight, b0.bias, conv.ACT_LRELU), b2.weight, b2.bias, conv.ACT_NONE, resid8=x8)
     fused = config.trunk_fused_resample and config.conv_fold_half and x8.size(2) % 2 == 0 and x8.size(3) % 2 == 0
-    xd = conv.conv3x3(x8_half if x8_half is not None else conv.resample(x8, 0), dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
-    cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
-    xu = conv.resample(conv.conv3x3(x8, up.weight, up.bias, conv.ACT_NONE), 1)               # 1x1
+    xh = x8_half if x8_half is not None else conv.resample(x8, 0)
+    compose = config.trunk_compose_1x1 and config.conv_pair and min(xh.shape[2:4]) >= 2
+    if compose:
+        # the down / up 1x1 convolutions live inside body.0's weights (border-aware bias): no 1x1 launches, body.0 reads the resampled x
+        wd0, bd0, ed0 = wts["body0_dn"]
+        wu0, bu0, eu0 = wts["body0_up"]
+        cu = conv.conv3x3(conv.conv3x3(xh, wd0, bd0, conv.ACT_LRELU, bias_edge=ed0), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
+        xu = conv.resample(x8, 1)
+    else:
+        xd = conv.conv3x3(xh, dn.weight, dn.bias, conv.ACT_NONE)            # 1x1
+        cu = conv.conv3x3(conv.conv3x3(xd, b0.weight, b0.bias, conv.ACT_LRELU), wts["up_body2"][0], wts["up_body2"][1], conv.ACT_NONE)
+        xu = conv.resample(conv.conv3x3(x8, up.weight, up.bias, conv.ACT_NONE), 1)               # 1x1
+        wu0, bu0, eu0 = b0.weight, b0.bias, None
     if config.conv_fold_half:
         # the 2x-resolution intermediate lives as its four parity planes: the stride-2 taps of the folded convolution are dense boxes
-        t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU, parity_planes=config.conv_parity_planes and config.conv_pair)
+        t2 = conv.conv3x3(xu, wu0, bu0, conv.ACT_LRELU, parity_planes=config.conv_parity_planes and config.conv_pair, bias_edge=eu0)
         # bilinear x0.5 of a 3x3 convolution = one 4x4 / stride-2 convolution: evaluated at 1x, the branch sum starts in its epilogue
         if fused:
             # ... and ends there: + bilinear x2 of the half-resolution branch, and the x0.5 of the sum for the next block's down branch
@@ -413,7 +438,7 @@ def cross_scale_block(blk, x8, x8_half=None, want_half=False):
         yb = conv.conv3x3_then_half(t2, wts["dn_body2"][0], wts["dn_body2"][1], resid8=y)
         out = conv.resample(None, 3, b=cu, base=yb)
     else:
-        t2 = conv.conv3x3(xu, b0.weight, b0.bias, conv.ACT_LRELU)
+        t2 = conv.conv3x3(xu, wu0, bu0, conv.ACT_LRELU, bias_edge=eu0)
         b3 = conv.conv3x3(t2, wts["dn_body2"][0], wts["dn_body2"][1], conv.ACT_NONE)
         out = conv.resample(b3, 2, b=cu, base=y)
     return (out, None) if want_half else out

@@ -301,6 +301,11 @@ int cdfo_conv3x3_pair_sm100_fwd(const void *x_c8, const void *wpk, const float *
  * y_planes = 2: y is NCHW fp32 [B,Cout,H,W]. */
 int cdfo_conv3x3_pair_sm100_planes_fwd(const void *x_c8, const void *wpk, const float *bias, const void *resid_c8, void *y, int B,
                                        int Cin, int Cout, int H, int W, int act, int y_planes, void *stream);
+/* Same, with bias_edge [9][Cout] fp32 (or NULL): the bias of the border pixels by class (row: top 0 / middle 1 / bottom 2) * 3 + (column: left
+ * 0 / middle 1 / right 2); `bias` stays the interior one (class 4).  For a 1x1 convolution composed INTO this 3x3 one (Block_'s down / up 1x1
+ * followed by body.0, arch/SIDECVSR_our.py:388-406): its bias passes only under the taps that lie inside the frame. */
+int cdfo_conv3x3_pair_sm100_edge_fwd(const void *x_c8, const void *wpk, const float *bias, const float *bias_edge, const void *resid_c8,
+                                     void *y, int B, int Cin, int Cout, int H, int W, int act, int y_planes, void *stream);
 /* ---- "3x3 convolution at 2H x 2W followed by bilinear x0.5" as ONE 4x4 / stride-2 convolution on a CTA pair
  * (csrc/conv4x4s2_pair_sm100.cu): the down(body(up(x))) branch of Block_.forward, arch/SIDECVSR_our.py:401-406 with Interpolate(0.5)
  * :324-333.  w3 [64,Cin,3,3] fp32 is the 3x3 weight (pack_weight folds the 2x2 mean into a 4x4 kernel);

@@ -167,6 +167,37 @@ def test_conv4x4s2_block_epilogue(cuda_dev, case):
     assert (conv.from_c8(h_b) - conv.from_c8(conv.resample(y_b, 0))).abs().max().item() <= 2 ** -7 * scale
 
 
+@pytest.mark.parametrize("B,H,W,planes", [(1, 16, 8, False), (2, 34, 50, False), (1, 40, 24, True), (2, 2, 2, False)])
+def test_conv3x3_with_composed_1x1_and_border_bias(cuda_dev, B, H, W, planes):
+    """A 1x1 convolution composed into the following zero-padded 3x3 one (hotpath._compose_3x3_after_1x1: Block_'s down / up 1x1 + body.0,
+    arch:388-406): composed weights + the border-class bias table of cdfo_conv3x3_pair_sm100_edge_fwd against the torch chain
+    conv2d(conv2d(x, w1, b1), w3, b3, padding=1), borders and corners included."""
+    from cdfo_b200 import conv, hotpath
+    g = torch.Generator().manual_seed(B * 100 + H)
+    d = lambda t: t.to(cuda_dev)
+    x = d(torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).float())
+    w1 = d(torch.randn(64, 64, 1, 1, generator=g) / 8)
+    b1 = d(torch.randn(64, generator=g))                       # a large 1x1 bias: the border classes differ visibly
+    w3 = d(torch.randn(256, 64, 3, 3, generator=g) / 24)
+    b3 = d(torch.randn(256, generator=g) * 0.1)
+    ref = F.leaky_relu(F.conv2d(F.conv2d(x, w1, b1), w3, b3, padding=1), 0.1)
+    w, b, be = hotpath._compose_3x3_after_1x1(w3, b3, w1, b1)
+    assert (be[0] - be[4]).abs().max().item() > 0.1
+    y = conv.conv3x3(conv.to_c8(x), w, b, conv.ACT_LRELU, parity_planes=planes, bias_edge=be)
+    if planes:
+        y = y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, 32, H, W, 8).contiguous()
+    y = conv.from_c8(y)
+    scale = max(1.0, ref.abs().max().item())
+    err = (y - ref).abs().max().item()
+    border = torch.ones_like(ref, dtype=torch.bool)
+    border[:, :, 1:-1, 1:-1] = False
+    print("composed 1x1 o 3x3 %dx%dx%d: max err %.3g (border %.3g), max|ref| %.3g" % (B, H, W, err, (y - ref)[border].abs().max().item(), scale))
+    assert err <= 1.2e-2 * scale          # bf16 rounding of the composed weights and of the output
+    # without the table the border pixels are wrong by the 1x1 bias seen through the missing taps
+    y0 = conv.from_c8(conv.conv3x3(conv.to_c8(x), w, b, conv.ACT_LRELU))
+    assert (y0 - ref)[border].abs().max().item() > 5 * err
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(1, 64, 256, 32, 16), (2, 64, 256, 66, 42), (1, 256, 64, 34, 18), (1, 64, 256, 544, 960)])
 def test_conv3x3_pair_parity_plane_output(cuda_dev, B, Cin, Cout, H, W):
     """The CTA-pair convolution writing its output as four parity planes [B, C/8, 2, 2, H/2, W/2, 8] (the layout the folded

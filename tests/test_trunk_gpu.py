@@ -29,10 +29,10 @@ def test_resample_c8_vs_interpolate(cuda_dev, H, W):
     assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_trunk_vs_oracle(cuda_dev, fused):
+@pytest.mark.parametrize("fused,compose", [(True, True), (True, False), (False, False)])
+def test_trunk_vs_oracle(cuda_dev, fused, compose):
     """SCNet_ (21 cross-scale blocks) on c8 bf16 with composed 1x1 convolutions vs the fp32 oracle (arch:378-480), with the block sums in
-    the folded convolution's epilogue (default) and with round 1's resampling kernels.  Observed on the B200: 7.2e-3 / 7.4e-3 of max|ref|
+    the folded convolution's epilogue and the down / up 1x1 convolutions composed into body.0 (default), and with round 1's separate kernels.  Observed on the B200: 7.2e-3 / 7.4e-3 of max|ref|
     (21 blocks of bf16 activations); the bound is 1e-2."""
     from cdfo_b200 import config, conv, hotpath
     from cdfo_b200.model import CVSR_V8
@@ -44,14 +44,14 @@ def test_trunk_vs_oracle(cuda_dev, fused):
     x = torch.randn(1, 64, 24, 40, generator=g)
     with torch.no_grad():
         ref = torch_ref.trunk(sd, x)
-    keep = config.trunk_fused_resample
+    keep = config.trunk_fused_resample, config.trunk_compose_1x1
     try:
-        config.trunk_fused_resample = fused
+        config.trunk_fused_resample, config.trunk_compose_1x1 = fused, compose
         got = conv.from_c8(hotpath.recon_trunk(m.recon_trunk, conv.to_c8(x.to(cuda_dev)))).cpu()
     finally:
-        config.trunk_fused_resample = keep
+        config.trunk_fused_resample, config.trunk_compose_1x1 = keep
     err = (got - ref).abs().max().item()
-    print("trunk (fused resampling %s) max err %.3g (max|ref| %.3g)" % (fused, err, ref.abs().max().item()))
+    print("trunk (fused resampling %s, composed 1x1 %s) max err %.3g (max|ref| %.3g)" % (fused, compose, err, ref.abs().max().item()))
     assert err <= 1e-2 * ref.abs().max().item()
 
 
