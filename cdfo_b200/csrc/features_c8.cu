@@ -101,31 +101,69 @@ __global__ void __launch_bounds__(128) layernorm_c8_kernel(const uint4 *__restri
   }
 }
 
-// ---- depthwise 3x3, stride 1, padding 1, no bias: thread per (pixel, chunk) ----
+// ---- depthwise 3x3, stride 1, padding 1, no bias ----
+// Thread = (column, 8-channel chunk, strip of kDwRows rows): the three input rows an output row needs slide through registers (24 values
+// unpacked per new row instead of 72 per output, 3 loads instead of 9, no per-tap bounds tests: rows / columns outside the frame enter
+// the window as zeros), the 72 weights of the chunk live in registers.  Same fp32 tap order (i, j row-major) as the direct form.
+constexpr int kDwRows = 16;
 __global__ void __launch_bounds__(128) dwconv3x3_c8_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, uint4 *__restrict__ y,
-                                                           int C8, int H, int W) {
-  __shared__ float ws[72];      // [8 channels of this chunk][9]
-  const int kc = blockIdx.y, b = blockIdx.z;
-  if (threadIdx.x < 72) ws[threadIdx.x] = w[kc * 72 + threadIdx.x];
-  __syncthreads();
-  const int HW = H * W, p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  const int h = p / W, wq = p - h * W;
-  const uint4 *xp = x + ((size_t)b * C8 + kc) * HW;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                                           int C8, int H, int W, int strips) {
+  const int kc = blockIdx.y / strips, strip = blockIdx.y - kc * strips, b = blockIdx.z;
+  const int wq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wq >= W) return;
+  float wr[8][9];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int e = 0; e < 8; ++e)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int hh = h + i - 1, ww = wq + j - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        float t[8];
-        unpack8(__ldg(xp + hh * W + ww), t);
+    for (int k = 0; k < 9; ++k) wr[e][k] = __ldg(w + kc * 72 + e * 9 + k);
+  const uint4 *xp = x + ((size_t)b * C8 + kc) * H * W;
+  uint4 *yp = y + ((size_t)b * C8 + kc) * H * W;
+  const int r0 = strip * kDwRows, r1 = min(r0 + kDwRows, H);
+  const bool has_l = wq > 0, has_r = wq + 1 < W;
+  float win[3][3][8];                           // [row slot][column -1, 0, +1][channel]
+  uint4 raw[2][3];                              // rows r + 1 and r + 2 in flight (two rows of look-ahead: the kernel is latency-bound)
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  auto load_raw = [&](int r, uint4 (&dst)[3]) {
+    dst[0] = dst[1] = dst[2] = z;
+    if (r >= 0 && r < H) {
+      const uint4 *row = xp + (size_t)r * W + wq;
+      if (has_l) dst[0] = __ldg(row - 1);
+      dst[1] = __ldg(row);
+      if (has_r) dst[2] = __ldg(row + 1);
+    }
+  };
+  auto unpack_row = [&](const uint4 (&src)[3], float (&dst)[3][8]) {
+    unpack8(src[0], dst[0]);
+    unpack8(src[1], dst[1]);
+    unpack8(src[2], dst[2]);
+  };
+  {
+    uint4 t0[3], t1[3];
+    load_raw(r0 - 1, t0);
+    load_raw(r0, t1);
+    load_raw(r0 + 1, raw[0]);
+    load_raw(r0 + 2, raw[1]);
+    unpack_row(t0, win[0]);
+    unpack_row(t1, win[1]);
+  }
+  for (int rb = r0; rb < r1; rb += 6) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(ws[e * 9 + i * 3 + j], t[e], acc[e]);
+    for (int u = 0; u < 6; ++u) {               // output row rb + u: window slots (u, u + 1, u + 2) mod 3 hold rows r - 1, r, r + 1
+      const int r = rb + u;
+      if (r < r1) {
+        unpack_row(raw[u % 2], win[(u + 2) % 3]);          // row r + 1, loaded two steps ago
+        load_raw(r + 3, raw[u % 2]);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(wr[e][i * 3 + j], win[(u + i) % 3][j][e], acc[e]);
+        yp[(size_t)r * W + wq] = pack8(acc);
       }
     }
-  y[((size_t)b * C8 + kc) * HW + p] = pack8(acc);
+  }
 }
 
 // ---- per-head Gram q k^T and squared row norms: head h = chunk h of q (chunks 0..7) and of k (chunks 8..15) ----
@@ -177,17 +215,19 @@ __global__ void __launch_bounds__(kGramThreads) mdta_gram_c8_kernel(const uint4 
 }
 
 // ---- M[b] = project_out . blockdiag_h softmax_j( G_h[i][j] / (max(|q_i|, eps) max(|k_j|, eps)) * T_h ): one CTA per sample ----
-__global__ void __launch_bounds__(64) mdta_fold_kernel(const float *__restrict__ partial, const float *__restrict__ temperature,
-                                                       const float *__restrict__ proj, float *__restrict__ M, int parts) {
+__global__ void __launch_bounds__(256) mdta_fold_kernel(const float *__restrict__ partial, const float *__restrict__ temperature,
+                                                        const float *__restrict__ proj, float *__restrict__ M, int parts) {
   __shared__ float s[640], attn[512];
   const int b = blockIdx.x, t = threadIdx.x;
-  for (int i = t; i < 640; i += 64) {
+  for (int i = t; i < 640; i += blockDim.x) {
+    const float *src = partial + (size_t)b * parts * 640 + i;
     float v = 0.f;
-    for (int pt = 0; pt < parts; ++pt) v += partial[((size_t)b * parts + pt) * 640 + i];     // fixed order
+#pragma unroll 8
+    for (int pt = 0; pt < parts; ++pt) v += src[(size_t)pt * 640];     // fixed order; independent loads, eight in flight
     s[i] = v;
   }
   __syncthreads();
-  {   // row t = (head, i): softmax over j
+  if (t < 64) {   // row t = (head, i): softmax over j
     const int head = t >> 3, i = t & 7;
     const float nq = fmaxf(sqrtf(s[512 + head * 8 + i]), 1e-12f);      // F.normalize: x / max(|x|, eps)
     float l[8], mx = -INFINITY;
@@ -204,64 +244,91 @@ __global__ void __launch_bounds__(64) mdta_fold_kernel(const float *__restrict__
     for (int j = 0; j < 8; ++j) attn[head * 64 + i * 8 + j] = l[j] / sum;
   }
   __syncthreads();
-  // M[o][8 head + j] = sum_i proj[o][8 head + i] attn[head][i][j]; thread t = output channel o
-  for (int c = 0; c < 64; ++c) {
-    const int head = c >> 3, j = c & 7;
+  // M[o][8 head + j] = sum_i proj[o][8 head + i] attn[head][i][j]
+  for (int e = t; e < 4096; e += blockDim.x) {
+    const int o = e >> 6, c = e & 63, head = c >> 3, j = c & 7;
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc = fmaf(proj[t * 64 + head * 8 + i], attn[head * 64 + i * 8 + j], acc);
-    M[((size_t)b * 64 + t) * 64 + c] = acc;
+    for (int i = 0; i < 8; ++i) acc = fmaf(proj[o * 64 + head * 8 + i], attn[head * 64 + i * 8 + j], acc);
+    M[(size_t)b * 4096 + e] = acc;
   }
 }
 
-// ---- out1 = x1 + M_b v, optionally out2 = out1 + x2: thread per pixel, v (chunks v_chunk0 .. +7 of the qkv tensor) in registers,
-//      M_b (16 KB fp32) in shared memory read as broadcast float4 ----
+// ---- out1 = x1 + M_b v, optionally out2 = out1 + x2, on the tensor cores (warp-level mma.sync m16n8k16 bf16, fp32 accumulate) ----
+// Pixels are the M dimension: the A fragments (v: 16 pixels x 16 input channels) and the C fragments (16 pixels x 8 output channels) are
+// 4-byte words of the c8 chunks, loaded from / stored to global memory directly (a warp instruction covers 8 pixels x 16 bytes = 128
+// contiguous bytes per chunk) -- no shared-memory staging; the B fragments (M_b as bf16, 64 registers) are loaded once per CTA.  The SIMT
+// form (thread per pixel, 4096 FMAs + 1024 broadcast LDS.128) was bound by both the fp32 pipe and the shared-memory reads at ~60 us each for
+// a job that moves 30 us of HBM traffic.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int kApplyLd = 36;      // words per row of M in shared memory: 36 % 32 == 4 -> conflict-free B-fragment loads
 __global__ void __launch_bounds__(128) mdta_apply_c8_kernel(const uint4 *__restrict__ qkv, int C8, int v_chunk0, const float *__restrict__ M,
                                                             const uint4 *__restrict__ x1, const uint4 *__restrict__ x2,
-                                                            uint4 *__restrict__ out1, uint4 *__restrict__ out2, int HW) {
-  __shared__ float4 Ms[64 * 16];
-  const int b = blockIdx.y;
-  const float4 *Mb = reinterpret_cast<const float4 *>(M + (size_t)b * 4096);
-  for (int e = threadIdx.x; e < 1024; e += blockDim.x) Ms[e] = Mb[e];
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  float v[64];
-#pragma unroll
-  for (int kc = 0; kc < 8; ++kc) {
-    float t[8];
-    unpack8(__ldg(qkv + ((size_t)b * C8 + v_chunk0 + kc) * HW + p), t);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[kc * 8 + e] = t[e];
+                                                            uint4 *__restrict__ out1, uint4 *__restrict__ out2, int HW, int tiles_per_cta) {
+  __shared__ uint32_t Ms[64 * kApplyLd];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const float2 *Mb = reinterpret_cast<const float2 *>(M + (size_t)b * 4096);
+  for (int e = tid; e < 2048; e += blockDim.x) {
+    const float2 m = Mb[e];
+    Ms[(e >> 5) * kApplyLd + (e & 31)] = pack_bf2(m.x, m.y);
   }
-#pragma unroll 1
-  for (int kc = 0; kc < 8; ++kc) {
-    float o[8];
-    unpack8(__ldg(x1 + ((size_t)b * 8 + kc) * HW + p), o);
+  __syncthreads();
+  uint32_t bfr[8][4][2];            // [output-channel tile nt][k step s]: M[8 nt + g][16 s + 2 t, +1], M[8 nt + g][16 s + 8 + 2 t, +1]
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float4 *row = Ms + (kc * 8 + e) * 16;
-      float acc = 0.f;
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 m = row[j];
-        acc = fmaf(m.x, v[4 * j], acc);
-        acc = fmaf(m.y, v[4 * j + 1], acc);
-        acc = fmaf(m.z, v[4 * j + 2], acc);
-        acc = fmaf(m.w, v[4 * j + 3], acc);
-      }
-      o[e] += acc;
+    for (int sk = 0; sk < 4; ++sk) {
+      bfr[nt][sk][0] = Ms[(nt * 8 + g) * kApplyLd + 8 * sk + t];
+      bfr[nt][sk][1] = Ms[(nt * 8 + g) * kApplyLd + 8 * sk + 4 + t];
     }
-    const uint4 packed = pack8(o);
-    out1[((size_t)b * 8 + kc) * HW + p] = packed;
-    if (out2) {
-      // the second output continues from the bf16-rounded first one, exactly as a separate add kernel reading out1 would
-      float r1[8], r2[8];
-      unpack8(packed, r1);
-      unpack8(__ldg(x2 + ((size_t)b * 8 + kc) * HW + p), r2);
+  const uint32_t *vw = reinterpret_cast<const uint32_t *>(qkv + ((size_t)b * C8 + v_chunk0) * HW);     // chunk kc, pixel p, word t: (kc HW + p) 4 + t
+  const uint32_t *x1w = reinterpret_cast<const uint32_t *>(x1 + (size_t)b * 8 * HW);
+  const uint32_t *x2w = x2 ? reinterpret_cast<const uint32_t *>(x2 + (size_t)b * 8 * HW) : nullptr;
+  uint32_t *o1w = reinterpret_cast<uint32_t *>(out1 + (size_t)b * 8 * HW);
+  uint32_t *o2w = out2 ? reinterpret_cast<uint32_t *>(out2 + (size_t)b * 8 * HW) : nullptr;
+  const int tile0 = (blockIdx.x * 4 + warp) * tiles_per_cta;       // 16-pixel tiles of this warp
+  for (int tl = 0; tl < tiles_per_cta; ++tl) {
+    const int px = (tile0 + tl) * 16;
+    if (px >= HW) break;
+    const int pa = px + g, pb = px + g + 8;
+    const bool va = pa < HW, vb = pb < HW;
+    uint32_t a[4][4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r1[e] += r2[e];
-      out2[((size_t)b * 8 + kc) * HW + p] = pack8(r1);
+    for (int sk = 0; sk < 4; ++sk) {
+      a[sk][0] = va ? __ldg(vw + ((size_t)(2 * sk) * HW + pa) * 4 + t) : 0u;
+      a[sk][1] = vb ? __ldg(vw + ((size_t)(2 * sk) * HW + pb) * 4 + t) : 0u;
+      a[sk][2] = va ? __ldg(vw + ((size_t)(2 * sk + 1) * HW + pa) * 4 + t) : 0u;
+      a[sk][3] = vb ? __ldg(vw + ((size_t)(2 * sk + 1) * HW + pb) * 4 + t) : 0u;
+    }
+    uint32_t ra[8], rb[8], sa[8], sb[8];      // residual words: x1 (and x2) at (pixel pa / pb, chunk nt, word t)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      ra[nt] = va ? __ldg(x1w + ((size_t)nt * HW + pa) * 4 + t) : 0u;
+      rb[nt] = vb ? __ldg(x1w + ((size_t)nt * HW + pb) * 4 + t) : 0u;
+      sa[nt] = (x2w && va) ? __ldg(x2w + ((size_t)nt * HW + pa) * 4 + t) : 0u;
+      sb[nt] = (x2w && vb) ? __ldg(x2w + ((size_t)nt * HW + pb) * 4 + t) : 0u;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int sk = 0; sk < 4; ++sk) mma_bf16_16816(c, a[sk], bfr[nt][sk][0], bfr[nt][sk][1]);
+      // c[0..1] = (pixel pa, channels 8 nt + 2 t, + 1), c[2..3] = pixel pb
+      const uint32_t oa = pack_bf2(c[0] + __uint_as_float(ra[nt] << 16), c[1] + __uint_as_float(ra[nt] & 0xffff0000u));
+      const uint32_t ob = pack_bf2(c[2] + __uint_as_float(rb[nt] << 16), c[3] + __uint_as_float(rb[nt] & 0xffff0000u));
+      if (va) o1w[((size_t)nt * HW + pa) * 4 + t] = oa;
+      if (vb) o1w[((size_t)nt * HW + pb) * 4 + t] = ob;
+      if (o2w) {
+        // the second output continues from the bf16-rounded first one, exactly as a separate add kernel reading out1 would
+        if (va) o2w[((size_t)nt * HW + pa) * 4 + t] = pack_bf2(__uint_as_float(oa << 16) + __uint_as_float(sa[nt] << 16),
+                                                                __uint_as_float(oa & 0xffff0000u) + __uint_as_float(sa[nt] & 0xffff0000u));
+        if (vb) o2w[((size_t)nt * HW + pb) * 4 + t] = pack_bf2(__uint_as_float(ob << 16) + __uint_as_float(sb[nt] << 16),
+                                                                __uint_as_float(ob & 0xffff0000u) + __uint_as_float(sb[nt] & 0xffff0000u));
+      }
     }
   }
 }
@@ -403,7 +470,10 @@ extern "C" int cdfo_layernorm_c8_fwd(const void *x_c8, const float *gamma, const
 extern "C" int cdfo_dwconv3x3_c8_fwd(const void *x_c8, const float *w, void *y_c8, int B, int C, int H, int W, void *stream) {
   CDFO_REQUIRE(x_c8 && w && y_c8, CDFO_ERR_NULL, "cdfo_dwconv3x3_c8_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0 && C / 8 <= 65535 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_dwconv3x3_c8_fwd: bad shape");
-  fc8::dwconv3x3_c8_kernel<<<dim3(ceil_div(H * W, 128), C / 8, B), 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8, w, (uint4 *)y_c8, C / 8, H, W);
+  const int strips = ceil_div(H, fc8::kDwRows);
+  CDFO_REQUIRE((long long)(C / 8) * strips <= 65535, CDFO_ERR_SHAPE, "cdfo_dwconv3x3_c8_fwd: too many row strips");
+  fc8::dwconv3x3_c8_kernel<<<dim3(ceil_div(W, 128), (C / 8) * strips, B), 128, 0, (cudaStream_t)stream>>>((const uint4 *)x_c8, w, (uint4 *)y_c8, C / 8,
+                                                                                                           H, W, strips);
   return check_launch("cdfo_dwconv3x3_c8_fwd");
 }
 
@@ -419,7 +489,7 @@ extern "C" int cdfo_mdta_fold_fwd(const float *partial, const float *temperature
                                   void *stream) {
   CDFO_REQUIRE(partial && temperature && project_out && M, CDFO_ERR_NULL, "cdfo_mdta_fold_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && parts > 0, CDFO_ERR_SHAPE, "cdfo_mdta_fold_fwd: bad shape");
-  fc8::mdta_fold_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(partial, temperature, project_out, M, parts);
+  fc8::mdta_fold_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(partial, temperature, project_out, M, parts);
   return check_launch("cdfo_mdta_fold_fwd");
 }
 
@@ -428,8 +498,12 @@ extern "C" int cdfo_mdta_apply_c8_fwd(const void *qkv_c8, int C, int v_channel0,
   CDFO_REQUIRE(qkv_c8 && M && x1_c8 && out1_c8 && (!out2_c8 || x2_c8), CDFO_ERR_NULL, "cdfo_mdta_apply_c8_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && B <= 65535 && C % 8 == 0 && v_channel0 % 8 == 0 && v_channel0 >= 0 && v_channel0 + 64 <= C && H > 0 && W > 0,
                CDFO_ERR_SHAPE, "cdfo_mdta_apply_c8_fwd: bad shape");
-  fc8::mdta_apply_c8_kernel<<<dim3(ceil_div(H * W, 128), B), 128, 0, (cudaStream_t)stream>>>(
-      (const uint4 *)qkv_c8, C / 8, v_channel0 / 8, M, (const uint4 *)x1_c8, (const uint4 *)x2_c8, (uint4 *)out1_c8, (uint4 *)out2_c8, H * W);
+  // a warp walks `tiles` 16-pixel tiles (its 64 B-fragment registers are loaded once): about two waves of four-warp CTAs over the SMs
+  const int n_tiles = ceil_div(H * W, 16);
+  int tiles = ceil_div(n_tiles * B, 4 * 2 * 6 * kNumSMs);
+  if (tiles < 1) tiles = 1;
+  fc8::mdta_apply_c8_kernel<<<dim3(ceil_div(n_tiles, 4 * tiles), B), 128, 0, (cudaStream_t)stream>>>(
+      (const uint4 *)qkv_c8, C / 8, v_channel0 / 8, M, (const uint4 *)x1_c8, (const uint4 *)x2_c8, (uint4 *)out1_c8, (uint4 *)out2_c8, H * W, tiles);
   return check_launch("cdfo_mdta_apply_c8_fwd");
 }
 

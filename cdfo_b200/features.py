@@ -83,7 +83,7 @@ def side_branch_c8(side, s8, resid8):
     return conv.conv3x3(pad, _padded_ci(b["11"].weight), b["11"].bias, conv.ACT_LRELU, resid8=resid8)
 
 
-def self_mdta_c8(attn, n8, x1, x2=None, parts=128):
+def self_mdta_c8(attn, n8, x1, x2=None, parts=32):
     """x1 + attn(n8) [and that + x2]: qkv 1x1 -> depthwise 3x3 -> per-head Gram -> folded 64x64 matrix -> apply (arch:1545-1576)."""
     B, _, H, W, _ = n8.shape
     dev = n8.device
@@ -91,6 +91,7 @@ def self_mdta_c8(attn, n8, x1, x2=None, parts=128):
     qkv = conv.conv3x3(n8, attn.qkv.weight, None, conv.ACT_NONE)                               # 1x1, 64 -> 192: [B, 24, H, W, 8]
     dw = torch.empty_like(qkv)
     _lib.call("cdfo_dwconv3x3_c8_fwd", _lib.ptr(qkv), _lib.ptr(_f32(attn.qkv_dwconv.weight).reshape(192, 9)), _lib.ptr(dw), B, 192, H, W, st)
+    # 32 pixel ranges per (sample, head): ~16 pixels per thread, so the 80-value block reduction of the Gram kernel is amortised
     parts = max(1, min(parts, (H * W + 255) // 256))
     partial = torch.empty((B, parts, 640), dtype=torch.float32, device=dev)
     _lib.call("cdfo_mdta_gram_c8_fwd", _lib.ptr(dw), _lib.ptr(partial), B, 192, H, W, parts, st)
