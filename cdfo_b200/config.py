@@ -47,3 +47,6 @@ mdta_c8 = os.environ.get("CDFO_MDTA_C8", "1") != "0"
 # True: the down / up 1x1 convolutions of a cross-scale block are composed into body.0's 3x3 weights (they commute with the bilinear
 # resampling; the 1x1 bias becomes a border-class bias table of the 3x3 kernel's epilogue): 42 fewer launches per trunk.
 trunk_compose_1x1 = os.environ.get("CDFO_TRUNK_COMPOSE_1X1", "1") != "0"
+# True: the mask logits of LLongRangAttention start from the ONE-channel residual map (conv_expand_rms composed with conv_du_re.0 + ReLU as one
+# direct 1 -> 64 convolution) instead of reading the 64-channel prior features through a 1x1 convolution kernel.
+lra_logits_from_prior = os.environ.get("CDFO_LRA_LOGITS_FROM_PRIOR", "1") != "0"

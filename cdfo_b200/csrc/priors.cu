@@ -145,7 +145,7 @@ __global__ void unpack_c8_kernel(const uint4 *__restrict__ in, float *__restrict
 // prior map.  One thread per pixel holds its 3x3 neighbourhood in registers and writes Co channels (coalesced along the
 // pixels of each channel plane): 4 * Co bytes written per pixel, HBM-bound.
 __global__ void __launch_bounds__(128) prior_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
-                                                         const float *__restrict__ bias, float *__restrict__ y, int Co, int H, int W) {
+                                                         const float *__restrict__ bias, float *__restrict__ y, int Co, int H, int W, int relu) {
   extern __shared__ float ws[];   // [Co][9] weights + [Co] bias
   for (int e = threadIdx.x; e < Co * 9; e += blockDim.x) ws[e] = w[e];
   for (int e = threadIdx.x; e < Co; e += blockDim.x) ws[Co * 9 + e] = bias ? bias[e] : 0.f;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) prior_conv_kernel(const float *__restrict
     float acc = ws[Co * 9 + c];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc = fmaf(ws[c * 9 + k], v[k], acc);   // same tap order as a direct fp32 convolution
-    __stcs(yp + (size_t)c * HW, acc);
+    __stcs(yp + (size_t)c * HW, relu ? fmaxf(acc, 0.f) : acc);
   }
 }
 
@@ -175,11 +175,16 @@ __global__ void __launch_bounds__(128) prior_conv_kernel(const float *__restrict
 
 using namespace cdfo;
 
-extern "C" int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, void *stream) {
+extern "C" int cdfo_prior_conv_act_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, int relu,
+                                       void *stream) {
   CDFO_REQUIRE(x && w && y, CDFO_ERR_NULL, "cdfo_prior_conv_fwd: NULL pointer");
   CDFO_REQUIRE(B > 0 && B <= 65535 && Co > 0 && Co <= 1024 && H > 0 && W > 0, CDFO_ERR_SHAPE, "cdfo_prior_conv_fwd: bad shape");
-  prior_conv_kernel<<<dim3(ceil_div(H * W, 128), B), 128, (size_t)Co * 10 * 4, (cudaStream_t)stream>>>(x, w, bias, y, Co, H, W);
+  prior_conv_kernel<<<dim3(ceil_div(H * W, 128), B), 128, (size_t)Co * 10 * 4, (cudaStream_t)stream>>>(x, w, bias, y, Co, H, W, relu ? 1 : 0);
   return check_launch("cdfo_prior_conv_fwd");
+}
+
+extern "C" int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, void *stream) {
+  return cdfo_prior_conv_act_fwd(x, w, bias, y, B, Co, H, W, 0, stream);
 }
 
 extern "C" int cdfo_mv2mvs(const void *mv, int mv_is_int32, float *flows, int H, int W, void *stream) {

@@ -254,18 +254,31 @@ def _pointwise(in1, in2, weight, bias, act, mode=0, resid1=None, resid2=None):
 
 
 @torch.no_grad()
-def long_range_attention(mod, res, x, u, x2=None, out8=None, channel0=0):
+def long_range_attention(mod, res, x, u, x2=None, out8=None, channel0=0, res_prior=None):
     """LLongRangAttention.forward, arch:2179-2249, on the input x (+ x2: the model's `fea + rms_prior`, arch:4449, is formed
     inside the kernels and never written); u = uniform noise of gumbel_softmax (arch:2169).
     The 1x1 convolutions (conv_du_re.0, input_conv, fuse) are tensor-core pointwise kernels, the mask / row / column /
     window attentions csrc/lra.cu; only the stride-2 3x3 of the mask logits and its global mean are cuDNN / ATen calls.
     With out8 (contiguous bf16 c8 [B, C8, H, W, 8]) the result leaves as bf16 in its channels [channel0, channel0 + 64) instead of a
-    new fp32 tensor (the fuse kernel's epilogue packs it)."""
+    new fp32 tensor (the fuse kernel's epilogue packs it).  res_prior = (conv module, one-channel map [B, 1, H, W]) says that res IS
+    that prior convolution's output (the model: res = conv_expand_rms(rms), arch:4447): v = ReLU(conv_du_re.0(res)) is then one direct
+    1 -> 64 convolution of the one-channel map with composed weights (`res` is not read for the mask logits)."""
     B, C, H, W = x.shape
-    res, x = _f32(res), _f32(x)
+    x = _f32(x)
     x2 = None if x2 is None else _f32(x2)
     du0 = mod.conv_du_re._modules["0"]
-    v = _pointwise(res, None, du0.weight, du0.bias, act=1)
+    if res_prior is not None:
+        pc, rms1 = res_prior
+
+        def build():
+            w1 = du0.weight.detach().float().reshape(64, 64)
+            return (w1 @ pc.weight.detach().float().reshape(64, 9)).contiguous(), (w1 @ pc.bias.detach().float() + du0.bias.detach().float()).contiguous()
+        wv, bv = _module_cache(mod, "du0_after_prior", _pkey(du0.weight, du0.bias, pc.weight, pc.bias), build)
+        rms1 = _f32(rms1)
+        v = torch.empty((B, 64, H, W), dtype=torch.float32, device=x.device)
+        _lib.call("cdfo_prior_conv_act_fwd", _lib.ptr(rms1), _lib.ptr(wv), _lib.ptr(bv), _lib.ptr(v), B, 64, H, W, 1, _lib.stream_ptr(x.device))
+    else:
+        v = _pointwise(_f32(res), None, du0.weight, du0.bias, act=1)
     vmax = mask_logits(mod, v)                                                          # bilinear up of a 1x1 map = broadcast
     qv = _pointwise(x, x2, mod.input_conv.weight, mod.input_conv.bias, act=0)
     nbytes = _lib.lib().cdfo_lra_workspace_bytes(B, H, W)
@@ -327,7 +340,8 @@ def align_and_fuse(model, center, fea_nb, ufs_nb, rms_nb, mv_nb, u_nb, B):
     off = 0
     for run in runs:
         sl = slice(off, off + run.size(0))
-        long_range_attention(model.RDAB, rms_prior[sl], run, u_nb[sl], x2=rms_prior[sl], out8=cat8[sl], channel0=64)
+        long_range_attention(model.RDAB, rms_prior[sl], run, u_nb[sl], x2=rms_prior[sl], out8=cat8[sl], channel0=64,
+                             res_prior=(model.conv_expand_rms, rms_nb[sl]) if config.lra_logits_from_prior else None)
         conv.to_c8(run, out=cat8[sl], channel0=0)
         off += run.size(0)
     fr = model.conv_expand_fea_r

@@ -90,6 +90,9 @@ int cdfo_mv_end_fix(float *flows, int B, int H, int W, int i, int max_idx, void 
 /* ---- A9: prior embedding convs conv_expand_ufs / conv_expand_rms = nn.Conv2d(1, Co, 3, 1, 1) (arch/SIDECVSR_our.py:4383-4384,
  * :4446-4447).  x [B,1,H,W] fp32, w [Co,1,3,3], bias [Co] or NULL -> y [B,Co,H,W] fp32. */
 int cdfo_prior_conv_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, void *stream);
+/* Same with an optional ReLU: a 1x1 convolution + ReLU that follows the prior convolution (LLongRangAttention.conv_du_re.0 on the residual
+ * prior, arch/SIDECVSR_our.py:2183 after :4447) composes into its weights exactly (w' = W1 w, b' = W1 b + b1: the 1x1 comes after). */
+int cdfo_prior_conv_act_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Co, int H, int W, int relu, void *stream);
 
 /* ---- layout adapters: NCHW fp32 <-> "c8" = [B, C/8, H, W, 8] bf16 (C % 8 == 0). ---- */
 int cdfo_pack_c8(const float *x_nchw, void *x_c8, int B, int C, int H, int W, void *stream);

@@ -222,3 +222,26 @@ def test_lra_row_tma_equals_cp_async(cuda_dev, B, H, W):
         _lib.call("cdfo_lra_set_row_tma", 1)
     out = m.RDAB(res, x, u)
     assert torch.equal(out, ref)
+
+
+def test_lra_mask_logits_from_one_channel_prior(cuda_dev):
+    """res = conv_expand_rms(rms) (arch:4447) feeds conv_du_re.0 + ReLU (arch:2183): composed into ONE direct 1 -> 64 convolution of the
+    one-channel map (long_range_attention(res_prior=...)).  The module output must agree with the 64-channel route and with the oracle."""
+    from cdfo_b200 import hotpath
+    B, H, W = 2, 40, 56
+    m = _model(cuda_dev)
+    g = torch.Generator().manual_seed(21)
+    rms1 = torch.rand(B, 1, H, W, generator=g)
+    _, x, u = _inputs(B, H, W, seed=9)
+    sd = G.seeded_weights("O1")
+    with torch.no_grad():
+        res = torch.nn.functional.conv2d(rms1, sd["conv_expand_rms.weight"], sd["conv_expand_rms.bias"], padding=1)
+        ref = torch_ref.long_range_attention(sd, "RDAB.", res, x, u)
+    d = lambda t: t.to(cuda_dev)
+    res_d = hotpath.prior_conv(m.conv_expand_rms, d(rms1))
+    a = hotpath.long_range_attention(m.RDAB, res_d, d(x), d(u))
+    b = hotpath.long_range_attention(m.RDAB, res_d, d(x), d(u), res_prior=(m.conv_expand_rms, d(rms1)))
+    err_a, err_b = (a.cpu() - ref).abs().max().item(), (b.cpu() - ref).abs().max().item()
+    print("LRA logits from the one-channel prior: max err %.3g (64-channel route %.3g), routes differ by %.3g"
+          % (err_b, err_a, (a - b).abs().max().item()))
+    assert err_b <= 2e-3 and err_a <= 2e-3
