@@ -649,6 +649,16 @@ static int conv3x3_run(const void *x_c8, const void *wpk, const float *bias, con
     CDFO_REQUIRE(nt == 144, CDFO_ERR_UNSUPPORTED, "cdfo_mv_offset_head_dual_sm100_fwd: needs the 144-channel N tile");
     return launch_conv3x3<144, 2, 64, 3, true>(tm, p, grid, s);
   }
+  // resident weights: with room for four 23 KB halo stages the TMA latency of the next tiles hides behind the current one (a 64 -> 64
+  // convolution has ONE K block per tile, so two stages meant one tile of look-ahead)
+  const bool deep = !p.stream_w && (size_t)taps * Cin * nt * 2 + 4 * (size_t)(64 / 8) * CvGeom<3>::kPlane + 2048 <= 227 * 1024;
+  if (deep) {
+    switch (nt) {
+      case 16: return launch_conv3x3<16, 4, 64, 3>(tm, p, grid, s);
+      case 32: return launch_conv3x3<32, 4, 64, 3>(tm, p, grid, s);
+      case 64: return launch_conv3x3<64, 4, 64, 3>(tm, p, grid, s);
+    }
+  }
   switch (nt) {
     case 16: return launch_conv3x3<16, 2, 64, 3>(tm, p, grid, s);
     case 32: return launch_conv3x3<32, 2, 64, 3>(tm, p, grid, s);
