@@ -3,7 +3,7 @@ import collections
 import csv
 import sys
 
-OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::", "cpair::", "c4::", "fdcn::", "fc8::", "lml::")
+OURS = ("cdfo::", "mdta::", "rs::", "dtex::", "pw::", "feat::", "cpair::", "c4::", "fdcn::", "fc8::", "lml::", "lct::")
 
 
 def main(src, dst, title, note, marker=None, first=0, last=0):
