@@ -5,6 +5,7 @@ missing, or a call returns a non-zero status, this raises.
 """
 import ctypes
 import os
+import re
 import weakref
 
 import torch
@@ -22,6 +23,42 @@ class CdfoError(RuntimeError):
 
 
 _lib = None
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "cdfo_b200.h")
+
+
+def _ctype(decl):
+    """C parameter / return type of include/cdfo_b200.h -> ctypes type."""
+    d = decl.strip()
+    if "*" in d:
+        return ctypes.c_void_p
+    base = re.sub(r"\b(const|unsigned|signed)\b", "", d).split()
+    t = base[0] if base else "int"
+    return {"float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t, "int": ctypes.c_int, "int64_t": ctypes.c_int64,
+            "uint8_t": ctypes.c_uint8, "long": ctypes.c_long}.get(t, ctypes.c_int)
+
+
+def prototypes(header=HEADER):
+    """{name: (restype, [argtypes])} of every function include/cdfo_b200.h declares: the ctypes calls are bound to the header's own
+    prototypes, so a float passed where the ABI says int (or a 64-bit value where it says int) raises instead of being truncated."""
+    src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for ret, name, params in re.findall(r"\b(const\s+char\s*\*|size_t|int|void)\s*(cdfo_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src, flags=re.S):
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [_ctype(a) for a in params.split(",")]
+        res = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else (None if ret == "void" else ctypes.c_int))
+        out[name] = (res, args)
+    return out
+
+
+def _bind_prototypes(handle):
+    if not os.path.isfile(HEADER):
+        raise CdfoError("cdfo_b200: %s not found (the ctypes prototypes are taken from it)" % HEADER)
+    for name, (res, args) in prototypes().items():
+        fn = getattr(handle, name, None)
+        if fn is None:
+            raise CdfoError("cdfo_b200: %s declares %s but %s does not export it (stale build?)" % (HEADER, name, SO_PATH))
+        fn.restype, fn.argtypes = res, args
 
 
 def lib():
@@ -32,21 +69,13 @@ def lib():
                 "cdfo_b200: %s not found -- build it with `python cdfo_b200/csrc/build.py` "
                 "(there is no CPU or PyTorch fallback for this path)" % SO_PATH)
         _lib = ctypes.CDLL(SO_PATH)
-        _lib.cdfo_last_error.restype = ctypes.c_char_p
-        _lib.cdfo_conv3x3_sm100_weight_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_conv_sm100_weight_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_lra_workspace_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_q4t_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_mdta_workspace_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_psnr_ssim_workspace_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_conv3x3_pair_sm100_weight_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_conv4x4s2_pair_sm100_weight_bytes.restype = ctypes.c_size_t
-        _lib.cdfo_lra_mask_logits_workspace_bytes.restype = ctypes.c_size_t
+        _bind_prototypes(_lib)
     return _lib
 
 
 # number of CUDA kernels each C-ABI entry launches (for bench.py's gpu_launches claim)
-_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_lra_c8_fwd": 5, "cdfo_mdta_fwd": 3, "cdfo_psnr_ssim_u8": 3, "cdfo_lra_mask_logits_fwd": 2,
+_LAUNCHES = {"cdfo_mv_end_fix": 3, "cdfo_lra_fwd": 5, "cdfo_lra_c8_fwd": 5, "cdfo_mdta_fwd": 3, "cdfo_mdta_c8_fwd": 3, "cdfo_psnr_ssim_u8": 3,
+             "cdfo_lra_mask_logits_fwd": 2,
              "cdfo_spatial_gate_c8_fwd": 2}
 launch_count = 0
 

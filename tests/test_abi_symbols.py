@@ -55,3 +55,23 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU or PyTorch fallback" in str(e)
     else:
         raise AssertionError("expected CdfoError")
+
+
+def test_ctypes_prototypes_come_from_the_header(cdfo_so):
+    """cdfo_b200._lib binds restype / argtypes of EVERY declared entry point from include/cdfo_b200.h: no default-int conversion of a
+    pointer or float argument, a float where the ABI says int raises."""
+    import cdfo_b200._lib as L
+    protos = L.prototypes()
+    assert sorted(protos) == declared_symbols()
+    lib = L.lib()
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        assert fn.restype is res and list(fn.argtypes) == args, name
+    assert protos["cdfo_last_error"][0] is ctypes.c_char_p and protos["cdfo_mdta_workspace_bytes"][0] is ctypes.c_size_t
+    assert protos["cdfo_lra_c8_fwd"][1][6] is ctypes.c_float and protos["cdfo_dcn_fwd"][1][0] is ctypes.c_void_p
+    try:
+        lib.cdfo_mdta_workspace_bytes(1.5, 8, 8, 8)
+    except ctypes.ArgumentError:
+        pass
+    else:
+        raise AssertionError("a float passed for an int parameter must raise")
