@@ -129,28 +129,60 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 // C8 = true: x, extra, pred are c8 bf16 [B][8][HW][8] (what their producers write: conv_expand_fea_r's tcgen05 epilogue, the prior
 // convolution, the centre feature packed for the stack) and warped leaves as c8 bf16 -- a corner of the gather is ONE 16-byte load per
 // 8 channels (32 loads per pixel instead of 256 scalar ones) and the kernel moves half the bytes; arithmetic stays fp32 / TF32.
+// Warp-specialised since round 2: threads [0, 256) are LOADERS (gather + tile loads of tile i + 1 into the other shared-memory stage, the
+// warped features to global memory), threads [256, 512) are CONSUMERS (row sums, fused = Wf [warped; pred] on the tensor cores, Gram) of
+// tile i; two mbarriers per stage hand the tiles over.  One CTA per SM.  Before, every thread did both and each 64-pixel tile paid one
+// exposed global round trip plus five block barriers (4.3 us per tile and SM for 33 KB of traffic).
 template <bool C8>
-__global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsParams p) {
+__global__ void __launch_bounds__(2 * kThreads, 1) mdta_stats_kernel(const StatsParams p) {
   extern __shared__ __align__(16) float sm[];
-  float *Wt = sm;                    // [64][kLd] warped, later fused
-  float *Pt = Wt + 64 * kLd;         // [64][kLd] pred
-  float *Xt = Pt + 64 * kLd;         // [64][kLd] x (query)
-  float *Wm = Xt + 64 * kLd;         // [64][132] fusion_out weight as TF32 bits
-  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  float *Wm = sm;                    // [64][132] fusion_out weight as TF32 bits
+  float *stage0 = Wm + 64 * 132;     // 2 stages x { Wt [64][kLd] warped, later fused | Pt [64][kLd] pred | Xt [64][kLd] x (query) }
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + 2 * 3 * 64 * kLd);      // full[2] | empty[2]
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const bool loader = threadIdx.x < kThreads;
+  const int tid = threadIdx.x & (kThreads - 1);       // index inside the group
+  const int b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
   const int HW = p.H * p.W;
   const int ntiles = (HW + kTP - 1) / kTP;
   const int t0 = (int)((long long)part * ntiles / parts), t1 = (int)((long long)(part + 1) * ntiles / parts);
-  for (int e = tid; e < 64 * 128; e += kThreads) Wm[(e >> 7) * 132 + (e & 127)] = __uint_as_float(to_tf32(p.wf[e]));
+  for (int e = threadIdx.x; e < 64 * 128; e += 2 * kThreads) Wm[(e >> 7) * 132 + (e & 127)] = __uint_as_float(to_tf32(p.wf[e]));
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * i), "r"(kThreads) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto bar_wait = [&](int i, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 20000;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar0 + 8u * i), "r"(parity)
+          : "memory");
+    }
+  };
+  auto bar_arrive = [&](int i) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * i) : "memory"); };
   const float *xs = p.x + (size_t)(b % p.x_batch) * 64 * HW;
   const float *ex = p.extra + (size_t)b * 64 * HW;
   const float *pr = p.pred + (size_t)b * 64 * HW;
   float *wo = reinterpret_cast<float *>(p.warped) + (size_t)b * 64 * HW;
-  const int hc = p.hc, npairs = 64 * hc;
-  float rs = 0.f, g[4] = {0.f, 0.f, 0.f, 0.f};
+  const int hc = p.hc;
+  float rs = 0.f, gacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // Gram fragments of consumer warps 0..3
 
-  for (int tile = t0; tile < t1; ++tile) {
+  if (loader) {
+  float nflow_x = 0.f, nflow_y = 0.f;
+  if (t0 < t1 && t0 * kTP + (tid & (kTP - 1)) < HW) {
+    nflow_x = __ldg(p.flow + ((size_t)b * 2 + 0) * HW + t0 * kTP + (tid & (kTP - 1)));
+    nflow_y = __ldg(p.flow + ((size_t)b * 2 + 1) * HW + t0 * kTP + (tid & (kTP - 1)));
+  }
+  for (int tile = t0, it = 0; tile < t1; ++tile, ++it) {
     const int p0 = tile * kTP, npx = min(kTP, HW - p0);
-    __syncthreads();   // previous tile's readers are done (and Wm is complete on the first pass)
+    const int st = it & 1;
+    float *Wt = stage0 + st * 3 * 64 * kLd, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
+    bar_wait(2 + st, ((it >> 1) & 1) ^ 1);     // the consumers are done with this stage
     const bool vec = !C8 && (HW & 3) == 0;
     uint4 pq[2] = {}, xq[2] = {};
     if (C8) {    // pred and x chunks of this thread (pixel tid & 63, chunks tid >> 6 and + 4): in flight underneath the gather
@@ -179,12 +211,18 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
       const int px = tid & (kTP - 1), part = tid >> kTPShift;   // 4 parts x 16 channels
       const int pp = p0 + px;
       const bool valid = px < npx;
+      // this tile's flow was loaded one tile ago (the gather addresses depend on it: two dependent global round trips per tile otherwise)
+      const float flow_x = nflow_x, flow_y = nflow_y;
+      if (tile + 1 < t1 && pp + kTP < HW) {
+        nflow_x = __ldg(p.flow + ((size_t)b * 2 + 0) * HW + pp + kTP);
+        nflow_y = __ldg(p.flow + ((size_t)b * 2 + 1) * HW + pp + kTP);
+      }
       int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
       float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
       if (valid) {
         const int h = pp / p.W, w = pp - h * p.W;
-        const float ix = warp_src_coord(w, __ldg(p.flow + ((size_t)b * 2 + 0) * HW + pp), p.W);
-        const float iy = warp_src_coord(h, __ldg(p.flow + ((size_t)b * 2 + 1) * HW + pp), p.H);
+        const float ix = warp_src_coord(w, flow_x, p.W);
+        const float iy = warp_src_coord(h, flow_y, p.H);
         const float fx = floorf(ix), fy = floorf(iy);
         // clamp before the int conversion: +-inf / NaN flows (mv2mvs keeps x/0 = inf) must not index out of range
         const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)p.W), y0 = (int)fminf(fmaxf(fy, -2.f), (float)p.H);
@@ -279,7 +317,15 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
       }
     }
     cp_async_wait<0>();
-    __syncthreads();
+    bar_arrive(st);                            // this thread's part of the stage is written
+  }
+  return;
+  }
+  // ------------------------------------------------ consumers
+  for (int tile = t0, it = 0; tile < t1; ++tile, ++it) {
+    const int st = it & 1;
+    float *Wt = stage0 + st * 3 * 64 * kLd, *Pt = Wt + 64 * kLd, *Xt = Pt + 64 * kLd;
+    bar_wait(st, (it >> 1) & 1);
     // ---- B: row sums of warped / pred / x^2, then fused = Wf [warped; pred]
     if (tid < 192) {
       const int role = tid >> 6, c = tid & 63;
@@ -298,9 +344,9 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
     zero_frags(acc);
     tile_gemm_mma(acc, Wm, 132, Wt, 64, tid >> 5, tid & 31);
     tile_gemm_mma(acc, Wm + 64, 132, Pt, 64, tid >> 5, tid & 31);
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // every consumer warp is done reading the warped tile
     stage_frags(acc, Wt, tid >> 5, tid & 31, p.relu != 0);
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- C: sum fused^2 and the per-head Gram
     if (tid >= 192) {
       const float *row = Wt + (tid - 192) * kLd;
@@ -309,28 +355,37 @@ __global__ void __launch_bounds__(kThreads, 2) mdta_stats_kernel(const StatsPara
       for (int q = 0; q < kTP; q += 4) { const float4 v = ld4(row + q); s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
       rs += s;
     }
+    // per-head Gram x_c . fused_c' over the pixels of the tile on the tensor cores: warp rb < 4 owns the 16 x 16 block of channels
+    // [16 rb, 16 rb + 16) (one head of 16 channels, or two heads of 8 on its diagonal), K = the 64 pixels.  (As fp32 dot products from
+    // shared memory this phase alone cost 2 048 of the ~4 600 shared-memory wavefronts per tile that bound the kernel.)
+    if ((tid >> 5) < 4) {
+      const int rb = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+      const float *xa = Xt + (16 * rb + gq) * kLd + tq, *fa = Wt + (16 * rb + gq) * kLd + tq;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = tid + kThreads * j;
-      if (e < npairs) {
-        const int c = e / hc, c2 = (c / hc) * hc + (e - c * hc);
-        const float *xr = Xt + c * kLd, *fr = Wt + c2 * kLd;
-        float s = 0.f;
-#pragma unroll 8
-        for (int q = 0; q < kTP; q += 4) {
-          const float4 a = ld4(xr + q), f = ld4(fr + q);
-          s += a.x * f.x + a.y * f.y + a.z * f.z + a.w * f.w;
-        }
-        g[j] += s;
+      for (int k0 = 0; k0 < kTP; k0 += 8) {
+        const uint32_t af[4] = {to_tf32(xa[k0]), to_tf32(xa[8 * kLd + k0]), to_tf32(xa[k0 + 4]), to_tf32(xa[8 * kLd + k0 + 4])};
+        mma_tf32(gacc[0], af, to_tf32(fa[k0]), to_tf32(fa[k0 + 4]));
+        mma_tf32(gacc[1], af, to_tf32(fa[8 * kLd + k0]), to_tf32(fa[8 * kLd + k0 + 4]));
       }
     }
+    bar_arrive(2 + st);                        // the stage may be refilled
   }
   float *out = p.partial + ((size_t)b * parts + part) * stats_len(hc);
   out[tid] = rs;   // [0,64) sum warped, [64,128) sum pred, [128,192) sum x^2, [192,256) sum fused^2
+  if ((tid >> 5) < 4) {
+    // C fragments: gacc[nt][0..1] = (channel 16 rb + gq, fused channel 16 rb + 8 nt + 2 tq, + 1), gacc[nt][2..3] = channel + 8.
+    // out[256 + c * hc + j] = x_c . fused_{head(c) * hc + j}: with 8-channel heads only the diagonal 8 x 8 blocks are pairs of one head
+    const int rb = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int e = tid + kThreads * j;
-    if (e < npairs) out[256 + e] = g[j];
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int c = 16 * rb + gq + 8 * r, c2 = 16 * rb + 8 * nt + 2 * tq;
+        if (c / hc == c2 / hc) {
+          out[256 + c * hc + (c2 % hc)] = gacc[nt][2 * r];
+          out[256 + c * hc + (c2 % hc) + 1] = gacc[nt][2 * r + 1];
+        }
+      }
   }
 }
 
@@ -730,7 +785,7 @@ static int mdta_run(const void *x, int x_batch, const void *extra, const void *p
   float *warped = mats + (size_t)B * 3 * 4096;
   const int nm = mode == 1 ? 3 : 2;
   const int nstages = (mode == 0 && (H * W) % 4 == 0) ? 2 : 1;
-  const size_t smem1 = (size_t)(3 * 64 * mdta::kLd + 64 * 132) * 4;
+  const size_t smem1 = (size_t)(2 * 3 * 64 * mdta::kLd + 64 * 132) * 4 + 64;
   const size_t smem3 = (size_t)(nstages * nm * 64 * mdta::kLd + nm * 64 * 68) * 4, smem3_max = (size_t)(4 * 64 * mdta::kLd + 3 * 64 * 68) * 4;
   const size_t smem3_c8 = (size_t)(2 * 64 * mdta::kLd + 2 * 64 * 68) * 4;
   static bool attr = false;
@@ -745,8 +800,8 @@ static int mdta_run(const void *x, int x_batch, const void *extra, const void *p
     attr = true;
   }
   mdta::StatsParams sp{(const float *)x, (const float *)extra, (const float *)pred, flow, fusion_w, warped, partial, H, W, x_batch, hc, mode == 1 ? 1 : 0};
-  if (c8) mdta::mdta_stats_kernel<true><<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
-  else mdta::mdta_stats_kernel<false><<<dim3(parts, B), mdta::kThreads, smem1, s>>>(sp);
+  if (c8) mdta::mdta_stats_kernel<true><<<dim3(parts, B), 2 * mdta::kThreads, smem1, s>>>(sp);
+  else mdta::mdta_stats_kernel<false><<<dim3(parts, B), 2 * mdta::kThreads, smem1, s>>>(sp);
   mdta::AttnParams ap{partial, du_w1, du_b1, du_w2, du_b2, temperature, proj_w, mode == 1 ? fusion_w : nullptr, mats, parts, hc, HW};
   mdta::mdta_attn_kernel<<<B, 256, 0, s>>>(ap);
   mdta::ApplyParams pp{warped, pred, x, mats, out, ca_sums, H, W, B, x_batch, mode, nstages};
