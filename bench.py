@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=4, help="independent sequences resident per GPU (batched per step)")
+    ap.add_argument("--seqs", type=int, default=8, help="independent sequences resident per GPU (batched per step; 4 -> 8: +4 %% frames/s from wave quantisation and per-launch fixed costs; c4 numbers in profiles/ were taken with 4)")
     ap.add_argument("--pool", type=int, default=3, help="distinct input windows rotated through")
     ap.add_argument("--variant", default="O2", choices=["O1", "O2"])
     ap.add_argument("--priors", default="LD", choices=["LD", "RA"], help="LD (configs c3/c4) or RA = bidirectional (l0, l1) MV pairs (config c5)")
@@ -517,7 +517,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=int, default=400, help="--impl reference: wall-clock cap of the CPU run (full frames; steps / warm-ups beyond it are dropped and the line says so)")
     ap.add_argument("--cpu-baseline-budget-s", type=int, default=80, help="cap of the in-arm cpu_baseline leg (full frames, rank 0, N = 1)")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the steady-state step as a CUDA graph (+1.7 %); 0 (default): eager "
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the steady-state step as a CUDA graph (+1.7 %%); 0 (default): eager "
                     "launches, which is what lets the DCN kernel be timed live with CUDA events inside the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
