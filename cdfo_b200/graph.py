@@ -1,6 +1,6 @@
 """CUDA-graph capture of the steady-state step (one new frame per resident sequence, cached L1 features).
 
-The step is ~330 kernel launches (this library's through ctypes + a few cuDNN / ATen calls); several of them run for
+The step is ~250 kernel launches (this library's through ctypes + a few ATen copies); several of them run for
 20-40 us at the half-resolution scale of the trunk, less than the host needs to issue the next one.  Capturing the whole
 step once and replaying it removes the host from the loop (frame driver of SURVEY.md 8f rank 3).  Everything the step
 touches is static: shapes, weights (packed copies are cached per parameter version), tensor maps and the texture

@@ -1,8 +1,8 @@
 """Execution of the hot-path modules of CVSR_V8 on the device.
 
 Each function takes the parameter-holder module (cdfo_b200/model.py) plus activations and runs the path the
-reference runs at the cited lines in the hand-written kernels of libcdfo_b200; DESIGN.md section 4 lists the few
-small stages that are still a cuDNN / ATen call.  Everything is CUDA-only.
+reference runs at the cited lines in the hand-written kernels of libcdfo_b200; DESIGN.md section 4 lists the ATen
+copies that are left in a step (no cuDNN / cuBLAS launch).  Everything is CUDA-only.
 """
 import ctypes
 
@@ -258,7 +258,7 @@ def long_range_attention(mod, res, x, u, x2=None, out8=None, channel0=0, res_pri
     """LLongRangAttention.forward, arch:2179-2249, on the input x (+ x2: the model's `fea + rms_prior`, arch:4449, is formed
     inside the kernels and never written); u = uniform noise of gumbel_softmax (arch:2169).
     The 1x1 convolutions (conv_du_re.0, input_conv, fuse) are tensor-core pointwise kernels, the mask / row / column /
-    window attentions csrc/lra.cu; only the stride-2 3x3 of the mask logits and its global mean are cuDNN / ATen calls.
+    window attentions csrc/lra.cu / csrc/lra_col_sm100.cu, the mask logits csrc/lra_mask_logits.cu: every launch is this library's.
     With out8 (contiguous bf16 c8 [B, C8, H, W, 8]) the result leaves as bf16 in its channels [channel0, channel0 + 64) instead of a
     new fp32 tensor (the fuse kernel's epilogue packs it).  res_prior = (conv module, one-channel map [B, 1, H, W]) says that res IS
     that prior convolution's output (the model: res = conv_expand_rms(rms), arch:4447): v = ReLU(conv_du_re.0(res)) is then one direct
