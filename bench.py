@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=8, help="independent sequences resident per GPU (batched per step; 4 -> 8: +4 %% frames/s from wave quantisation and per-launch fixed costs; c4 numbers in profiles/ were taken with 4)")
+    ap.add_argument("--seqs", type=int, default=4, help="independent sequences resident per GPU (batched per step).  8 measured 89.2 / 85.5 HR fps on one GPU and 677 on eight against 85.6 and 699 with 4: about +4 %% per SM clock, less than the spread between power-capped boxes")
     ap.add_argument("--pool", type=int, default=3, help="distinct input windows rotated through")
     ap.add_argument("--variant", default="O2", choices=["O1", "O2"])
     ap.add_argument("--priors", default="LD", choices=["LD", "RA"], help="LD (configs c3/c4) or RA = bidirectional (l0, l1) MV pairs (config c5)")
